@@ -1,0 +1,69 @@
+"""Build libtif_b200.so (sm_100a) in-tree with nvcc.  No torch headers are involved: the library is
+plain CUDA runtime + the C ABI of include/tif_b200.h, so it cross-compiles on a box without a GPU."""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(REPO_ROOT, "include")
+BUILD_DIR = os.path.join(PKG_DIR, "build")
+LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+# translation unit -> extra flags.  The plan restates numpy float64 expressions one rounding per
+# operation, so it must not contract a*b+c into an FMA.
+UNITS = {
+    "tif_plan.cu": ["-fmad=false"],
+    "tif_exec.cu": [],
+}
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; libtif_b200.so cannot be built")
+    return exe
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_library(force=False, verbose=False):
+    """Compile every CUDA unit for sm_100a and link libtif_b200.so next to this file."""
+    headers = [os.path.join(CSRC, "tif_common.cuh"), os.path.join(INCLUDE, "tif_b200.h"), os.path.abspath(__file__)]
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    objects = []
+    rebuilt = False
+    for unit, extra in UNITS.items():
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(BUILD_DIR, unit.replace(".cu", ".o"))
+        objects.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                print(" ".join(cmd))
+                print(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed for %s" % unit)
+            rebuilt = True
+    if rebuilt or force or _stale(LIB_PATH, objects):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB_PATH] + objects + ["-lcudart"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            print(res.stdout + res.stderr)
+            raise RuntimeError("nvcc link failed")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,141 @@
+"""PyTorch custom ops (`torch.ops.tangentflow.*`) over the C ABI of libtif_b200.so.
+
+Torch is plumbing only: tensors own the device memory, `torch.cuda.current_stream()` provides the
+stream, and the ops make the kernels addressable from torch programs.  Every op takes CUDA tensors
+and launches hand-written sm_100a kernels through ctypes; there is no eager / CPU implementation
+registered, so calling one with CPU tensors raises.
+"""
+import torch
+
+from . import _geometry, _lib
+
+_registry = {}          # plan id -> Plan (custom ops cannot take Python objects)
+
+
+def register_plan(plan):
+    pid = id(plan)
+    _registry[pid] = plan
+    return pid
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.TifError("tangentflow ops need CUDA tensors (no CPU fallback)")
+
+
+_libdef = torch.library.Library("tangentflow", "DEF")
+_libdef.define("erp2ico(Tensor erp, int plan, bool full_face_image) -> Tensor")
+_libdef.define("ico2erp_flow(Tensor tangent_flow, Tensor? erp_src, Tensor? erp_tar, int plan, int blend, "
+               "bool wrap_around) -> Tensor")
+_libdef.define("warp_backward(Tensor image, Tensor flow, int mode) -> Tensor")
+_libdef.define("flow_warp_meshgrid(Tensor flow_u, Tensor flow_v) -> Tensor")
+_libdef.define("erp_of_wraparound_(Tensor(a!) erp_flow, float u_threshold) -> Tensor(a!)")
+
+
+def _erp2ico(erp, plan, full_face_image):
+    p = _registry[plan]
+    _need_cuda(erp)
+    if erp.dtype != torch.uint8 or erp.dim() != 4 or erp.shape[1:] != (p.erp_h, p.erp_w, 3):
+        raise ValueError("erp2ico expects uint8 [B,%d,%d,3], got %s %s" % (p.erp_h, p.erp_w, erp.dtype, tuple(erp.shape)))
+    erp = erp.contiguous()
+    out = torch.empty((erp.shape[0], p.tangent_pixels, 4), dtype=torch.uint8, device=erp.device)
+    with torch.cuda.device(erp.device):
+        _lib.check(p.lib.tif_erp2ico_u8(p.handle, erp.data_ptr(), erp.shape[0], int(full_face_image), out.data_ptr(),
+                                        _stream()), "tif_erp2ico_u8")
+    return out
+
+
+def _ico2erp_flow(tangent_flow, erp_src, erp_tar, plan, blend, wrap_around):
+    p = _registry[plan]
+    _need_cuda(tangent_flow, erp_src, erp_tar)
+    if tangent_flow.dtype != torch.float32 or tangent_flow.dim() != 3 or tangent_flow.shape[1:] != (p.tangent_pixels, 2):
+        raise ValueError("ico2erp_flow expects float32 [B,%d,2], got %s %s" %
+                         (p.tangent_pixels, tangent_flow.dtype, tuple(tangent_flow.shape)))
+    batch = tangent_flow.shape[0]
+    tangent_flow = tangent_flow.contiguous()
+    src_ptr = tar_ptr = scratch_ptr = None
+    scratch = None
+    if blend == _lib.BLEND_NORMWARP:
+        for name, img in (("erp_src", erp_src), ("erp_tar", erp_tar)):
+            if img is None or img.dtype != torch.uint8 or tuple(img.shape) != (batch, p.erp_h, p.erp_w, 3):
+                raise ValueError("normwarp needs uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
+        erp_src, erp_tar = erp_src.contiguous(), erp_tar.contiguous()
+        src_ptr, tar_ptr = erp_src.data_ptr(), erp_tar.data_ptr()
+        nbytes = p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend)
+        scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=tangent_flow.device)
+        scratch_ptr = scratch.data_ptr()
+    out = torch.empty((batch, p.erp_h, p.erp_w, 2), dtype=torch.float32, device=tangent_flow.device)
+    with torch.cuda.device(tangent_flow.device):
+        _lib.check(p.lib.tif_ico2erp_flow_f32(p.handle, tangent_flow.data_ptr(), src_ptr, tar_ptr, batch, int(blend),
+                                              int(wrap_around), out.data_ptr(), scratch_ptr, _stream()),
+                   "tif_ico2erp_flow_f32")
+    return out
+
+
+def _flow_dtype(flow):
+    if flow.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    if flow.dtype == torch.float64:
+        return _lib.DTYPE_F64
+    raise ValueError("flow must be float32 or float64, got %s" % flow.dtype)
+
+
+def _warp_backward(image, flow, mode):
+    _need_cuda(image, flow)
+    if image.dim() != 4 or flow.dim() != 4 or flow.shape[-1] != 2 or flow.shape[:3] != image.shape[:3]:
+        raise ValueError("warp_backward expects image [B,H,W,C] and flow [B,H,W,2]")
+    image, flow = image.contiguous(), flow.contiguous()
+    b, h, w, ch = image.shape
+    out = torch.empty_like(image)
+    lib = _lib.load()
+    with torch.cuda.device(image.device):
+        if image.dtype == torch.uint8:
+            fn, name = lib.tif_warp_backward_u8, "tif_warp_backward_u8"
+        elif image.dtype == torch.float32:
+            fn, name = lib.tif_warp_backward_f32, "tif_warp_backward_f32"
+        else:
+            raise ValueError("warp_backward image must be uint8 or float32, got %s" % image.dtype)
+        _lib.check(fn(image.data_ptr(), flow.data_ptr(), _flow_dtype(flow), b, h, w, ch, int(mode), out.data_ptr(),
+                      _stream()), name)
+    return out
+
+
+def _flow_warp_meshgrid(flow_u, flow_v):
+    _need_cuda(flow_u, flow_v)
+    if flow_u.shape != flow_v.shape or flow_u.dim() != 3 or flow_u.dtype != flow_v.dtype:
+        raise ValueError("flow_warp_meshgrid expects two [B,H,W] tensors of one dtype")
+    flow_u, flow_v = flow_u.contiguous(), flow_v.contiguous()
+    b, h, w = flow_u.shape
+    out = torch.empty((b, 2, h, w), dtype=flow_u.dtype, device=flow_u.device)
+    lib = _lib.load()
+    with torch.cuda.device(flow_u.device):
+        _lib.check(lib.tif_flow_warp_meshgrid(flow_u.data_ptr(), flow_v.data_ptr(), _flow_dtype(flow_u), b, h, w,
+                                              out.data_ptr(), _stream()), "tif_flow_warp_meshgrid")
+    return out
+
+
+def _erp_of_wraparound_(erp_flow, u_threshold):
+    _need_cuda(erp_flow)
+    if erp_flow.dim() != 4 or erp_flow.shape[-1] != 2 or not erp_flow.is_contiguous():
+        raise ValueError("erp_of_wraparound_ expects a contiguous [B,H,W,2] tensor")
+    b, h, w, _ = erp_flow.shape
+    lib = _lib.load()
+    with torch.cuda.device(erp_flow.device):
+        _lib.check(lib.tif_erp_of_wraparound(erp_flow.data_ptr(), _flow_dtype(erp_flow), b, h, w, float(u_threshold),
+                                             _stream()), "tif_erp_of_wraparound")
+    return erp_flow
+
+
+_libimpl = torch.library.Library("tangentflow", "IMPL", "CUDA")
+_libimpl.impl("erp2ico", _erp2ico)
+_libimpl.impl("ico2erp_flow", _ico2erp_flow)
+_libimpl.impl("warp_backward", _warp_backward)
+_libimpl.impl("flow_warp_meshgrid", _flow_warp_meshgrid)
+_libimpl.impl("erp_of_wraparound_", _erp_of_wraparound_)
+
+ops = torch.ops.tangentflow

@@ -1,0 +1,87 @@
+// tif_common.cuh -- shared declarations of libtif_b200.so (sm_100a).
+//
+// The library has two translation units:
+//   tif_plan.cu  geometry plan: fp64, compiled with -fmad=false so that every + - * / rounds once,
+//                exactly like the numpy expressions of the reference it restates;
+//   tif_exec.cu  per-batch execute kernels: gathers, bilinear, end-point lift, blend (HBM-bound).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "tif_b200.h"
+
+#define TIF_PI 3.141592653589793
+#define TIF_TWO_PI 6.283185307179586
+#define TIF_HALF_PI 1.5707963267948966
+
+// stage-1 table entry flag: tangent pixel lies outside the padded triangle (full_face_image=False)
+#define TIF_S1_OUTSIDE 0x80000000u
+
+// stage-2 membership entry: face<<25 | mult<<22 | iy<<11 | ix
+#define TIF_E_FACE(e) ((e) >> 25)
+#define TIF_E_MULT(e) (((e) >> 22) & 7u)
+#define TIF_E_IY(e) (((e) >> 11) & 2047u)
+#define TIF_E_IX(e) ((e) & 2047u)
+
+// fixed-point scale of the normwarp face-mean accumulation (integer sums are order-independent,
+// which keeps the blend deterministic run to run)
+#define TIF_NW_FIXED_SCALE 32768.0f
+
+struct TifPlan {
+    int n_faces, erp_h, erp_w, tangent_w;
+    int64_t tangent_pixels;        // P
+    int max_faces_per_pixel;       // K
+    int64_t accepted_unique;
+    int64_t referenced_tangent_pixels;
+    int64_t device_bytes;
+    TifFace* h_faces;              // host copy
+    TifFace* d_faces;              // [F]
+    int32_t* d_pix_face;           // [P / Wt] face of every tangent row (ragged stacks)
+    // stage 1: per tangent pixel
+    uint32_t* d_s1_base;           // [P] (y0*W + x0) | TIF_S1_OUTSIDE ; taps (x0,x0+1) x (y0,y0+1) are always in range
+    float2* d_s1_frac;             // [P] bilinear fractions (fx, fy), float32 fast path
+    double2* d_s1_frac64;          // [P] the same in float64 (exact scipy weights, rounding fallback)
+    double* d_s1_ex;               // [P] ERP sample x after sph2erp(modulo)   (parity export)
+    double* d_s1_ey;               // [P]
+    // stage 2: per ERP pixel
+    uint8_t* d_s2_count;           // [H*W] number of accepting faces
+    uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
+    double* d_col_theta;           // [W] theta of every ERP column
+    double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
+};
+
+void tif_set_error(const char* fmt, ...);
+
+#define TIF_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            tif_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return TIF_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+// np.remainder for doubles: fmod, then move into the divisor's sign (numpy npy_divmod)
+__device__ __forceinline__ double np_remainder(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if ((b < 0.0) != (m < 0.0)) m += b;
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+// scipy NI_EXTEND_WRAP coordinate map: periodic with period n-1 (ni_interpolation.c map_coordinate)
+__device__ __forceinline__ double scipy_wrap(double c, int n) {
+    if (n <= 1) return 0.0;
+    double sz = (double)(n - 1);
+    if (c < 0.0) {
+        c += sz * (double)((long long)(-c / sz) + 1);
+    } else if (c > sz) {
+        c -= sz * (double)((long long)(c / sz));
+    }
+    return c;
+}

@@ -1,0 +1,467 @@
+// tif_plan.cu -- geometry plan kernels (fp64) and plan lifetime.  COMPILE WITH -fmad=false.
+//
+// The plan is the input-independent half of the reference's two hot functions, which the reference
+// recomputes for every face of every call:
+//   stage 1  erp2ico_image   projection_icosahedron.py:197-229  tangent pixel -> ERP sample position
+//   stage 2  ico2erp_flow    projection_icosahedron.py:282-329  ERP pixel -> accepting faces + nearest tangent pixel
+// Both are evaluated once per configuration by the kernels below and kept resident in HBM.
+//
+// Bit-exactness: face membership and pixel indices are decided by float64 compares.  Every
+// transcendental those compares depend on comes from host tables evaluated by numpy (TifPlanTables),
+// and this file is compiled without FMA contraction, so each + - * / below rounds once, in the
+// reference's operation order.  Stage 1 needs sqrt/atan2/sin/cos/asin of 2-D quantities; those use
+// CUDA's fp64 libm (<= 2 ulp from numpy's), which moves a sample position by ~1e-13 px.
+#include <float.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tif_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+void tif_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int tif_abi_version(void) { return TIF_ABI_VERSION; }
+
+extern "C" const char* tif_last_error(void) { return g_last_error; }
+
+extern "C" int tif_struct_sizes(int32_t* face_bytes, int32_t* tables_bytes, int32_t* info_bytes) {
+    if (face_bytes) *face_bytes = (int32_t)sizeof(TifFace);
+    if (tables_bytes) *tables_bytes = (int32_t)sizeof(TifPlanTables);
+    if (info_bytes) *info_bytes = (int32_t)sizeof(TifPlanInfo);
+    return TIF_OK;
+}
+
+extern "C" const char* tif_status_string(int status) {
+    switch (status) {
+        case TIF_OK: return "TIF_OK";
+        case TIF_ERR_INVALID_ARG: return "TIF_ERR_INVALID_ARG";
+        case TIF_ERR_CUDA: return "TIF_ERR_CUDA";
+        case TIF_ERR_ALLOC: return "TIF_ERR_ALLOC";
+        case TIF_ERR_RANGE: return "TIF_ERR_RANGE";
+        case TIF_ERR_UNSUPPORTED: return "TIF_ERR_UNSUPPORTED";
+        default: return "TIF_ERR_UNKNOWN";
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point-in-polygon, polygon.py:59-118 with on_line=True (ray cast, inclusive y range, eps-wide edges)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pip_accept(double px, double py, const double (*tri)[2], double eps) {
+    bool inside = false, online = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double x1 = tri[k][0], y1 = tri[k][1];
+        const double x2 = tri[(k + 1) % 3][0], y2 = tri[(k + 1) % 3][1];
+        bool t = (py >= fmin(y1, y2)) && (py <= fmax(y1, y2)) && (px <= fmax(x1, x2));
+        double ix;
+        if (fabs(y1 - y2) <= eps) {
+            t = t && (px >= fmin(x1, x2));
+            ix = px;
+        } else {
+            ix = (py - y1) * (x2 - x1) / (y2 - y1) + x1;
+        }
+        online = online || (t && (fabs(px - ix) <= eps));
+        inside = inside != (t && (px <= ix));
+    }
+    return inside || online;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: one thread per tangent pixel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row_face,
+              const double* __restrict__ gnom_x, const double* __restrict__ gnom_y,
+              int erp_h, int erp_w, int tangent_w, int64_t n_pix,
+              uint32_t* __restrict__ s1_base, float2* __restrict__ s1_frac, double2* __restrict__ s1_frac64,
+              double* __restrict__ s1_ex, double* __restrict__ s1_ey) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    const int64_t grow = p / tangent_w;          // row in the concatenated stack
+    const int j = (int)(p - grow * tangent_w);
+    const int f = row_face[grow];
+    const TifFace& F = faces[f];
+    const double x = gnom_x[(int64_t)f * tangent_w + j];
+    const double y = gnom_y[grow];
+
+    // reverse_gnomonic_projection, gnomonic_projection.py:76-93
+    double rho = sqrt(x * x + y * y);
+    const bool zero = (rho == 0.0);
+    if (zero) rho = DBL_EPSILON;
+    const double c = atan2(rho, 1.0);
+    double sc, cc;
+    sincos(c, &sc, &cc);
+    double phi = asin(cc * F.sin_phi0 + (y * sc * F.cos_phi0) / rho);
+    double theta = F.theta0 + atan2(x * sc, rho * F.cos_phi0 * cc - y * F.sin_phi0 * sc);
+    if (zero) {
+        phi = F.phi0;
+        theta = F.theta0;
+    }
+    // sph2erp(sph_modulo=True), spherical_coordinates.py:59-60,122-124
+    theta = np_remainder(theta + TIF_PI, 2 * TIF_PI) - TIF_PI;
+    phi = -(np_remainder(-phi + 0.5 * TIF_PI, TIF_PI) - 0.5 * TIF_PI);
+    const double ex = (theta + TIF_PI) / (2.0 * TIF_PI / erp_w) - 0.5;
+    const double ey = (-phi + 0.5 * TIF_PI) / (TIF_PI / erp_h) - 0.5;
+    s1_ex[p] = ex;
+    s1_ey[p] = ey;
+
+    // scipy map_coordinates(order=1, mode='wrap'): period n-1, taps floor(c), floor(c)+1.
+    // The base tap is clamped to n-2 (fraction 1.0 when c == n-1 exactly) so both taps are always
+    // in range; the product with scipy's zero weight is unchanged.
+    const double cx = scipy_wrap(ex, erp_w);
+    const double cy = scipy_wrap(ey, erp_h);
+    double x0 = floor(cx), y0 = floor(cy);
+    if (x0 > (double)(erp_w - 2)) x0 = (double)(erp_w - 2);
+    if (y0 > (double)(erp_h - 2)) y0 = (double)(erp_h - 2);
+    if (x0 < 0.0) x0 = 0.0;
+    if (y0 < 0.0) y0 = 0.0;
+    const double fx = cx - x0, fy = cy - y0;
+    uint32_t base = (uint32_t)((int64_t)y0 * erp_w + (int64_t)x0);
+    if (!pip_accept(x, y, F.tri, F.eps_image)) base |= TIF_S1_OUTSIDE;
+    s1_base[p] = base;
+    s1_frac[p] = make_float2((float)fx, (float)fy);
+    s1_frac64[p] = make_double2(fx, fy);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: one thread per ERP pixel, faces visited in index order ("pull" form)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floor_div(int a, int b) {   // b > 0
+    int q = a / b, r = a % b;
+    return (r != 0 && r < 0) ? q - 1 : q;
+}
+
+// number of integers k in [start, stop] with k mod n == v  (0 <= v < n): multiplicity of a wrapped
+// candidate row / column after flow_postproc.erp_pixles_modulo (flow_postproc.py:12-13)
+__device__ __forceinline__ int wrapped_multiplicity(int start, int stop, int v, int n) {
+    if (stop < start) return 0;
+    return floor_div(stop - v, n) - floor_div(start - 1 - v, n);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp_w, int tangent_w,
+              const double* __restrict__ row_sincos, const double* __restrict__ col_sincos,
+              uint8_t* __restrict__ count, uint32_t* __restrict__ entries, int max_k,
+              uint8_t* __restrict__ ref_mark, unsigned long long* __restrict__ face_mult_sum,
+              int* __restrict__ status /* [0]=max count, [1]=range errors */) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_pix = (int64_t)erp_h * erp_w;
+    if (pix >= n_pix) return;
+    const int r = (int)(pix / erp_w);
+    const int c = (int)(pix - (int64_t)r * erp_w);
+    const double sin_phi = row_sincos[2 * r], cos_phi = row_sincos[2 * r + 1];
+    int n = 0;
+    for (int f = 0; f < n_faces; ++f) {
+        const TifFace& F = faces[f];
+        const int mr = wrapped_multiplicity(F.row_start, F.row_stop, r, erp_h);
+        if (mr == 0) continue;
+        const int mc = wrapped_multiplicity(F.col_start, F.col_stop, c, erp_w);
+        if (mc == 0) continue;
+        const double sin_d = col_sincos[2 * ((int64_t)f * erp_w + c)];
+        const double cos_d = col_sincos[2 * ((int64_t)f * erp_w + c) + 1];
+        // gnomonic_projection, gnomonic_projection.py:36-49 (hemisphere mask discarded by the caller)
+        double cos_c = F.sin_phi0 * sin_phi + F.cos_phi0 * cos_phi * cos_d;
+        double x, y;
+        if (cos_c == 0.0) {
+            x = 0.0;
+            y = 0.0;
+        } else {
+            x = cos_phi * sin_d / cos_c;
+            y = (F.cos_phi0 * sin_phi - F.sin_phi0 * cos_phi * cos_d) / cos_c;
+        }
+        if (!pip_accept(x, y, F.tri, F.eps_stitch)) continue;
+        if (FILL) {
+            // gnomonic2pixel, gnomonic_projection.py:141-147 (padding_size 0.0, padded range)
+            const double fx = (x - F.xmin + 0.0) * F.g2p_x + 0.5;
+            const double fy = -(y - F.ymax - 0.0) * F.g2p_y + 0.5;
+            int ix = (int)fx, iy = (int)fy;          // astype(int): truncation toward zero
+            const int m = mr * mc;
+            if (ix < 0 || ix >= tangent_w || iy < 0 || iy >= F.tangent_h || m > 7) {
+                atomicAdd(&status[1], 1);
+                ix = min(max(ix, 0), tangent_w - 1);
+                iy = min(max(iy, 0), F.tangent_h - 1);
+            }
+            if (n < max_k)
+                entries[(int64_t)n * n_pix + pix] =
+                    ((uint32_t)f << 25) | ((uint32_t)min(m, 7) << 22) | ((uint32_t)iy << 11) | (uint32_t)ix;
+            ref_mark[(int64_t)F.pix_offset + (int64_t)iy * tangent_w + ix] = 1;
+            atomicAdd(&face_mult_sum[f], (unsigned long long)m);
+        }
+        ++n;
+    }
+    if (FILL) {
+        count[pix] = (uint8_t)min(n, max_k);
+    } else {
+        if (n > 0) atomicMax(&status[0], n);
+    }
+}
+
+__global__ void k_count_marks(const uint8_t* __restrict__ mark, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        local += mark[i];
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan lifetime
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(T** p, size_t n, TifPlan* plan) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        tif_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        *p = nullptr;
+        return TIF_ERR_ALLOC;
+    }
+    plan->device_bytes += (int64_t)(n * sizeof(T));
+    return TIF_OK;
+}
+
+extern "C" int tif_plan_destroy(TifPlan* plan) {
+    if (!plan) return TIF_OK;
+    cudaFree(plan->d_faces);
+    cudaFree(plan->d_pix_face);
+    cudaFree(plan->d_s1_base);
+    cudaFree(plan->d_s1_frac);
+    cudaFree(plan->d_s1_frac64);
+    cudaFree(plan->d_s1_ex);
+    cudaFree(plan->d_s1_ey);
+    cudaFree(plan->d_s2_count);
+    cudaFree(plan->d_s2_entries);
+    cudaFree(plan->d_col_theta);
+    cudaFree(plan->d_face_mult_sum);
+    free(plan->h_faces);
+    free(plan);
+    return TIF_OK;
+}
+
+#define PLAN_TRY(expr)              \
+    do {                            \
+        int _s = (expr);            \
+        if (_s != TIF_OK) {         \
+            tif_plan_destroy(plan); \
+            cudaFree(d_gx);         \
+            cudaFree(d_gy);         \
+            cudaFree(d_rows);       \
+            cudaFree(d_cols);       \
+            cudaFree(d_mark);       \
+            cudaFree(d_status);     \
+            cudaFree(d_msum);       \
+            return _s;              \
+        }                           \
+    } while (0)
+
+static int cuda_status(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return TIF_OK;
+    tif_set_error("%s failed: %s", what, cudaGetErrorString(e));
+    return TIF_ERR_CUDA;
+}
+
+extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int erp_w, int tangent_w,
+                               const TifPlanTables* tables, void* stream_v, TifPlan** plan_out) {
+    if (!faces || !tables || !plan_out || n_faces <= 0 || n_faces > TIF_MAX_FACES || erp_h < 2 || erp_w < 2 ||
+        tangent_w < 2 || tangent_w > TIF_MAX_TANGENT_DIM || !tables->gnom_x || !tables->gnom_y ||
+        !tables->row_sincos || !tables->col_sincos || !tables->col_theta) {
+        tif_set_error("tif_plan_create: invalid argument");
+        return TIF_ERR_INVALID_ARG;
+    }
+    if ((int64_t)erp_h * erp_w >= (int64_t)1 << 31) {
+        tif_set_error("tif_plan_create: ERP larger than 2^31 pixels");
+        return TIF_ERR_UNSUPPORTED;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int64_t n_tangent = 0;
+    for (int f = 0; f < n_faces; ++f) {
+        if (faces[f].tangent_h < 2 || faces[f].tangent_h > TIF_MAX_TANGENT_DIM ||
+            faces[f].pix_offset != n_tangent) {
+            tif_set_error("tif_plan_create: face %d has tangent_h %d / pix_offset %d (expected offset %lld)", f,
+                          faces[f].tangent_h, faces[f].pix_offset, (long long)n_tangent);
+            return TIF_ERR_INVALID_ARG;
+        }
+        n_tangent += (int64_t)faces[f].tangent_h * tangent_w;
+    }
+    if (n_tangent >= (int64_t)1 << 31) {
+        tif_set_error("tif_plan_create: tangent stack larger than 2^31 pixels");
+        return TIF_ERR_UNSUPPORTED;
+    }
+    const int64_t n_rows = n_tangent / tangent_w;
+    const int64_t n_erp = (int64_t)erp_h * erp_w;
+
+    TifPlan* plan = (TifPlan*)calloc(1, sizeof(TifPlan));
+    if (!plan) return TIF_ERR_ALLOC;
+    plan->n_faces = n_faces;
+    plan->erp_h = erp_h;
+    plan->erp_w = erp_w;
+    plan->tangent_w = tangent_w;
+    plan->tangent_pixels = n_tangent;
+    plan->h_faces = (TifFace*)malloc(sizeof(TifFace) * n_faces);
+    memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
+
+    double *d_gx = nullptr, *d_gy = nullptr, *d_rows = nullptr, *d_cols = nullptr;
+    uint8_t* d_mark = nullptr;
+    int* d_status = nullptr;
+    unsigned long long* d_msum = nullptr;
+
+    int32_t* h_row_face = (int32_t*)malloc(sizeof(int32_t) * n_rows);
+    {
+        int64_t row = 0;
+        for (int f = 0; f < n_faces; ++f)
+            for (int i = 0; i < faces[f].tangent_h; ++i) h_row_face[row++] = f;
+    }
+
+    PLAN_TRY(dev_alloc(&plan->d_faces, n_faces, plan));
+    PLAN_TRY(dev_alloc(&plan->d_pix_face, n_rows, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s1_base, n_tangent, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s1_frac, n_tangent, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s1_frac64, n_tangent, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s1_ex, n_tangent, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s1_ey, n_tangent, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s2_count, n_erp, plan));
+    PLAN_TRY(dev_alloc(&plan->d_col_theta, erp_w, plan));
+    PLAN_TRY(dev_alloc(&plan->d_face_mult_sum, n_faces, plan));
+    int64_t scratch_bytes = 0;
+    {
+        TifPlan tmp;   // scratch is not part of the plan footprint
+        tmp.device_bytes = 0;
+        PLAN_TRY(dev_alloc(&d_gx, (size_t)n_faces * tangent_w, &tmp));
+        PLAN_TRY(dev_alloc(&d_gy, n_rows, &tmp));
+        PLAN_TRY(dev_alloc(&d_rows, (size_t)erp_h * 2, &tmp));
+        PLAN_TRY(dev_alloc(&d_cols, (size_t)n_faces * erp_w * 2, &tmp));
+        PLAN_TRY(dev_alloc(&d_mark, n_tangent, &tmp));
+        PLAN_TRY(dev_alloc(&d_status, 2, &tmp));
+        PLAN_TRY(dev_alloc(&d_msum, n_faces + 1, &tmp));
+        scratch_bytes = tmp.device_bytes;
+    }
+    (void)scratch_bytes;
+
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_faces, faces, sizeof(TifFace) * n_faces, cudaMemcpyHostToDevice, stream), "copy faces"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_pix_face, h_row_face, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, stream), "copy row->face"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gx, tables->gnom_x, sizeof(double) * n_faces * tangent_w, cudaMemcpyHostToDevice, stream), "copy gnom_x"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gy, tables->gnom_y, sizeof(double) * n_rows, cudaMemcpyHostToDevice, stream), "copy gnom_y"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_rows, tables->row_sincos, sizeof(double) * erp_h * 2, cudaMemcpyHostToDevice, stream), "copy row table"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_cols, tables->col_sincos, sizeof(double) * n_faces * erp_w * 2, cudaMemcpyHostToDevice, stream), "copy column table"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_col_theta, tables->col_theta, sizeof(double) * erp_w, cudaMemcpyHostToDevice, stream), "copy column theta"));
+    PLAN_TRY(cuda_status(cudaMemsetAsync(d_mark, 0, n_tangent, stream), "memset"));
+    PLAN_TRY(cuda_status(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), stream), "memset"));
+    PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, (n_faces + 1) * sizeof(unsigned long long), stream), "memset"));
+    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan upload"));   // h_row_face is pageable
+    free(h_row_face);
+
+    const int threads = 256;
+    k_plan_stage1<<<(unsigned)((n_tangent + threads - 1) / threads), threads, 0, stream>>>(
+        plan->d_faces, plan->d_pix_face, d_gx, d_gy, erp_h, erp_w, tangent_w, n_tangent, plan->d_s1_base,
+        plan->d_s1_frac, plan->d_s1_frac64, plan->d_s1_ex, plan->d_s1_ey);
+    PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage1 launch"));
+
+    const unsigned blocks2 = (unsigned)((n_erp + threads - 1) / threads);
+    k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
+                                                         d_cols, nullptr, nullptr, 0, nullptr, nullptr, d_status);
+    PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<count> launch"));
+    int h_status[2] = {0, 0};
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, stream), "read max count"));
+    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan stage 2 count"));
+    plan->max_faces_per_pixel = h_status[0] > 0 ? h_status[0] : 1;
+    if (plan->max_faces_per_pixel > 255) {
+        tif_set_error("tif_plan_create: %d faces cover one pixel (max 255)", plan->max_faces_per_pixel);
+        PLAN_TRY(TIF_ERR_RANGE);
+    }
+    PLAN_TRY(dev_alloc(&plan->d_s2_entries, (size_t)plan->max_faces_per_pixel * n_erp, plan));
+    k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
+                                                        d_cols, plan->d_s2_count, plan->d_s2_entries,
+                                                        plan->max_faces_per_pixel, d_mark, d_msum, d_status);
+    PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<fill> launch"));
+    k_count_marks<<<1024, 256, 0, stream>>>(d_mark, n_tangent, d_msum + n_faces);
+    PLAN_TRY(cuda_status(cudaGetLastError(), "k_count_marks launch"));
+    unsigned long long* h_msum = (unsigned long long*)malloc(sizeof(unsigned long long) * (n_faces + 1));
+    cudaError_t e1 = cudaMemcpyAsync(h_msum, d_msum, sizeof(unsigned long long) * (n_faces + 1), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e2 = cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e3 = cudaStreamSynchronize(stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        free(h_msum);
+        PLAN_TRY(cuda_status(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "plan stage 2 fill"));
+    }
+    double* h_fm = (double*)malloc(sizeof(double) * n_faces);
+    for (int f = 0; f < n_faces; ++f) h_fm[f] = (double)h_msum[f];
+    plan->referenced_tangent_pixels = (int64_t)h_msum[n_faces];
+    free(h_msum);
+    e1 = cudaMemcpy(plan->d_face_mult_sum, h_fm, sizeof(double) * n_faces, cudaMemcpyHostToDevice);
+    free(h_fm);
+    PLAN_TRY(cuda_status(e1, "copy face multiplicity sums"));
+    if (h_status[1] != 0) {
+        tif_set_error("tif_plan_create: %d membership entries out of range (tangent index outside the face or multiplicity > 7)", h_status[1]);
+        PLAN_TRY(TIF_ERR_RANGE);
+    }
+    // accepted_unique = sum of per-pixel counts; computed from the mark pass' sibling: reuse k_count_marks
+    PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, sizeof(unsigned long long), stream), "memset"));
+    k_count_marks<<<1024, 256, 0, stream>>>(plan->d_s2_count, n_erp, d_msum);
+    unsigned long long h_acc = 0;
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(&h_acc, d_msum, sizeof(h_acc), cudaMemcpyDeviceToHost, stream), "read accepted"));
+    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan finish"));
+    plan->accepted_unique = (int64_t)h_acc;
+
+    cudaFree(d_gx);
+    cudaFree(d_gy);
+    cudaFree(d_rows);
+    cudaFree(d_cols);
+    cudaFree(d_mark);
+    cudaFree(d_status);
+    cudaFree(d_msum);
+    *plan_out = plan;
+    return TIF_OK;
+}
+
+extern "C" int tif_plan_info(const TifPlan* plan, TifPlanInfo* info) {
+    if (!plan || !info) return TIF_ERR_INVALID_ARG;
+    info->n_faces = plan->n_faces;
+    info->erp_h = plan->erp_h;
+    info->erp_w = plan->erp_w;
+    info->tangent_w = plan->tangent_w;
+    info->tangent_pixels = plan->tangent_pixels;
+    info->max_faces_per_pixel = plan->max_faces_per_pixel;
+    info->accepted_unique = plan->accepted_unique;
+    info->referenced_tangent_pixels = plan->referenced_tangent_pixels;
+    info->device_bytes = plan->device_bytes;
+    return TIF_OK;
+}
+
+__global__ void k_export_inside(const uint32_t* __restrict__ base, int64_t n, uint8_t* __restrict__ inside) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) inside[p] = (base[p] & TIF_S1_OUTSIDE) ? 0 : 1;
+}
+
+extern "C" int tif_plan_export_stage1(const TifPlan* plan, double* erp_x, double* erp_y, uint8_t* inside, void* stream_v) {
+    if (!plan) return TIF_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int64_t n = plan->tangent_pixels;
+    if (erp_x) TIF_CUDA_CHECK(cudaMemcpyAsync(erp_x, plan->d_s1_ex, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (erp_y) TIF_CUDA_CHECK(cudaMemcpyAsync(erp_y, plan->d_s1_ey, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (inside) {
+        k_export_inside<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan->d_s1_base, n, inside);
+        TIF_CUDA_CHECK(cudaGetLastError());
+    }
+    return TIF_OK;
+}
+
+extern "C" int tif_plan_export_stage2(const TifPlan* plan, uint8_t* count, uint32_t* entries, void* stream_v) {
+    if (!plan) return TIF_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int64_t n = (int64_t)plan->erp_h * plan->erp_w;
+    if (count) TIF_CUDA_CHECK(cudaMemcpyAsync(count, plan->d_s2_count, n, cudaMemcpyDeviceToDevice, stream));
+    if (entries)
+        TIF_CUDA_CHECK(cudaMemcpyAsync(entries, plan->d_s2_entries, (size_t)plan->max_faces_per_pixel * n * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToDevice, stream));
+    return TIF_OK;
+}

@@ -1,0 +1,62 @@
+"""Drop-in replacement of the hot functions of the reference's src/flow_warp.py.
+
+    flow_warp_meshgrid(motion_flow_u, motion_flow_v)   -> [2,H,W]
+    warp_backward(image_target, of_forward)            -> image like image_target
+
+numpy in -> numpy out with the reference's dtypes; torch CUDA tensors with a leading batch axis stay
+on the device.  The rotation-estimation functions of the reference (flow2rotation_*,
+global_rotation_warping) are out of scope.
+"""
+import numpy as np
+import torch
+
+from . import _lib, _ops
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.TifError("no CUDA device: flow_warp has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def flow_warp_meshgrid(motion_flow_u, motion_flow_v):
+    """End points of the flow on the pixel grid with a single wrap (src/flow_warp.py:15-51)."""
+    if isinstance(motion_flow_u, torch.Tensor):
+        return _ops.ops.flow_warp_meshgrid(motion_flow_u, motion_flow_v)
+    u = np.ascontiguousarray(motion_flow_u, dtype=np.float64)
+    v = np.ascontiguousarray(motion_flow_v, dtype=np.float64)
+    if u.shape != v.shape:
+        raise ValueError("motion flow u shape %s is not equal motion flow v shape %s" % (u.shape, v.shape))
+    dev = _device()
+    out = _ops.ops.flow_warp_meshgrid(torch.from_numpy(u).to(dev)[None], torch.from_numpy(v).to(dev)[None])
+    return out[0].cpu().numpy()
+
+
+def warp_backward(image_target, of_forward):
+    """Backward warp: out(y,x) = bilinear(image_target, (y+v, x+u)) (src/flow_warp.py:54-88).
+
+    [H,W,C] images use scipy's mode='wrap' (period n-1), [H,W] images mode='constant' with 255;
+    uint8 images are rounded half-up.  float64 images are computed in float64 on the device side of the
+    bilinear (float32 storage), other float images likewise.
+    """
+    if isinstance(image_target, torch.Tensor):
+        mode = _lib.WARP_WRAP
+        return _ops.ops.warp_backward(image_target, of_forward, mode)
+    image_target = np.asarray(image_target)
+    flow = np.ascontiguousarray(of_forward)
+    if flow.dtype not in (np.float32, np.float64):
+        flow = flow.astype(np.float64)
+    if image_target.ndim == 3:
+        mode, img = _lib.WARP_WRAP, image_target
+    elif image_target.ndim == 2:
+        mode, img = _lib.WARP_CONSTANT255, image_target[:, :, None]
+    else:
+        raise ValueError("The image shape is %s, do not support." % (image_target.shape,))
+    dev = _device()
+    if img.dtype == np.uint8:
+        img_dev = torch.from_numpy(np.ascontiguousarray(img)).to(dev)[None]
+    else:
+        img_dev = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)[None]
+    out = _ops.ops.warp_backward(img_dev, torch.from_numpy(flow).to(dev)[None], mode)[0].cpu().numpy()
+    out = out.astype(image_target.dtype, copy=False)
+    return out if image_target.ndim == 3 else out[:, :, 0]

@@ -1,0 +1,106 @@
+"""Drop-in replacement of the reference's src/projection_icosahedron.py hot functions.
+
+Same names, argument meaning and return types as the reference:
+
+    get_icosahedron_parameters(triangle_index, padding_size=0.0)
+    erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_image=True)
+    ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, image_erp_src=None,
+                 image_erp_tar=None, wrap_around=False, face_blending_method="straightforward")
+
+numpy in -> numpy out exactly like the reference (list of 20 int64 [Ht,Wt,4] images; float64 [H,W,2]
+flow).  Torch CUDA tensors with a leading batch axis go straight through and stay on the device:
+erp2ico_image([B,H,W,3] uint8) -> [B,20,Ht,Wt,4] uint8, ico2erp_flow([B,20,Ht,Wt,2] float32) ->
+[B,H,W,2] float32.  All per-pixel work runs in libtif_b200.so; there is no CPU fallback.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import _geometry, _lib, _ops
+from ._geometry import get_icosahedron_parameters, tangent_image_height  # noqa: F401  (reference API)
+
+log = logging.getLogger(__name__)
+
+_BLENDS = {"straightforward": _lib.BLEND_STRAIGHTFORWARD, "normwarp": _lib.BLEND_NORMWARP}
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.TifError("no CUDA device: the tangent-image hot path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_image=True):
+    """Project an ERP image to the 20 padded tangent images (src/projection_icosahedron.py:163-248)."""
+    if isinstance(erp_image, torch.Tensor):
+        if erp_image.dim() != 4:
+            raise ValueError("torch input must be [B,H,W,3] uint8")
+        if erp_image.shape[-1] == 4:
+            erp_image = erp_image[..., 0:3]
+        plan = _geometry.get_plan(padding_size, erp_image.shape[1], tangent_image_width, erp_image.device)
+        out = _ops.ops.erp2ico(erp_image, _ops.register_plan(plan), bool(full_face_image))
+        return out.view(erp_image.shape[0], plan.n_faces, plan.tangent_h, plan.tangent_w, 4)
+
+    erp_image = np.asarray(erp_image)
+    if erp_image.ndim == 3 and erp_image.shape[2] == 4:
+        erp_image = erp_image[:, :, 0:3]
+    if erp_image.ndim != 3 or erp_image.shape[2] != 3 or erp_image.dtype != np.uint8:
+        raise NotImplementedError("erp2ico_image: only uint8 [H,W,3|4] images are on the accelerated path "
+                                  "(got %s %s)" % (erp_image.dtype, erp_image.shape))
+    if erp_image.shape[1] != erp_image.shape[0] * 2:
+        log.error("the ERP image dimession is %s", np.shape(erp_image))     # the reference logs and continues
+        raise ValueError("ERP image must be 2:1, got %s" % (erp_image.shape,))
+    dev = _device()
+    plan = _geometry.get_plan(padding_size, erp_image.shape[0], tangent_image_width, dev)
+    erp_dev = torch.from_numpy(np.ascontiguousarray(erp_image)).to(dev)[None]
+    out = _ops.ops.erp2ico(erp_dev, _ops.register_plan(plan), bool(full_face_image))
+    stack = out.view(plan.n_faces, plan.tangent_h, plan.tangent_w, 4).cpu().numpy()
+    # the reference builds its images with np.full(..., 255): int64, 4 channels
+    return [stack[f].astype(np.int64) for f in range(plan.n_faces)]
+
+
+def ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, image_erp_src=None, image_erp_tar=None,
+                 wrap_around=False, face_blending_method="straightforward"):
+    """Stitch the 20 tangent flows into an ERP flow (src/projection_icosahedron.py:251-398)."""
+    if face_blending_method not in _BLENDS:
+        # the reference falls through to an UnboundLocalError on face_weight_mat
+        raise UnboundLocalError("face_blending_method %r is not 'straightforward' or 'normwarp'" % (face_blending_method,))
+    blend = _BLENDS[face_blending_method]
+
+    if isinstance(tangent_flows_list, torch.Tensor):
+        flows = tangent_flows_list
+        if flows.dim() != 5 or flows.shape[-1] != 2:
+            raise ValueError("torch input must be [B,20,Ht,Wt,2] float32")
+        batch, n_faces, ht, wt = flows.shape[:4]
+        erp_h = int(ht * 2.0) if erp_flow_height is None else int(erp_flow_height)
+        plan = _geometry.get_plan(padding_size, erp_h, wt, flows.device)
+        if n_faces != plan.n_faces or ht != plan.tangent_h:
+            raise ValueError("expected [B,%d,%d,%d,2] tangent flows" % (plan.n_faces, plan.tangent_h, plan.tangent_w))
+        return _ops.ops.ico2erp_flow(flows.reshape(batch, plan.tangent_pixels, 2), image_erp_src, image_erp_tar,
+                                     _ops.register_plan(plan), blend, bool(wrap_around))
+
+    if len(tangent_flows_list) != 20:
+        log.error("the ico face flow number is not 20")
+        raise ValueError("the ico face flow number is not 20")
+    ht, wt = np.shape(tangent_flows_list[0])[:2]
+    if np.shape(tangent_flows_list[0])[2] != 2:
+        log.error("The flow channels number is %s", np.shape(tangent_flows_list[0])[2])
+        raise ValueError("tangent flows must have 2 channels")
+    erp_h = int(ht * 2.0) if erp_flow_height is None else int(erp_flow_height)
+    dev = _device()
+    plan = _geometry.get_plan(padding_size, erp_h, wt, dev)
+    flows = np.stack([np.asarray(f, dtype=np.float32) for f in tangent_flows_list])
+    flows_dev = torch.from_numpy(flows).to(dev).reshape(1, plan.tangent_pixels, 2)
+    src_dev = tar_dev = None
+    if blend == _lib.BLEND_NORMWARP:
+        imgs = []
+        for img in (image_erp_src, image_erp_tar):
+            img = np.asarray(img)
+            if img.dtype != np.uint8 or img.shape != (plan.erp_h, plan.erp_w, 3):
+                raise NotImplementedError("normwarp blending needs uint8 [H,W,3] ERP images of the flow's size "
+                                          "(got %s %s)" % (img.dtype, img.shape))
+            imgs.append(torch.from_numpy(np.ascontiguousarray(img)).to(dev)[None])
+        src_dev, tar_dev = imgs
+    out = _ops.ops.ico2erp_flow(flows_dev, src_dev, tar_dev, _ops.register_plan(plan), blend, bool(wrap_around))
+    return out[0].cpu().numpy().astype(np.float64)

@@ -1,0 +1,180 @@
+/*
+ * tif_b200.h -- C ABI of the B200-native tangent-image hot path (libtif_b200.so).
+ *
+ * The reference (yuanmingze/360OpticalFlow-TangentImages) is pure Python and has no FFI / plugin
+ * boundary of its own: the drop-in boundary is the Python call surface of
+ * src/projection_icosahedron.py, src/flow_warp.py and src/flow_postproc.py.  Every entry point
+ * below names the reference function it replaces (file:line relative to /root/reference/src); the
+ * Python modules in 360opticalflow-tangentimages_b200/ keep those functions' names and argument
+ * meaning and call these symbols through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in any signature.
+ *   - All data pointers are DEVICE pointers unless the parameter is documented as host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Execute calls are
+ *     asynchronous on that stream and never synchronise the host; plan creation does synchronise
+ *     (it sizes its tables from a device-side count).
+ *   - Caller allocates every output; nothing is retained except inside a TifPlan.
+ *   - Return value: TIF_OK (0) or a negative TifStatus.  tif_status_string() names it,
+ *     tif_last_error() gives the thread's last detailed message.
+ *   - There is no CPU fallback anywhere: without a CUDA device every call fails with TIF_ERR_CUDA.
+ *
+ * Layouts
+ *   ERP image        uint8  [B, H, W, 3]      interleaved RGB, W == 2H
+ *   tangent stack    uint8  [B, P, 4]         RGBA; P = sum_f Ht_f * Wt; face f starts at pixel
+ *                                             faces[f].pix_offset and is row-major [Ht_f, Wt]
+ *                                             (for the 20-face icosahedron: [B, 20, Ht, Wt, 4])
+ *   tangent flows    float32 [B, P, 2]        (u, v) in tangent pixels, same face order
+ *   ERP flow         float32 [B, H, W, 2]     (u, v) in ERP pixels
+ */
+#ifndef TIF_B200_H
+#define TIF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIF_ABI_VERSION 1
+#define TIF_MAX_FACES 128      /* 7-bit face id in a membership entry */
+#define TIF_MAX_TANGENT_DIM 2048 /* 11-bit tangent row / column in a membership entry */
+
+typedef enum TifStatus {
+    TIF_OK = 0,
+    TIF_ERR_INVALID_ARG = -1,
+    TIF_ERR_CUDA = -2,          /* CUDA runtime error (including "no device") */
+    TIF_ERR_ALLOC = -3,
+    TIF_ERR_RANGE = -4,         /* plan: nearest tangent pixel fell outside the face, multiplicity > 7, ... */
+    TIF_ERR_UNSUPPORTED = -5
+} TifStatus;
+
+/* face_blending_method of ico2erp_flow (projection_icosahedron.py:251,368-381) */
+#define TIF_BLEND_STRAIGHTFORWARD 0
+#define TIF_BLEND_NORMWARP 1
+
+/* boundary rule of warp_backward (flow_warp.py:82-86): 3-D input -> scipy 'wrap' (period n-1),
+ * 2-D input -> scipy 'constant' with cval 255 */
+#define TIF_WARP_WRAP 0
+#define TIF_WARP_CONSTANT255 1
+
+#define TIF_DTYPE_F32 0
+#define TIF_DTYPE_F64 1
+
+/*
+ * One tangent face.  Replaces the dict returned by get_icosahedron_parameters
+ * (projection_icosahedron.py:19-160) plus the per-face scalars erp2ico_image (:199-208) and
+ * ico2erp_flow (:285-305) derive from it.  Every double is computed on the host in float64 with the
+ * reference's own operation order, so the device only adds, multiplies, divides and compares.
+ */
+typedef struct TifFace {
+    double theta0, phi0;            /* tangent point */
+    double sin_phi0, cos_phi0;      /* np.sin / np.cos of phi0 */
+    double tri[3][2];               /* padded triangle, gnomonic (x, y), reference vertex order */
+    double xmin, xmax, ymin, ymax;  /* gnomonic bounding box of the padded triangle */
+    double g2p_x, g2p_y;            /* (Wt-1)/(xmax-xmin), (Ht-1)/(ymax-ymin): gnomonic2pixel ratios
+                                       (gnomonic_projection.py:141,145) */
+    double p2g_x, p2g_y;            /* (Wt-1)/|xmax-xmin|, (Ht-1)/|ymax-ymin|: pixel2gnomonic ratios (:188,192) */
+    double eps_stitch;              /* |xmax-xmin| / (2*Wt)   (projection_icosahedron.py:296) */
+    double eps_image;               /* (xmax-xmin) / Wt       (:215, full_face_image=False) */
+    int32_t col_start, col_stop;    /* integer ERP bounding box (:299-305); may leave the image */
+    int32_t row_start, row_stop;
+    int32_t tangent_h;              /* Ht of this face */
+    int32_t pix_offset;             /* first pixel of this face in the tangent stack */
+} TifFace;
+
+/*
+ * Host-side lookup tables handed to tif_plan_create (all HOST pointers, copied during the call).
+ * They hold every transcendental the membership test needs, evaluated by the host's numpy exactly as
+ * the reference evaluates them, which is what makes membership and pixel indices bit-identical.
+ */
+typedef struct TifPlanTables {
+    const double* gnom_x;       /* [F][Wt]   np.linspace(xmin, xmax, Wt)      (projection_icosahedron.py:207) */
+    const double* gnom_y;       /* [P / Wt]  np.linspace(ymax, ymin, Ht_f), faces concatenated (:208) */
+    const double* row_sincos;   /* [H][2]    sin(phi_r), cos(phi_r), phi_r per spherical_coordinates.py:93 */
+    const double* col_sincos;   /* [F][W][2] sin(theta_c - theta0_f), cos(theta_c - theta0_f) (gnomonic_projection.py:36) */
+    const double* col_theta;    /* [W]       theta_c per spherical_coordinates.py:92,99 */
+} TifPlanTables;
+
+typedef struct TifPlan TifPlan;     /* opaque; owns device tables */
+
+typedef struct TifPlanInfo {
+    int32_t n_faces, erp_h, erp_w, tangent_w;
+    int64_t tangent_pixels;         /* P */
+    int32_t max_faces_per_pixel;    /* K: membership planes */
+    int64_t accepted_unique;        /* sum over ERP pixels of accepting faces */
+    int64_t referenced_tangent_pixels; /* unique tangent pixels the stitch reads (P_ref) */
+    int64_t device_bytes;           /* plan footprint in HBM */
+} TifPlanInfo;
+
+int tif_abi_version(void);
+/* sizeof(TifFace), sizeof(TifPlanTables), sizeof(TifPlanInfo) as compiled into the library, so a
+ * binding in another language can verify its struct layout before the first call. */
+int tif_struct_sizes(int32_t* face_bytes, int32_t* tables_bytes, int32_t* info_bytes);
+const char* tif_status_string(int status);
+const char* tif_last_error(void);
+
+/*
+ * Geometry plan for one (face table, H, W, Wt) configuration: per tangent pixel the ERP sample
+ * position (stage 1), per ERP pixel the accepting faces and nearest tangent pixels (stage 2).
+ * Input-independent, built by fp64 kernels on the device, kept resident in HBM and reused by every
+ * execute call.  Replaces the geometry half of erp2ico_image (projection_icosahedron.py:197-229)
+ * and ico2erp_flow (:282-329), which the reference recomputes for every face of every call.
+ */
+int tif_plan_create(const TifFace* faces /*host*/, int n_faces, int erp_h, int erp_w, int tangent_w,
+                    const TifPlanTables* tables /*host*/, void* stream, TifPlan** plan_out);
+int tif_plan_destroy(TifPlan* plan);
+int tif_plan_info(const TifPlan* plan, TifPlanInfo* info /*host*/);
+
+/* Parity / debug exports (device outputs).
+ * stage 1: float ERP sample coordinate of each tangent pixel after sph2erp(modulo) (:225), and the
+ *          inside-padded-triangle flag used by full_face_image=False (:214-218).
+ * stage 2: per ERP pixel the number of accepting faces and, plane k, the packed entry
+ *          face<<25 | multiplicity<<22 | iy<<11 | ix  (faces in ascending order). */
+int tif_plan_export_stage1(const TifPlan* plan, double* erp_x /*[P]*/, double* erp_y /*[P]*/,
+                           uint8_t* inside /*[P]*/, void* stream);
+int tif_plan_export_stage2(const TifPlan* plan, uint8_t* count /*[H*W]*/, uint32_t* entries /*[K][H*W]*/,
+                           void* stream);
+
+/*
+ * erp2ico_image (projection_icosahedron.py:163-248): ERP -> padded tangent images, bilinear with
+ * scipy's mode='wrap' (period n-1) and uint8 round-half-up; RGB = samples, A = 255 (0 and RGB 255
+ * outside the padded triangle when full_face_image == 0).
+ */
+int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp /*[B,H,W,3]*/, int batch, int full_face_image,
+                   uint8_t* tangent_rgba /*[B,P,4]*/, void* stream);
+
+/*
+ * ico2erp_flow (projection_icosahedron.py:251-398): tangent flows -> ERP flow.  Nearest-pixel
+ * gather, end-point lift through pixel2gnomonic / reverse_gnomonic_projection / sph2erp, seam fix
+ * (wrap_around), face weights (blend), weighted mean over faces in index order, and the final
+ * flow_postproc.erp_of_wraparound when wrap_around != 0.  src/tar are only read for
+ * TIF_BLEND_NORMWARP (projection.py:15-61); `scratch` must then hold tif_ico2erp_scratch_bytes().
+ */
+int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend);
+int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow /*[B,P,2]*/,
+                         const uint8_t* erp_src /*[B,H,W,3] or NULL*/, const uint8_t* erp_tar /*[B,H,W,3] or NULL*/,
+                         int batch, int blend, int wrap_around, float* erp_flow /*[B,H,W,2]*/,
+                         void* scratch, void* stream);
+
+/*
+ * flow_warp.warp_backward (flow_warp.py:54-88): out(y,x) = bilinear(img, (y+v, x+u)).
+ * flow_dtype selects float32 / float64 flow ([B,H,W,2]); float64 reproduces the reference's
+ * coordinates exactly.  uint8 images are rounded half-up like scipy; float images stay float.
+ */
+int tif_warp_backward_u8(const uint8_t* image /*[B,H,W,C]*/, const void* flow, int flow_dtype,
+                         int batch, int h, int w, int channels, int mode, uint8_t* out, void* stream);
+int tif_warp_backward_f32(const float* image /*[B,H,W,C]*/, const void* flow, int flow_dtype,
+                          int batch, int h, int w, int channels, int mode, float* out, void* stream);
+
+/* flow_warp.flow_warp_meshgrid (flow_warp.py:15-51): end points with a single wrap; out [B,2,H,W]. */
+int tif_flow_warp_meshgrid(const void* flow_u /*[B,H,W]*/, const void* flow_v /*[B,H,W]*/, int dtype,
+                           int batch, int h, int w, void* out /*[B,2,H,W] same dtype*/, void* stream);
+
+/* flow_postproc.erp_of_wraparound (flow_postproc.py:17-44), in place on [B,H,W,2]. */
+int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIF_B200_H */

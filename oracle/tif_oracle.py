@@ -1,0 +1,522 @@
+"""CPU oracle: numpy restatement of the reference's tangent-image hot path.
+
+TEST INFRASTRUCTURE ONLY -- the checker, never the thing measured or shipped.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The product package (360opticalflow-tangentimages_b200/) never does.
+
+Parity pin: the reference holds no golden vectors or tests of its own, so the
+pin is the reference itself run live in the build container: `oracle/make_golden.py` imports the
+unmodified reference through `oracle/ref_shim.py` and writes tests/golden/*.npz; tests/test_oracle_*.py
+check this restatement against those fixtures (everywhere) and against the live reference (where
+/root/reference exists).  Third-party arithmetic on the path -- scipy.ndimage.map_coordinates(order=1)
+(scipy 1.18.1 here, unpinned in the reference's requirements.txt:5) -- is restated in
+`map_coordinates_order1` from scipy's ni_interpolation.c and pinned against the installed scipy.
+
+Every function cites the reference file:line (relative to /root/reference/src) it follows.
+All arithmetic is float64 with one IEEE rounding per operation, in the reference's operation order,
+so face membership and pixel indices are bit-identical to the reference on the same host.
+"""
+import numpy as np
+
+PI = np.pi
+NUM_FACES = 20
+
+# ------------------------------------------------------------------------------------------------
+# scipy.ndimage.map_coordinates(order=1) -- third-party; call sites projection_icosahedron.py:241,
+# 333,336; projection.py:52-53; flow_warp.py:84,86.  Restated from scipy/ndimage/src/ni_interpolation.c
+# (NI_GeometricTransform + map_coordinate + get_spline_interpolation_weights).
+# ------------------------------------------------------------------------------------------------
+
+
+def _wrap_coordinate(c, n):
+    """scipy mode='wrap' (NI_EXTEND_WRAP): periodic with period n-1, NOT n."""
+    c = np.array(c, dtype=np.float64, copy=True)
+    if n <= 1:
+        c[...] = 0.0
+        return c
+    sz = float(n - 1)
+    neg = c < 0
+    if neg.any():
+        cn = c[neg]
+        c[neg] = cn + sz * (np.trunc(-cn / sz) + 1.0)
+    big = c > (n - 1)
+    if big.any():
+        cb = c[big]
+        c[big] = cb - sz * np.trunc(cb / sz)
+    return c
+
+
+def map_coordinates_order1(image, ys, xs, mode, cval=0.0):
+    """Bilinear sample of a 2-D array at float coordinates with scipy's boundary rules.
+
+    mode: 'wrap' (period n-1), 'constant' (any coordinate <0 or >n-1 -> cval outright),
+    'nearest' (clamp).  Output dtype = input dtype; for uint8 the double accumulator t is
+    converted as `t>0 ? t+0.5 : 0`, clamped to [0,255], truncated (round-half-up).
+    Accumulation order = scipy's: taps (y0,x0),(y0,x1),(y1,x0),(y1,x1), each p*wy*wx, summed in double.
+    """
+    image = np.asarray(image)
+    H, W = image.shape
+    ys = np.asarray(ys, dtype=np.float64)
+    xs = np.asarray(xs, dtype=np.float64)
+    shape = ys.shape
+    ys = ys.ravel()
+    xs = xs.ravel()
+    outside = np.zeros(ys.shape, dtype=bool)
+    if mode == "wrap":
+        ys = _wrap_coordinate(ys, H)
+        xs = _wrap_coordinate(xs, W)
+    elif mode == "constant":
+        outside = (ys < 0) | (ys > H - 1) | (xs < 0) | (xs > W - 1)
+        ys = np.where(outside, 0.0, ys)
+        xs = np.where(outside, 0.0, xs)
+    elif mode == "nearest":
+        ys = np.clip(ys, 0.0, H - 1.0)
+        xs = np.clip(xs, 0.0, W - 1.0)
+    else:
+        raise ValueError(mode)
+    y0f = np.floor(ys)
+    x0f = np.floor(xs)
+    y0 = y0f.astype(np.int64)
+    x0 = x0f.astype(np.int64)
+    fy = ys - y0f
+    fx = xs - x0f
+    wy0 = 1.0 - fy
+    wy1 = 1.0 - wy0     # scipy: last weight = 1 - sum(others)
+    wx0 = 1.0 - fx
+    wx1 = 1.0 - wx0
+    # the +1 tap falls outside only when the coordinate is exactly n-1 (weight 0): scipy mirrors it
+    y1 = np.where(y0 + 1 >= H, max(H - 2, 0), y0 + 1)
+    x1 = np.where(x0 + 1 >= W, max(W - 2, 0), x0 + 1)
+    img = image.astype(np.float64, copy=False)
+    t = img[y0, x0] * wy0 * wx0
+    t = t + img[y0, x1] * wy0 * wx1
+    t = t + img[y1, x0] * wy1 * wx0
+    t = t + img[y1, x1] * wy1 * wx1
+    if mode == "constant":
+        t = np.where(outside, float(cval), t)
+    if image.dtype == np.uint8:
+        t = np.where(t > 0, t + 0.5, 0.0)
+        t = np.clip(t, 0.0, 255.0)
+        return t.astype(np.uint8).reshape(shape)
+    if image.dtype == np.float32:
+        return t.astype(np.float32).reshape(shape)
+    return t.reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry primitives
+# ------------------------------------------------------------------------------------------------
+
+def gnomonic_forward(theta, phi, theta_0, phi_0):
+    """gnomonic_projection.py:18-56 (x, y only; the hemisphere mask is computed and discarded by
+    the stitcher, projection_icosahedron.py:317)."""
+    cos_c = np.sin(phi_0) * np.sin(phi) + np.cos(phi_0) * np.cos(phi) * np.cos(theta - theta_0)
+    zeros = cos_c == 0
+    if np.any(zeros):
+        cos_c = np.where(zeros, np.finfo(float).eps, cos_c)
+    x = np.cos(phi) * np.sin(theta - theta_0) / cos_c
+    y = (np.cos(phi_0) * np.sin(phi) - np.sin(phi_0) * np.cos(phi) * np.cos(theta - theta_0)) / cos_c
+    if np.any(zeros):
+        x = np.where(zeros, 0.0, x)
+        y = np.where(zeros, 0.0, y)
+    return x, y
+
+
+def gnomonic_reverse(x, y, theta_0, phi_0):
+    """gnomonic_projection.py:59-95.  theta is continuous (may leave [-pi,pi)); rho==0 -> (theta_0, phi_0)."""
+    rho = np.sqrt(x ** 2 + y ** 2)
+    zeros = rho == 0
+    if np.any(zeros):
+        rho = np.where(zeros, np.finfo(float).eps, rho)
+    c = np.arctan2(rho, 1)
+    phi_ = np.arcsin(np.cos(c) * np.sin(phi_0) + (y * np.sin(c) * np.cos(phi_0)) / rho)
+    theta_ = theta_0 + np.arctan2(x * np.sin(c), rho * np.cos(phi_0) * np.cos(c) - y * np.sin(phi_0) * np.sin(c))
+    if np.any(zeros):
+        phi_ = np.where(zeros, phi_0, phi_)
+        theta_ = np.where(zeros, theta_0, theta_)
+    return theta_, phi_
+
+
+def erp_sph_modulo(theta, phi):
+    """spherical_coordinates.py:55-61."""
+    return np.remainder(theta + PI, 2 * PI) - PI, -(np.remainder(-phi + 0.5 * PI, PI) - 0.5 * PI)
+
+
+def sph_coord_modulo(theta, phi):
+    """spherical_coordinates.py:234-239 (note +pi/2 -> -pi/2)."""
+    return np.remainder(theta + PI, PI * 2.0) - PI, np.remainder(phi + 0.5 * PI, PI) - 0.5 * PI
+
+
+def sph2erp(theta, phi, erp_h, sph_modulo=False):
+    """spherical_coordinates.py:104-125."""
+    if sph_modulo:
+        theta, phi = erp_sph_modulo(theta, phi)
+    erp_w = 2 * erp_h
+    return (theta + PI) / (2.0 * PI / erp_w) - 0.5, (-phi + 0.5 * PI) / (PI / erp_h) - 0.5
+
+
+def erp2sph_axes(cols, rows, erp_h):
+    """spherical_coordinates.py:64-101 evaluated on separable column / row index vectors
+    (every operation there is elementwise, so a 1-D evaluation is bitwise the 2-D one)."""
+    width = erp_h * 2
+    theta = cols * (2 * PI / width) + PI / width - PI
+    phi = -(rows * (PI / erp_h) + PI / erp_h * 0.5) + 0.5 * PI
+    theta = np.where(theta == PI, -PI, theta)
+    phi = np.where(phi == -0.5 * PI, 0.5 * PI, phi)
+    return theta, phi
+
+
+def inside_polygon(px, py, poly, eps):
+    """polygon.py:59-118 with on_line=True: ray cast with inclusive y range and eps-wide edges.
+    px, py: arrays of equal shape; poly: [n,2].  Returns inside | online."""
+    inside = np.zeros(px.shape, dtype=bool)
+    online = np.zeros(px.shape, dtype=bool)
+    n = len(poly)
+    for k in range(n):
+        x1, y1 = poly[k][0], poly[k][1]
+        x2, y2 = poly[(k + 1) % n][0], poly[(k + 1) % n][1]
+        t = (py >= min(y1, y2)) & (py <= max(y1, y2)) & (px <= max(x1, x2))
+        if not t.any():
+            continue
+        if abs(y1 - y2) <= eps:
+            t = t & (px >= min(x1, x2))
+            ix = px
+        else:
+            ix = (py - y1) * (x2 - x1) / (y2 - y1) + x1
+        online |= t & (np.abs(px - ix) <= eps)
+        inside ^= t & (px <= ix)
+    return inside | online
+
+
+def _find_intersection(p1, p2, p3, p4):
+    """polygon.py:8-40."""
+    dx12 = p2[0] - p1[0]
+    dy12 = p2[1] - p1[1]
+    dx34 = p4[0] - p3[0]
+    dy34 = p4[1] - p3[1]
+    den = (dy12 * dx34 - dx12 * dy34)
+    if den == 0:
+        return None
+    t1 = ((p1[0] - p3[0]) * dy34 + (p3[1] - p1[1]) * dx34) / den
+    return [p1[0] + dx12 * t1, p1[1] + dy12 * t1]
+
+
+def enlarge_polygon(pts, offset):
+    """polygon.py:121-167: push every edge outward by `offset` (absolute gnomonic units) and intersect."""
+    out = []
+    n = len(pts)
+    for j in range(n):
+        i = (j - 1) % n
+        k = (j + 1) % n
+        v1 = np.array([pts[j][0] - pts[i][0], pts[j][1] - pts[i][1]], float)
+        v1 = v1 / np.linalg.norm(v1) * offset
+        n1 = [-v1[1], v1[0]]
+        pij1 = [pts[i][0] + n1[0], pts[i][1] + n1[1]]
+        pij2 = [pts[j][0] + n1[0], pts[j][1] + n1[1]]
+        v2 = np.array([pts[k][0] - pts[j][0], pts[k][1] - pts[j][1]], float)
+        v2 = v2 / np.linalg.norm(v2) * offset
+        n2 = [-v2[1], v2[0]]
+        pjk1 = [pts[j][0] + n2[0], pts[j][1] + n2[1]]
+        pjk2 = [pts[k][0] + n2[0], pts[k][1] + n2[1]]
+        out.append(_find_intersection(pij1, pij2, pjk1, pjk2))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# face table -- projection_icosahedron.py:19-160
+# ------------------------------------------------------------------------------------------------
+
+def icosahedron_face(face, padding=0.0):
+    """Returns dict(theta_0, phi_0, tri [3,2] padded gnomonic triangle, area [th_min, th_max, phi_rowstart, phi_rowstop])."""
+    r_circ = np.sin(2 * np.pi / 5.0)
+    r_in = np.sqrt(3) / 12.0 * (3 + np.sqrt(5))
+    r_mid = np.cos(np.pi / 5.0)
+    step = 2.0 * np.pi / 5.0
+    at = np.arctan(0.5)
+    if 0 <= face <= 4:
+        i = face
+        theta_0 = - np.pi + step / 2.0 + i * step
+        phi_0 = np.pi / 2 - np.arccos(r_in / r_circ)
+        v = [(-np.pi + i * step, at),
+             (-np.pi + np.pi * 2.0 / 5.0 / 2.0 + i * step, np.pi / 2.0),
+             (-np.pi + (i + 1) * step, at)]
+    elif 5 <= face <= 9:
+        i = face - 5
+        theta_0 = - np.pi + step / 2.0 + i * step
+        phi_0 = np.pi / 2.0 - np.arccos(r_in / r_circ) - 2 * np.arccos(r_in / r_mid)
+        v = [(-np.pi + i * step, at),
+             (-np.pi + (i + 1) * step, at),
+             (-np.pi + step / 2.0 + i * step, -at)]
+    elif 10 <= face <= 14:
+        i = face - 10
+        theta_0 = - np.pi + i * step
+        phi_0 = -(np.pi / 2.0 - np.arccos(r_in / r_circ) - 2 * np.arccos(r_in / r_mid))
+        v = [(- np.pi - step / 2.0 + i * step, -at),
+             (-np.pi + i * step, at),
+             (- np.pi + step / 2.0 + i * step, -at)]
+    elif 15 <= face <= 19:
+        i = face - 15
+        theta_0 = - np.pi + i * step
+        phi_0 = - (np.pi / 2 - np.arccos(r_in / r_circ))
+        v = [(- np.pi - step / 2.0 + i * step, -at),
+             (- np.pi + step / 2.0 + i * step, -at),
+             (- np.pi + i * step, -np.pi / 2.0)]
+    else:
+        raise ValueError(face)
+    tri0 = [gnomonic_forward(th, ph, theta_0, phi_0) for th, ph in v]
+    tri = enlarge_polygon(tri0, padding)
+    sph = [list(gnomonic_reverse(p[0], p[1], theta_0, phi_0)) for p in tri]
+    tri_a = np.array(tri)
+    mx = np.sort(tri_a[:, 0])[1]
+    my = np.sort(tri_a[:, 1])[1]
+    sph_a = np.append(np.array(sph), [gnomonic_reverse(mx, my, theta_0, phi_0)], axis=0)
+    if face <= 4 or face >= 15:
+        if padding > 0.0:
+            th = [-np.pi, np.pi]
+        else:
+            th = [np.amin(sph_a[:, 0]), np.amax(sph_a[:, 0])]
+        if face <= 4:
+            area = th + [np.pi / 2.0, np.amin(sph_a[:, 1])]
+        else:
+            area = th + [np.amax(sph_a[:, 1]), -np.pi / 2.0]
+    else:
+        area = [np.amin(sph_a[:, 0]), np.amax(sph_a[:, 0]), np.amax(sph_a[:, 1]), np.amin(sph_a[:, 1])]
+    return {"theta_0": theta_0, "phi_0": phi_0, "tri": tri_a, "area": area}
+
+
+def _pyint_start(v):
+    return int(v) if int(v) > 0 else int(v - 0.5)
+
+
+def _pyint_stop(v):
+    return int(v + 0.5) if int(v) > 0 else int(v)
+
+
+def face_erp_bbox(face_par, erp_h):
+    """projection_icosahedron.py:299-305: integer (col_start, col_stop, row_start, row_stop); may leave the image."""
+    a = face_par["area"]
+    cs, rs = sph2erp(a[0], a[2], erp_h, False)
+    ce, re = sph2erp(a[1], a[3], erp_h, False)
+    return _pyint_start(cs), _pyint_stop(ce), _pyint_start(rs), _pyint_stop(re)
+
+
+def tangent_height(tangent_w):
+    """projection_icosahedron.py:194."""
+    return int((tangent_w / 2.0) / np.tan(np.radians(30.0)) + 0.5)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1: ERP -> tangent images -- projection_icosahedron.py:163-248
+# ------------------------------------------------------------------------------------------------
+
+def erp2ico_sample_coords(face_par, erp_h, tangent_w, tangent_h):
+    """Float ERP sample coordinate of every tangent pixel of one face (:203-225)."""
+    tri = face_par["tri"]
+    xmin, xmax = np.amin(tri[:, 0]), np.amax(tri[:, 0])
+    ymin, ymax = np.amin(tri[:, 1]), np.amax(tri[:, 1])
+    gx = np.linspace(xmin, xmax, num=tangent_w, endpoint=True)
+    gy = np.linspace(ymax, ymin, num=tangent_h, endpoint=True)
+    gxv, gyv = np.meshgrid(gx, gy)
+    th, ph = gnomonic_reverse(gxv, gyv, face_par["theta_0"], face_par["phi_0"])
+    ex, ey = sph2erp(th, ph, erp_h, True)
+    return ex, ey, gxv, gyv, (xmin, xmax, ymin, ymax)
+
+
+def erp2ico_image(erp_image, tangent_w, padding=0.0, full_face_image=True, faces=range(NUM_FACES)):
+    """Returns list of int64 [Ht,Wt,4] (RGB rounded uint8 values, alpha 255/0) like the reference."""
+    erp_image = np.asarray(erp_image)
+    if erp_image.ndim == 3 and erp_image.shape[2] == 4:
+        erp_image = erp_image[:, :, 0:3]
+    elif erp_image.ndim == 2:
+        erp_image = erp_image[:, :, None]
+    erp_h = erp_image.shape[0]
+    nch = erp_image.shape[2]
+    tangent_h = tangent_height(tangent_w)
+    out = []
+    for f in faces:
+        par = icosahedron_face(f, padding)
+        ex, ey, gxv, gyv, (xmin, xmax, ymin, ymax) = erp2ico_sample_coords(par, erp_h, tangent_w, tangent_h)
+        inside = np.ones(gxv.shape, dtype=bool)
+        if not full_face_image:
+            eps = (xmax - xmin) / tangent_w
+            inside = inside_polygon(gxv, gyv, par["tri"], eps)
+        # gnomonic2pixel (gnomonic_projection.py:141-147) with padding 0 and the padded range
+        tx = ((gxv[inside] - xmin + 0.0) * ((tangent_w - 1.0) / (xmax - xmin + 0.0)) + 0.5).astype(np.int64)
+        ty = (-(gyv[inside] - ymax - 0.0) * ((tangent_h - 1.0) / (ymax - ymin + 0.0)) + 0.5).astype(np.int64)
+        img = np.full([tangent_h, tangent_w, 4 if nch == 3 else nch], 255, dtype=np.int64)
+        for ch in range(nch):
+            img[ty, tx, ch] = map_coordinates_order1(erp_image[:, :, ch], ey[inside], ex[inside], "wrap", 255)
+        if img.shape[2] == 4:
+            img[:, :, 3] = 0
+            img[ty, tx, 3] = 255
+        out.append(img)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 2+3: tangent flows -> ERP flow -- projection_icosahedron.py:251-398, "pull" form per face
+# ------------------------------------------------------------------------------------------------
+
+def _axis_candidates(start, stop, n):
+    """Unique wrapped indices of the integer range [start, stop] with their multiplicities
+    (flow_postproc.py:9-14 maps j -> rem(j+0.5, n)-0.5 == j mod n for integer j)."""
+    idx = np.remainder(np.arange(start, stop + 1, dtype=np.float64) + 0.5, n) - 0.5
+    vals, counts = np.unique(idx.astype(np.int64), return_counts=True)
+    return vals, counts
+
+
+def face_membership(face_par, erp_h, tangent_w, tangent_h):
+    """Steps A.3-1..5 of SURVEY.md for one face: candidate rows/cols, accepted mask, nearest tangent pixel.
+    Returns rows [R], cols [C], mult [R,C], accepted [R,C] bool, ix [R,C] int64, iy [R,C] int64, range tuple."""
+    erp_w = 2 * erp_h
+    tri = face_par["tri"]
+    th0, ph0 = face_par["theta_0"], face_par["phi_0"]
+    xmin, xmax = np.amin(tri[:, 0]), np.amax(tri[:, 0])
+    ymin, ymax = np.amin(tri[:, 1]), np.amax(tri[:, 1])
+    eps = abs(xmax - xmin) / (2 * tangent_w)
+    cs, ce, rs, re = face_erp_bbox(face_par, erp_h)
+    cols, mc = _axis_candidates(cs, ce, erp_w)
+    rows, mr = _axis_candidates(rs, re, erp_h)
+    theta, phi = erp2sph_axes(cols.astype(np.float64), rows.astype(np.float64), erp_h)
+    x, y = gnomonic_forward(theta[None, :], phi[:, None], th0, ph0)
+    acc = inside_polygon(x, y, tri, eps)
+    ix = ((x - xmin + 0.0) * ((tangent_w - 1.0) / (xmax - xmin + 0.0 * 2.0)) + 0.5)
+    iy = (-(y - ymax - 0.0) * ((tangent_h - 1.0) / (ymax - ymin + 0.0 * 2.0)) + 0.5)
+    with np.errstate(invalid="ignore"):
+        ix = np.where(acc, ix, 0.0).astype(np.int64)
+        iy = np.where(acc, iy, 0.0).astype(np.int64)
+    mult = mr[:, None] * mc[None, :]
+    return rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta
+
+
+def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_tar=None,
+                 wrap_around=False, blending="straightforward", return_debug=False):
+    """Returns float64 [H, 2H, 2] (and per-face debug dict when asked)."""
+    tangent_h, tangent_w = tangent_flows[0].shape[:2]
+    if erp_h is None:
+        erp_h = int(tangent_h * 2.0)
+    erp_h = int(erp_h)
+    erp_w = int(erp_h * 2.0)
+    acc_flow = np.zeros((erp_h, erp_w, 2), dtype=np.float64)
+    acc_w = np.zeros((erp_h, erp_w), dtype=np.float64)
+    if blending == "normwarp":
+        img_s = np.asarray(image_src).astype(np.float64)     # the same-size `resize` (:374-377) is this cast
+        img_t = np.asarray(image_tar).astype(np.float64)
+    debug = []
+    for f in range(len(tangent_flows)):
+        par = icosahedron_face(f, padding)
+        th0, ph0 = par["theta_0"], par["phi_0"]
+        rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta_cols = \
+            face_membership(par, erp_h, tangent_w, tangent_h)
+        rr, cc = np.nonzero(acc)
+        r = rows[rr]
+        c = cols[cc]
+        ixa = ix[rr, cc]
+        iya = iy[rr, cc]
+        flow = np.asarray(tangent_flows[f])
+        # map_coordinates(order=1, mode='nearest') at integer coordinates == clamped gather (:333-337)
+        gi = np.clip(iya, 0, tangent_h - 1)
+        gj = np.clip(ixa, 0, tangent_w - 1)
+        px = ixa + flow[gi, gj, 0]          # int64 + float32 -> float64
+        py = iya + flow[gi, gj, 1]
+        # pixel2gnomonic (gnomonic_projection.py:186-194)
+        gx = px / ((tangent_w - 1.0) / (abs(xmax - xmin) + 0.0 * 2.0)) + xmin - 0.0
+        gy = - py / ((tangent_h - 1.0) / (abs(ymax - ymin) + 0.0 * 2.0)) + ymax + 0.0
+        th_t, ph_t = gnomonic_reverse(gx, gy, th0, ph0)
+        th_t, ph_t = sph_coord_modulo(th_t, ph_t)
+        tx, ty = sph2erp(th_t, ph_t, erp_h, True)
+        if wrap_around:
+            th_s = np.remainder(theta_cols[cc] + PI, PI * 2.0) - PI
+            long_line = np.abs(th_t - th_s) > PI
+            minus = long_line & (th_s < 0) & (th_t > 0)
+            plus = long_line & (th_s > 0) & (th_t < 0)
+            tx = np.where(minus, tx - erp_w, tx)
+            tx = np.where(plus, tx + erp_w, tx)
+        fu = tx - c
+        fv = ty - r
+        if blending == "straightforward":
+            w = np.ones(fu.shape, dtype=np.float64)
+        elif blending == "normwarp":
+            # projection.py:15-61 -- weight = exp(-mean_ch|tar(tx,ty)-src(c,r)| / face-global mean),
+            # duplicates of wrapped candidate pixels counted with their multiplicity in the global mean
+            d = np.zeros((fu.shape[0], 3), dtype=np.float64)
+            for ch in range(3):
+                ts = map_coordinates_order1(img_t[:, :, ch], ty, tx, "constant", 255)
+                d[:, ch] = np.abs(ts - img_s[r, c, ch])
+            m = mult[rr, cc].astype(np.float64)
+            gmean = np.sum(d * m[:, None]) / (3.0 * np.sum(m))
+            w = np.exp(-(np.mean(d, axis=1) / gmean))
+        else:
+            raise ValueError(blending)
+        acc_flow[r, c, 0] += fu * w
+        acc_flow[r, c, 1] += fv * w
+        acc_w[r, c] += w
+        if return_debug:
+            debug.append({"rows": r, "cols": c, "ix": ixa, "iy": iya, "mult": mult[rr, cc],
+                          "candidates": int(mult.sum()), "accepted": int(mult[rr, cc].sum()),
+                          "bbox": face_erp_bbox(par, erp_h)})
+    nz = acc_w != 0.0
+    for ch in range(2):
+        plane = acc_flow[:, :, ch]
+        plane[nz] = plane[nz] / acc_w[nz]
+    if wrap_around:
+        acc_flow = erp_of_wraparound(acc_flow)
+    if return_debug:
+        return acc_flow, debug
+    return acc_flow
+
+
+# ------------------------------------------------------------------------------------------------
+# flow_postproc / flow_warp
+# ------------------------------------------------------------------------------------------------
+
+def erp_pixles_modulo(x, y, image_width, image_height):
+    """flow_postproc.py:9-14."""
+    return np.remainder(x + 0.5, image_width) - 0.5, np.remainder(y + 0.5, image_height) - 0.5
+
+
+def erp_of_wraparound(erp_flow, of_u_threshold=None):
+    """flow_postproc.py:17-44.  Mutates the u plane of its argument (through a view) like the reference."""
+    w = erp_flow.shape[1]
+    if of_u_threshold is None:
+        of_u_threshold = w / 2.0
+    u = erp_flow[:, :, 0]
+    split = int(w - 1 - of_u_threshold)
+    left = np.zeros(u.shape, dtype=bool)
+    left[:, 0:split] = True
+    sel = left & (u > of_u_threshold)
+    u[sel] = u[sel] - w
+    right = np.zeros(u.shape, dtype=bool)
+    right[:, split:w - 1] = True
+    sel = right & (u < -of_u_threshold)
+    u[sel] = u[sel] + w
+    return np.stack((u, erp_flow[:, :, 1]), axis=2)
+
+
+def flow_warp_meshgrid(flow_u, flow_v):
+    """flow_warp.py:15-51: end points with a SINGLE wrap (not a modulo)."""
+    h, w = flow_u.shape
+    xa, ya = np.meshgrid(np.linspace(0, w - 1, w), np.linspace(0, h - 1, h))
+    eu = xa + flow_u
+    ev = ya + flow_v
+    eu = np.where(eu >= w - 0.5, eu - w, eu)
+    eu = np.where(eu < -0.5, eu + w, eu)
+    ev = np.where(ev >= h - 0.5, ev - h, ev)
+    ev = np.where(ev < -0.5, ev + h, ev)
+    return np.stack((eu, ev))
+
+
+def warp_backward(image_target, of_forward):
+    """flow_warp.py:54-88: out(y,x) = bilinear(img, (y+v, x+u)); 'wrap' for HxWxC, 'constant' 255 for HxW."""
+    image_target = np.asarray(image_target)
+    h, w = image_target.shape[:2]
+    xa, ya = np.meshgrid(np.linspace(0, w - 1, w), np.linspace(0, h - 1, h))
+    xn = xa + of_forward[:, :, 0]
+    yn = ya + of_forward[:, :, 1]
+    out = np.zeros_like(image_target)
+    if image_target.ndim == 3:
+        for ch in range(image_target.shape[2]):
+            out[:, :, ch] = map_coordinates_order1(image_target[:, :, ch], yn, xn, "wrap")
+    else:
+        out[:, :] = map_coordinates_order1(image_target, yn, xn, "constant", 255)
+    return out
