@@ -403,6 +403,10 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
         img_s = np.asarray(image_src).astype(np.float64)     # the same-size `resize` (:374-377) is this cast
         img_t = np.asarray(image_tar).astype(np.float64)
     debug = []
+    # distance of the closest contributing end point to a discontinuity of the reference's own map:
+    # the +-pi seam (u jumps by W without the seam fix) and the hard edge of mode='constant' sampling
+    seam_dist = np.full((erp_h, erp_w), np.inf)
+    edge_dist = np.full((erp_h, erp_w), np.inf)
     for f in range(len(tangent_flows)):
         par = icosahedron_face(f, padding)
         th0, ph0 = par["theta_0"], par["phi_0"]
@@ -425,6 +429,8 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
         th_t, ph_t = gnomonic_reverse(gx, gy, th0, ph0)
         th_t, ph_t = sph_coord_modulo(th_t, ph_t)
         tx, ty = sph2erp(th_t, ph_t, erp_h, True)
+        if return_debug:
+            np.minimum.at(seam_dist, (r, c), PI - np.abs(th_t))
         if wrap_around:
             th_s = np.remainder(theta_cols[cc] + PI, PI * 2.0) - PI
             long_line = np.abs(th_t - th_s) > PI
@@ -434,6 +440,9 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
             tx = np.where(plus, tx + erp_w, tx)
         fu = tx - c
         fv = ty - r
+        if return_debug:
+            e = np.minimum(np.minimum(np.abs(tx), np.abs(tx - (erp_w - 1))), np.minimum(np.abs(ty), np.abs(ty - (erp_h - 1))))
+            np.minimum.at(edge_dist, (r, c), e)
         if blending == "straightforward":
             w = np.ones(fu.shape, dtype=np.float64)
         elif blending == "normwarp":
@@ -462,7 +471,7 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
     if wrap_around:
         acc_flow = erp_of_wraparound(acc_flow)
     if return_debug:
-        return acc_flow, debug
+        return acc_flow, {"faces": debug, "seam_dist": seam_dist, "edge_dist": edge_dist}
     return acc_flow
 
 
