@@ -13,7 +13,7 @@ from . import polygon, spherical_coordinates, gnomonic_projection  # noqa: F401
 __all__ = ["projection_icosahedron", "flow_warp", "flow_postproc", "gnomonic_projection",
            "spherical_coordinates", "polygon", "install_dropin", "sharding"]
 
-_LAZY = ("projection_icosahedron", "flow_warp", "flow_postproc", "_geometry", "_ops", "sharding")
+_LAZY = ("projection_icosahedron", "flow_warp", "flow_postproc", "_geometry", "_ops", "sharding", "pipeline")
 
 
 def __getattr__(name):

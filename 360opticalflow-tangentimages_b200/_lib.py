@@ -67,6 +67,7 @@ SYMBOLS = {
     "tif_erp2ico_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "tif_ico2erp_scratch_bytes": (C.c_int64, [_VP, C.c_int, C.c_int]),
     "tif_ico2erp_flow_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "tif_ico2erp_flow_f32_ex": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, _VP]),
     "tif_warp_backward_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_warp_backward_f32": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_flow_warp_meshgrid": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),

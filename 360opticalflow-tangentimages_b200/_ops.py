@@ -37,16 +37,49 @@ _libdef.define("flow_warp_meshgrid(Tensor flow_u, Tensor flow_v) -> Tensor")
 _libdef.define("erp_of_wraparound_(Tensor(a!) erp_flow, float u_threshold) -> Tensor(a!)")
 
 
-def _erp2ico(erp, plan, full_face_image):
-    p = _registry[plan]
-    _need_cuda(erp)
-    if erp.dtype != torch.uint8 or erp.dim() != 4 or erp.shape[1:] != (p.erp_h, p.erp_w, 3):
-        raise ValueError("erp2ico expects uint8 [B,%d,%d,3], got %s %s" % (p.erp_h, p.erp_w, erp.dtype, tuple(erp.shape)))
-    erp = erp.contiguous()
-    out = torch.empty((erp.shape[0], p.tangent_pixels, 4), dtype=torch.uint8, device=erp.device)
+def erp2ico_out(p, erp, full_face_image, out):
+    """tif_erp2ico_u8 on the current stream into a caller-owned [B,P,4] uint8 tensor."""
+    _need_cuda(erp, out)
+    if erp.dtype != torch.uint8 or erp.dim() != 4 or erp.shape[1:] != (p.erp_h, p.erp_w, 3) or not erp.is_contiguous():
+        raise ValueError("erp2ico expects contiguous uint8 [B,%d,%d,3], got %s %s" % (p.erp_h, p.erp_w, erp.dtype, tuple(erp.shape)))
+    if out.dtype != torch.uint8 or tuple(out.shape) != (erp.shape[0], p.tangent_pixels, 4) or not out.is_contiguous():
+        raise ValueError("erp2ico output must be contiguous uint8 [B,%d,4]" % p.tangent_pixels)
     with torch.cuda.device(erp.device):
         _lib.check(p.lib.tif_erp2ico_u8(p.handle, erp.data_ptr(), erp.shape[0], int(full_face_image), out.data_ptr(),
                                         _stream()), "tif_erp2ico_u8")
+    return out
+
+
+def _erp2ico(erp, plan, full_face_image):
+    p = _registry[plan]
+    _need_cuda(erp)
+    erp = erp.contiguous()
+    out = torch.empty((erp.shape[0], p.tangent_pixels, 4), dtype=torch.uint8, device=erp.device)
+    return erp2ico_out(p, erp, full_face_image, out)
+
+
+def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out, scratch=None, pass_mask=3):
+    """tif_ico2erp_flow_f32 on the current stream into a caller-owned [B,H,W,2] float32 tensor.
+    Inputs must be contiguous; `scratch` (uint8, >= tif_ico2erp_scratch_bytes) is needed for normwarp."""
+    _need_cuda(tangent_flow, erp_src, erp_tar, out)
+    batch = tangent_flow.shape[0]
+    if tangent_flow.dtype != torch.float32 or tuple(tangent_flow.shape) != (batch, p.tangent_pixels, 2) or not tangent_flow.is_contiguous():
+        raise ValueError("ico2erp_flow expects contiguous float32 [B,%d,2]" % p.tangent_pixels)
+    if out.dtype != torch.float32 or tuple(out.shape) != (batch, p.erp_h, p.erp_w, 2) or not out.is_contiguous():
+        raise ValueError("ico2erp_flow output must be contiguous float32 [B,%d,%d,2]" % (p.erp_h, p.erp_w))
+    src_ptr = tar_ptr = scratch_ptr = None
+    if blend == _lib.BLEND_NORMWARP:
+        for name, img in (("erp_src", erp_src), ("erp_tar", erp_tar)):
+            if img is None or img.dtype != torch.uint8 or tuple(img.shape) != (batch, p.erp_h, p.erp_w, 3) or not img.is_contiguous():
+                raise ValueError("normwarp needs contiguous uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
+        need = p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend)
+        if scratch is None or scratch.numel() * scratch.element_size() < need:
+            raise ValueError("normwarp needs %d bytes of scratch" % need)
+        src_ptr, tar_ptr, scratch_ptr = erp_src.data_ptr(), erp_tar.data_ptr(), scratch.data_ptr()
+    with torch.cuda.device(tangent_flow.device):
+        _lib.check(p.lib.tif_ico2erp_flow_f32_ex(p.handle, tangent_flow.data_ptr(), src_ptr, tar_ptr, batch, int(blend),
+                                                 int(wrap_around), out.data_ptr(), scratch_ptr, int(pass_mask), _stream()),
+                   "tif_ico2erp_flow_f32")
     return out
 
 

@@ -382,9 +382,9 @@ extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int
     return (int64_t)batch * plan->n_faces * (int64_t)sizeof(unsigned long long);
 }
 
-extern "C" int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
-                                    const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
-                                    void* scratch, void* stream_v) {
+extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
+                                       const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
+                                       void* scratch, int pass_mask, void* stream_v) {
     if (!plan || !tangent_flow || !erp_flow || batch <= 0) {
         tif_set_error("tif_ico2erp_flow_f32: invalid argument");
         return TIF_ERR_INVALID_ARG;
@@ -409,14 +409,23 @@ extern "C" int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_fl
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
         k_stitch<0><<<grid, threads, smem, stream>>>(STITCH_ARGS);
     } else {
-        TIF_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)tif_ico2erp_scratch_bytes(plan, batch, blend), stream));
-        k_stitch<1><<<grid, threads, smem, stream>>>(STITCH_ARGS);
-        TIF_CUDA_CHECK(cudaGetLastError());
-        k_stitch<2><<<grid, threads, smem, stream>>>(STITCH_ARGS);
+        if (pass_mask & 1) {
+            TIF_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)tif_ico2erp_scratch_bytes(plan, batch, blend), stream));
+            k_stitch<1><<<grid, threads, smem, stream>>>(STITCH_ARGS);
+            TIF_CUDA_CHECK(cudaGetLastError());
+        }
+        if (pass_mask & 2) k_stitch<2><<<grid, threads, smem, stream>>>(STITCH_ARGS);
     }
 #undef STITCH_ARGS
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
+}
+
+extern "C" int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
+                                    const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
+                                    void* scratch, void* stream) {
+    return tif_ico2erp_flow_f32_ex(plan, tangent_flow, erp_src, erp_tar, batch, blend, wrap_around, erp_flow, scratch, 3,
+                                   stream);
 }
 
 // ------------------------------------------------------------------------------------------------

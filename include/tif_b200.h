@@ -157,6 +157,12 @@ int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow /*[B,P,2
                          int batch, int blend, int wrap_around, float* erp_flow /*[B,H,W,2]*/,
                          void* scratch, void* stream);
 
+/* Profiling aid: the same call restricted to one of the two normwarp passes (pass_mask 1 = face-global
+ * warp-error sums, 2 = weights + blend using the sums already in `scratch`, 3 = both = the call above). */
+int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
+                            const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
+                            void* scratch, int pass_mask, void* stream);
+
 /*
  * flow_warp.warp_backward (flow_warp.py:54-88): out(y,x) = bilinear(img, (y+v, x+u)).
  * flow_dtype selects float32 / float64 flow ([B,H,W,2]); float64 reproduces the reference's

@@ -389,81 +389,84 @@ def face_membership(face_par, erp_h, tangent_w, tangent_h):
     return rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta
 
 
-def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_tar=None,
-                 wrap_around=False, blending="straightforward", return_debug=False):
-    """Returns float64 [H, 2H, 2] (and per-face debug dict when asked)."""
-    tangent_h, tangent_w = tangent_flows[0].shape[:2]
-    if erp_h is None:
-        erp_h = int(tangent_h * 2.0)
-    erp_h = int(erp_h)
+def stitch_face(face, flow, erp_h, padding, img_s, img_t, wrap_around, blending):
+    """One iteration of the reference's face loop (projection_icosahedron.py:282-381) in pull form.
+    flow: float32 [Ht,Wt,2]; img_s/img_t: float64 [H,W,3] (normwarp only).
+    Returns dict(r, c, fu, fv, w, ix, iy, mult, candidates, accepted, bbox, th_t, tx, ty)."""
+    flow = np.asarray(flow)
+    tangent_h, tangent_w = flow.shape[:2]
+    erp_w = int(erp_h * 2.0)
+    par = icosahedron_face(face, padding)
+    th0, ph0 = par["theta_0"], par["phi_0"]
+    rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta_cols = \
+        face_membership(par, erp_h, tangent_w, tangent_h)
+    rr, cc = np.nonzero(acc)
+    r = rows[rr]
+    c = cols[cc]
+    ixa = ix[rr, cc]
+    iya = iy[rr, cc]
+    # map_coordinates(order=1, mode='nearest') at integer coordinates == clamped gather (:333-337)
+    gi = np.clip(iya, 0, tangent_h - 1)
+    gj = np.clip(ixa, 0, tangent_w - 1)
+    px = ixa + flow[gi, gj, 0]          # int64 + float32 -> float64
+    py = iya + flow[gi, gj, 1]
+    # pixel2gnomonic (gnomonic_projection.py:186-194)
+    gx = px / ((tangent_w - 1.0) / (abs(xmax - xmin) + 0.0 * 2.0)) + xmin - 0.0
+    gy = - py / ((tangent_h - 1.0) / (abs(ymax - ymin) + 0.0 * 2.0)) + ymax + 0.0
+    th_t, ph_t = gnomonic_reverse(gx, gy, th0, ph0)
+    th_t, ph_t = sph_coord_modulo(th_t, ph_t)
+    tx, ty = sph2erp(th_t, ph_t, erp_h, True)
+    if wrap_around:
+        th_s = np.remainder(theta_cols[cc] + PI, PI * 2.0) - PI
+        long_line = np.abs(th_t - th_s) > PI
+        minus = long_line & (th_s < 0) & (th_t > 0)
+        plus = long_line & (th_s > 0) & (th_t < 0)
+        tx = np.where(minus, tx - erp_w, tx)
+        tx = np.where(plus, tx + erp_w, tx)
+    fu = tx - c
+    fv = ty - r
+    m = mult[rr, cc]
+    if blending == "straightforward":
+        w = np.ones(fu.shape, dtype=np.float64)
+    elif blending == "normwarp":
+        # projection.py:15-61 -- weight = exp(-mean_ch|tar(tx,ty)-src(c,r)| / face-global mean),
+        # duplicates of wrapped candidate pixels counted with their multiplicity in the global mean
+        d = np.zeros((fu.shape[0], 3), dtype=np.float64)
+        for ch in range(3):
+            ts = map_coordinates_order1(img_t[:, :, ch], ty, tx, "constant", 255)
+            d[:, ch] = np.abs(ts - img_s[r, c, ch])
+        mf = m.astype(np.float64)
+        gmean = np.sum(d * mf[:, None]) / (3.0 * np.sum(mf))
+        w = np.exp(-(np.mean(d, axis=1) / gmean))
+    else:
+        raise ValueError(blending)
+    return {"r": r, "c": c, "fu": fu, "fv": fv, "w": w, "ix": ixa, "iy": iya, "mult": m,
+            "candidates": int(mult.sum()), "accepted": int(m.sum()), "bbox": face_erp_bbox(par, erp_h),
+            "th_t": th_t, "tx": tx, "ty": ty}
+
+
+def blend_faces(face_results, erp_h, wrap_around, return_debug=False):
+    """Accumulate per-face results in face order, normalise, wrap (projection_icosahedron.py:384-396)."""
     erp_w = int(erp_h * 2.0)
     acc_flow = np.zeros((erp_h, erp_w, 2), dtype=np.float64)
     acc_w = np.zeros((erp_h, erp_w), dtype=np.float64)
-    if blending == "normwarp":
-        img_s = np.asarray(image_src).astype(np.float64)     # the same-size `resize` (:374-377) is this cast
-        img_t = np.asarray(image_tar).astype(np.float64)
-    debug = []
     # distance of the closest contributing end point to a discontinuity of the reference's own map:
     # the +-pi seam (u jumps by W without the seam fix) and the hard edge of mode='constant' sampling
     seam_dist = np.full((erp_h, erp_w), np.inf)
     edge_dist = np.full((erp_h, erp_w), np.inf)
-    for f in range(len(tangent_flows)):
-        par = icosahedron_face(f, padding)
-        th0, ph0 = par["theta_0"], par["phi_0"]
-        rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta_cols = \
-            face_membership(par, erp_h, tangent_w, tangent_h)
-        rr, cc = np.nonzero(acc)
-        r = rows[rr]
-        c = cols[cc]
-        ixa = ix[rr, cc]
-        iya = iy[rr, cc]
-        flow = np.asarray(tangent_flows[f])
-        # map_coordinates(order=1, mode='nearest') at integer coordinates == clamped gather (:333-337)
-        gi = np.clip(iya, 0, tangent_h - 1)
-        gj = np.clip(ixa, 0, tangent_w - 1)
-        px = ixa + flow[gi, gj, 0]          # int64 + float32 -> float64
-        py = iya + flow[gi, gj, 1]
-        # pixel2gnomonic (gnomonic_projection.py:186-194)
-        gx = px / ((tangent_w - 1.0) / (abs(xmax - xmin) + 0.0 * 2.0)) + xmin - 0.0
-        gy = - py / ((tangent_h - 1.0) / (abs(ymax - ymin) + 0.0 * 2.0)) + ymax + 0.0
-        th_t, ph_t = gnomonic_reverse(gx, gy, th0, ph0)
-        th_t, ph_t = sph_coord_modulo(th_t, ph_t)
-        tx, ty = sph2erp(th_t, ph_t, erp_h, True)
-        if return_debug:
-            np.minimum.at(seam_dist, (r, c), PI - np.abs(th_t))
-        if wrap_around:
-            th_s = np.remainder(theta_cols[cc] + PI, PI * 2.0) - PI
-            long_line = np.abs(th_t - th_s) > PI
-            minus = long_line & (th_s < 0) & (th_t > 0)
-            plus = long_line & (th_s > 0) & (th_t < 0)
-            tx = np.where(minus, tx - erp_w, tx)
-            tx = np.where(plus, tx + erp_w, tx)
-        fu = tx - c
-        fv = ty - r
-        if return_debug:
-            e = np.minimum(np.minimum(np.abs(tx), np.abs(tx - (erp_w - 1))), np.minimum(np.abs(ty), np.abs(ty - (erp_h - 1))))
-            np.minimum.at(edge_dist, (r, c), e)
-        if blending == "straightforward":
-            w = np.ones(fu.shape, dtype=np.float64)
-        elif blending == "normwarp":
-            # projection.py:15-61 -- weight = exp(-mean_ch|tar(tx,ty)-src(c,r)| / face-global mean),
-            # duplicates of wrapped candidate pixels counted with their multiplicity in the global mean
-            d = np.zeros((fu.shape[0], 3), dtype=np.float64)
-            for ch in range(3):
-                ts = map_coordinates_order1(img_t[:, :, ch], ty, tx, "constant", 255)
-                d[:, ch] = np.abs(ts - img_s[r, c, ch])
-            m = mult[rr, cc].astype(np.float64)
-            gmean = np.sum(d * m[:, None]) / (3.0 * np.sum(m))
-            w = np.exp(-(np.mean(d, axis=1) / gmean))
-        else:
-            raise ValueError(blending)
-        acc_flow[r, c, 0] += fu * w
-        acc_flow[r, c, 1] += fv * w
+    debug = []
+    for fr in face_results:
+        r, c, w = fr["r"], fr["c"], fr["w"]
+        acc_flow[r, c, 0] += fr["fu"] * w
+        acc_flow[r, c, 1] += fr["fv"] * w
         acc_w[r, c] += w
         if return_debug:
-            debug.append({"rows": r, "cols": c, "ix": ixa, "iy": iya, "mult": mult[rr, cc],
-                          "candidates": int(mult.sum()), "accepted": int(mult[rr, cc].sum()),
-                          "bbox": face_erp_bbox(par, erp_h)})
+            tx, ty = fr["tx"], fr["ty"]
+            np.minimum.at(seam_dist, (r, c), PI - np.abs(fr["th_t"]))
+            e = np.minimum(np.minimum(np.abs(tx), np.abs(tx - (erp_w - 1))), np.minimum(np.abs(ty), np.abs(ty - (erp_h - 1))))
+            np.minimum.at(edge_dist, (r, c), e)
+            debug.append({"rows": r, "cols": c, "ix": fr["ix"], "iy": fr["iy"], "mult": fr["mult"],
+                          "candidates": fr["candidates"], "accepted": fr["accepted"], "bbox": fr["bbox"]})
     nz = acc_w != 0.0
     for ch in range(2):
         plane = acc_flow[:, :, ch]
@@ -473,6 +476,22 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
     if return_debug:
         return acc_flow, {"faces": debug, "seam_dist": seam_dist, "edge_dist": edge_dist}
     return acc_flow
+
+
+def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_tar=None,
+                 wrap_around=False, blending="straightforward", return_debug=False):
+    """Returns float64 [H, 2H, 2] (and a debug dict when asked)."""
+    tangent_h = tangent_flows[0].shape[0]
+    if erp_h is None:
+        erp_h = int(tangent_h * 2.0)
+    erp_h = int(erp_h)
+    img_s = img_t = None
+    if blending == "normwarp":
+        img_s = np.asarray(image_src).astype(np.float64)     # the same-size `resize` (:374-377) is this cast
+        img_t = np.asarray(image_tar).astype(np.float64)
+    results = [stitch_face(f, tangent_flows[f], erp_h, padding, img_s, img_t, wrap_around, blending)
+               for f in range(len(tangent_flows))]
+    return blend_faces(results, erp_h, wrap_around, return_debug)
 
 
 # ------------------------------------------------------------------------------------------------
