@@ -49,6 +49,10 @@ struct TifPlan {
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
     double* d_col_theta;           // [W] theta of every ERP column
+    float2* d_row_sc;              // [H] (sin phi_r, cos phi_r) in float32
+    float2* d_col_sc;              // [F][W] (sin, cos)(theta_c - theta0_f) in float32
+    double2* d_row_sc64;           // [H] the same tables in float64 (membership test, polar rows of the stitch)
+    double2* d_col_sc64;           // [F][W]
     double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
 };
 

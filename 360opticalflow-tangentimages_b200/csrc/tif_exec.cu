@@ -57,49 +57,111 @@ __device__ __forceinline__ uint8_t round_u8_guarded(float t, float p00, float p0
 // ------------------------------------------------------------------------------------------------
 // stage 1: ERP -> tangent images
 // ------------------------------------------------------------------------------------------------
+// The two taps of one image row are 6 consecutive bytes (R0 G0 B0 R1 G1 B1) at an arbitrary byte
+// address.  They are fetched with one or two aligned 8-byte loads and funnel-shifted into place
+// instead of six byte loads.  `o` = address & 7.  The caller guarantees that 16 bytes from the aligned
+// address are readable.
+__device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ p, unsigned o,
+                                              uint32_t& lo /* R0 G0 B0 R1 */, uint32_t& hi /* G1 B1 . . */) {
+    const uint2* q = reinterpret_cast<const uint2*>(p - o);
+    const uint2 v0 = __ldg(q);
+    uint2 v1 = make_uint2(0u, 0u);
+    if (o > 2) v1 = __ldg(q + 1);                                // bytes o..o+5 leave the first 8 only then
+    const bool up = o >= 4;
+    const uint32_t wa = up ? v0.y : v0.x;
+    const uint32_t wb = up ? v1.x : v0.y;
+    const uint32_t wc = up ? v1.y : v1.x;
+    const unsigned sh = (o & 3) * 8;
+    lo = __funnelshift_r(wa, wb, sh);
+    hi = __funnelshift_r(wb, wc, sh);
+}
+
+__device__ __forceinline__ void load_tap_pair_bytes(const uint8_t* __restrict__ p, uint32_t& lo, uint32_t& hi) {
+    lo = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+    hi = (uint32_t)__ldg(p + 4) | ((uint32_t)__ldg(p + 5) << 8);
+}
+
+#define TIF_BYTE(w, k) __byte_perm((w), 0u, 0x4440u | (k))       // zero-extended byte k: one PRMT, no XU conversion
+
+// Fixed-point bilinear: weights scaled by 2^24 (exactly rounded from the float64 scipy weights), so the
+// top byte of p00 W00 + p01 W01 + p10 W10 + p11 W11 + 2^23 is scipy's trunc(t + 0.5).  The fixed-point
+// sum is within 3.1e-5 of t; if t + 0.5 lies within 2^-11 of an integer the exact float64 expression
+// decides instead (about 1e-3 of the samples).
+#define TIF_FIX_ONE 16777216.0
+#define TIF_FIX_HALF 0x00800000u
+#define TIF_FIX_GUARD 0x00002000u
+
+__device__ __forceinline__ uint32_t fix_bilinear(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, uint32_t w00,
+                                                 uint32_t w01, uint32_t w10, uint32_t w11) {
+    return p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + TIF_FIX_HALF;
+}
+
+__device__ __forceinline__ bool fix_undecided(uint32_t acc) {
+    return ((acc + TIF_FIX_GUARD) & 0x00ffffffu) < 2u * TIF_FIX_GUARD;
+}
+
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
-k_erp2ico(const uint32_t* __restrict__ s1_base, const float2* __restrict__ s1_frac,
-          const double2* __restrict__ s1_frac64, const uint8_t* __restrict__ erp, uint8_t* __restrict__ out,
-          int64_t n_pix, int erp_h, int erp_w, int batch, int full_face) {
+k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
+          const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int erp_h, int erp_w, int batch,
+          int batch_per_block_row, int full_face) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pix) return;
-    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+    const int b_begin = blockIdx.y * batch_per_block_row;
+    const int b_end = min(batch, b_begin + batch_per_block_row);
     const uint32_t bs = s1_base[p];
-    const bool outside = (bs & TIF_S1_OUTSIDE) && !full_face;
     const size_t image_bytes = (size_t)erp_h * erp_w * 3;
     const size_t row_bytes = (size_t)erp_w * 3;
-    uchar4* out4 = reinterpret_cast<uchar4*>(out);
-    if (outside) {
-        for (int bb = 0; bb < TIF_BATCH_CHUNK && b0 + bb < batch; ++bb)
-            out4[(size_t)(b0 + bb) * n_pix + p] = make_uchar4(255, 255, 255, 0);
+    uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
+    if ((bs & TIF_S1_OUTSIDE) && !full_face) {
+        for (int b = b_begin; b < b_end; ++b, o4 += n_pix) *o4 = 0x00ffffffu;   // RGB 255, alpha 0
         return;
     }
-    const float2 fr = s1_frac[p];
-    const float wx1 = fr.x, wx0 = 1.0f - fr.x, wy1 = fr.y, wy0 = 1.0f - fr.y;
+    const double2 fr = s1_frac64[p];
+    uint32_t w00, w01, w10, w11;
+    {
+        // scipy: w0 = 1 - f, w1 = 1 - w0 per axis; tap weight = wy * wx
+        const double wx0 = 1.0 - fr.x, wx1 = 1.0 - wx0, wy0 = 1.0 - fr.y, wy1 = 1.0 - wy0;
+        w00 = (uint32_t)(wy0 * wx0 * TIF_FIX_ONE + 0.5);
+        w01 = (uint32_t)(wy0 * wx1 * TIF_FIX_ONE + 0.5);
+        w10 = (uint32_t)(wy1 * wx0 * TIF_FIX_ONE + 0.5);
+        w11 = (uint32_t)(wy1 * wx1 * TIF_FIX_ONE + 0.5);
+    }
     const size_t tap = (size_t)(bs & 0x7fffffffu) * 3;
-#pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
-        const int b = b0 + bb;
-        if (b >= batch) break;
-        const uint8_t* r0 = erp + (size_t)b * image_bytes + tap;
-        const uint8_t* r1 = r0 + row_bytes;
-        uint8_t px[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float p00 = (float)__ldg(r0 + ch), p01 = (float)__ldg(r0 + 3 + ch);
-            const float p10 = (float)__ldg(r1 + ch), p11 = (float)__ldg(r1 + 3 + ch);
-            const float t = bilinear_f32(p00, p01, p10, p11, wx0, wx1, wy0, wy1);
-            const float r = t + 0.5f;
-            const float fl = floorf(r);
-            const float frac = r - fl;
-            if (frac < TIF_ROUND_GUARD || frac > 1.0f - TIF_ROUND_GUARD) {
-                const double2 f64 = s1_frac64[p];
-                px[ch] = scipy_round_u8(bilinear_f64_exact((double)p00, (double)p01, (double)p10, (double)p11, f64.x, f64.y));
-            } else {
-                px[ch] = (uint8_t)fl;
+    const uint8_t* r0 = erp + (size_t)b_begin * image_bytes + tap;
+    // The wide loads may touch up to 15 bytes past the second tap pair; only a tap at the very end of an
+    // image could leave the buffer, and only in the last image: those few pixels use byte loads.
+    const bool tail = tap + row_bytes + 16 > image_bytes;
+    unsigned o0 = 0, o1 = 0;
+    if (ALIGNED) {      // image stride and base are multiples of 8: the byte phase is the same for every image
+        o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
+        o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
+    }
+#pragma unroll 2
+    for (int b = b_begin; b < b_end; ++b, r0 += image_bytes, o4 += n_pix) {
+        uint32_t lo0, hi0, lo1, hi1;
+        if (tail) {
+            load_tap_pair_bytes(r0, lo0, hi0);
+            load_tap_pair_bytes(r0 + row_bytes, lo1, hi1);
+        } else {
+            if (!ALIGNED) {
+                o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
+                o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
             }
+            load_tap_pair(r0, o0, lo0, hi0);
+            load_tap_pair(r0 + row_bytes, o1, lo1, hi1);
         }
-        out4[(size_t)b * n_pix + p] = make_uchar4(px[0], px[1], px[2], 255);
+        // R: bytes 0,3 of lo;  G: byte 1 of lo, byte 0 of hi;  B: byte 2 of lo, byte 1 of hi
+        uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
+        uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
+        uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
+        if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
+            ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
+            ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
+            ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
+        }
+        // top bytes -> R | G<<8 | B<<16 | 255<<24
+        *o4 = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
     }
 }
 
@@ -110,10 +172,23 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         return TIF_ERR_INVALID_ARG;
     }
     const int threads = 256;
-    dim3 grid((unsigned)((plan->tangent_pixels + threads - 1) / threads), (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK));
-    k_erp2ico<<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac, plan->d_s1_frac64, erp,
-                                                          tangent_rgba, plan->tangent_pixels, plan->erp_h, plan->erp_w,
-                                                          batch, full_face_image);
+    const unsigned blocks_x = (unsigned)((plan->tangent_pixels + threads - 1) / threads);
+    // every thread walks the whole batch so that the plan entry is read once; only tiny problems
+    // split the batch over blockIdx.y to fill the 148 SMs
+    int rows = 1;
+    while (rows < batch && (int64_t)blocks_x * rows < 148 * 16) rows *= 2;
+    const int per_row = (batch + rows - 1) / rows;
+    dim3 grid(blocks_x, (unsigned)((batch + per_row - 1) / per_row));
+    const size_t image_bytes = (size_t)plan->erp_h * plan->erp_w * 3;
+    const bool aligned = (image_bytes % 8 == 0) && (reinterpret_cast<uintptr_t>(erp) % 8 == 0);
+    if (aligned)
+        k_erp2ico<true><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
+                                                                    plan->tangent_pixels, plan->erp_h, plan->erp_w, batch,
+                                                                    per_row, full_face_image);
+    else
+        k_erp2ico<false><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
+                                                                     plan->tangent_pixels, plan->erp_h, plan->erp_w, batch,
+                                                                     per_row, full_face_image);
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
 }
@@ -121,16 +196,34 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // ------------------------------------------------------------------------------------------------
 // stage 2+3: tangent flows -> ERP flow
 // ------------------------------------------------------------------------------------------------
+#define TIF_STITCH_THREADS 128
+// rows whose sin(colatitude) is below this use the float64 end-point lift when the blend samples the
+// images (normwarp): next to the poles the faces disagree by hundreds of ERP pixels, and the photometric
+// weights turn an end-point error of 1e-4 px into a flow error above the 1e-3 px tolerance
+#define TIF_POLAR_SIN 0.1f
+
 struct FaceConst {          // per-face constants of the end-point lift, staged in shared memory
-    double theta0, sin_phi0, cos_phi0;
+    double sin_phi0, cos_phi0;
     double xmin, ymax;
-    double inv_p2g_x, inv_p2g_y;
+    double kx, ky;              // 1 / pixel2gnomonic ratios (gnomonic_projection.py:188-194)
+    double ky_sin, ky_cos;      // ky * sin(phi0), ky * cos(phi0)
     int pix_offset;
     int pad;
 };
 
-// atan(q) for q in [0,1]: q + q*s*P(s), s = q*q; max abs error 3e-8 (float32 Horner, double final add)
-__device__ __forceinline__ double atan_unit(float q) {
+// atan(y/x) for x > 0 and |y| <= 0.4143 x: q + q s P(s); max abs error 2.3e-8
+__device__ __forceinline__ float atan_small(float y, float x) {
+    const float q = y * __frcp_rn(x);
+    const float s = q * q;
+    float r = 7.901539654e-02f;
+    r = fmaf(r, s, -1.382412463e-01f);
+    r = fmaf(r, s, 1.997184753e-01f);
+    r = fmaf(r, s, -3.333275616e-01f);
+    return fmaf(r, q * s, q);
+}
+
+// atan(q) for q in [0,1]: q + q s P(s); max abs error 3e-8 before the final float32 rounding
+__device__ __forceinline__ float atan_unit(float q) {
     const float s = q * q;
     float r = -1.602407545e-03f;
     r = fmaf(r, s, 1.002551895e-02f);
@@ -141,95 +234,168 @@ __device__ __forceinline__ double atan_unit(float q) {
     r = fmaf(r, s, -1.425546259e-01f);
     r = fmaf(r, s, 1.999762058e-01f);
     r = fmaf(r, s, -3.333326280e-01f);
-    return (double)q + (double)(r * (q * s));
+    return fmaf(r, q * s, q);
 }
 
-// atan2(y, x) in (-pi, pi]; float32 ratio + polynomial, double quadrant assembly
-__device__ __forceinline__ double atan2_mixed(float y, float x) {
+// atan2(y, x) in (-pi, pi].  The common case of the stitch (a small angle between the flow end point
+// and its source pixel) takes the short polynomial; everything else the full octant reduction.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
+    if (x > 0.0f && ay <= 0.4143f * x) return atan_small(y, x);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float q = mx > 0.0f ? mn / mx : 0.0f;
-    double r = atan_unit(q);
-    if (ay > ax) r = TIF_HALF_PI - r;
-    if (x < 0.0f) r = TIF_PI - r;
+    const float q = mx > 0.0f ? mn * __frcp_rn(mx) : 0.0f;
+    float r = atan_unit(q);
+    if (ay > ax) r = (float)TIF_HALF_PI - r;
+    if (x < 0.0f) r = (float)TIF_PI - r;
     return y < 0.0f ? -r : r;
 }
 
-struct Lifted {
-    float fu, fv;     // ERP flow of this face at this pixel
-    float tx, ty;     // ERP position of the flow end point (after the seam fix), for the normwarp sample
+struct SampleGeom {       // per (ERP pixel, accepting face): constant over the batch
+    double gx0, bz0, cy0;           // direction of the tangent pixel centre: gx, cos(phi0) - gy sin(phi0), sin(phi0) + gy cos(phi0)
+    double kx, ky_sin, ky_cos;
+    float gx0f, bz0f, cy0f, kxf, ky_sinf, ky_cosf;
+    float sin_d, cos_d;             // sin / cos of (theta_src - theta0)
+    int tpix;
+    int face;
+    float mult;
 };
 
-// End point of one accepted sample: projection_icosahedron.py:336-366.
-//   pixel2gnomonic (gnomonic_projection.py:186-194), reverse_gnomonic_projection (:76-85) written as
-//   theta = theta0 + atan2(gx, cos(phi0) - gy sin(phi0)), colatitude = atan2(hypot(.,.), sin(phi0) + gy cos(phi0))
-//   (algebraically identical: sin c = rho cos c; better conditioned at the poles than arcsin),
-//   sph_coord_modulo + sph2erp(modulo) (spherical_coordinates.py:237-238,59-60,122-124), seam fix (:350-361).
-// The direction vector is formed in float64 (cancellation at the poles), the two arctangents in
-// float32 with a float64 quadrant sum: <= 1.5e-7 rad, i.e. < 1e-4 px up to 4096-wide ERP.
-__device__ __forceinline__ Lifted lift_endpoint(const FaceConst& F, int ix, int iy, float u, float v, double theta_src,
-                                                int r, int c, int erp_h, int erp_w, bool wrap_around) {
-    const double px = (double)ix + (double)u;
-    const double py = (double)iy + (double)v;
-    const double gx = px * F.inv_p2g_x + F.xmin;
-    const double gy = F.ymax - py * F.inv_p2g_y;
-    const double bz = F.cos_phi0 - gy * F.sin_phi0;
-    const double cy = F.sin_phi0 + gy * F.cos_phi0;
-    const float a32 = (float)gx, b32 = (float)bz, c32 = (float)cy;
-    const double dtheta = atan2_mixed(a32, b32);
-    const float h32 = sqrtf(a32 * a32 + b32 * b32);
-    const double colat = atan2_mixed(h32, c32);           // [0, pi]
-    // theta_t wrapped into [-pi, pi) (np.remainder(theta + pi, 2 pi) - pi)
-    double tt = F.theta0 + dtheta;
-    tt -= TIF_TWO_PI * floor((tt + TIF_PI) * (1.0 / TIF_TWO_PI));
-    double d = tt - theta_src;
-    if (wrap_around) {
-        if (d > TIF_PI && theta_src < 0.0 && tt > 0.0) d -= TIF_TWO_PI;
-        else if (d < -TIF_PI && theta_src > 0.0 && tt < 0.0) d += TIF_TWO_PI;
+struct Lifted {
+    float fu, fv;         // ERP flow of this face at this pixel
+    int xi, yi;           // floor(fu), floor(fv)
+    float fx, fy;         // fu - floor(fu), fv - floor(fv): bilinear fractions of the end point
+};
+
+// floor / fraction without the XU pipe (|x| < 2^22): round to nearest with the 1.5*2^23 trick, then fix down
+__device__ __forceinline__ void split_floor(float x, int& xi, float& frac) {
+    const float y = x + 12582912.0f;
+    xi = __float_as_int(y) - 0x4B400000;
+    frac = x - (y - 12582912.0f);
+    if (frac < 0.0f) {
+        frac += 1.0f;
+        xi -= 1;
     }
+}
+
+// End point of one accepted sample, projection_icosahedron.py:336-366, written as two rotations:
+//   direction of the end point  d = (gx, cos(phi0) - gy sin(phi0), sin(phi0) + gy cos(phi0))
+//       [reverse_gnomonic_projection (gnomonic_projection.py:76-85) with sin c = rho cos c divided out;
+//        gx, gy = pixel2gnomonic (:186-194) of (ix + u, iy + v)]
+//   delta_theta  = atan2 of (d.x, d.y) rotated back by (theta_src - theta0)      -> u = delta_theta * W / 2 pi
+//   delta_colat  = atan2 of (hypot(d.x, d.y), d.z) rotated back by colat_src     -> v = delta_colat * H / pi
+// Both arctangents see the small angle between end point and source pixel, so float32 keeps a relative
+// precision of 1e-7 on the flow itself.  delta_theta in (-pi, pi] is the reference's flow after its seam
+// fix (:350-361); without wrap_around the reference leaves theta_t wrapped into [-pi, pi) instead
+// (spherical_coordinates.py:237,59), restored at the end.
+//
+// PRECISE = false: float32 throughout (end point away from the poles).
+// PRECISE = true : direction and rotations in float64, CUDA's double atan2/sqrt (rows next to the poles,
+//                  where d.x, d.y cancel and a rotation by a float32 sine loses the small polar radius).
+template <bool PRECISE>
+__device__ __forceinline__ Lifted lift_endpoint(const SampleGeom& G, float u, float v, float sin_colat_src,
+                                                float cos_colat_src, double sin_cs64, double cos_cs64, double sin_d64,
+                                                double cos_d64, float theta_src, float u_scale, float v_scale,
+                                                double u_scale64, double v_scale64, bool wrap_around) {
     Lifted o;
-    const double fu = d * ((double)erp_w * (1.0 / TIF_TWO_PI));
-    const double ty = colat * ((double)erp_h * (1.0 / TIF_PI)) - 0.5;
-    o.fu = (float)fu;
-    o.fv = (float)(ty - (double)r);
-    o.tx = (float)(fu + (double)c);
-    o.ty = (float)ty;
+    if (PRECISE) {
+        const double a = fma((double)u, G.kx, G.gx0);
+        const double b = fma((double)v, G.ky_sin, G.bz0);
+        const double c = fma(-(double)v, G.ky_cos, G.cy0);
+        const double xr = fma(b, cos_d64, a * sin_d64);
+        const double yr = fma(a, cos_d64, -b * sin_d64);
+        double dtheta = atan2(yr, xr);
+        const double h = sqrt(fma(xr, xr, yr * yr));
+        const double xc = fma(c, cos_cs64, h * sin_cs64);
+        const double yc = fma(h, cos_cs64, -c * sin_cs64);
+        const double dcolat = atan2(yc, xc);
+        if (!wrap_around) {
+            const double tt = (double)theta_src + dtheta;
+            if (tt >= TIF_PI) dtheta -= TIF_TWO_PI;
+            else if (tt < -TIF_PI) dtheta += TIF_TWO_PI;
+        }
+        const double fu = dtheta * u_scale64, fv = dcolat * v_scale64;
+        const double fiu = floor(fu), fiv = floor(fv);
+        o.fu = (float)fu;
+        o.fv = (float)fv;
+        o.xi = (int)fiu;
+        o.yi = (int)fiv;
+        o.fx = (float)(fu - fiu);
+        o.fy = (float)(fv - fiv);
+        return o;
+    }
+    const float a = fmaf(u, G.kxf, G.gx0f);
+    const float b = fmaf(v, G.ky_sinf, G.bz0f);
+    const float c = fmaf(-v, G.ky_cosf, G.cy0f);
+    const float xr = fmaf(b, G.cos_d, a * G.sin_d);
+    const float yr = fmaf(a, G.cos_d, -b * G.sin_d);
+    float dtheta = atan2_fast(yr, xr);
+    const float h = sqrtf(fmaf(xr, xr, yr * yr));
+    const float xc = fmaf(c, cos_colat_src, h * sin_colat_src);
+    const float yc = fmaf(h, cos_colat_src, -c * sin_colat_src);
+    const float dcolat = atan2_fast(yc, xc);
+    if (!wrap_around) {
+        const float tt = theta_src + dtheta;
+        if (tt >= (float)TIF_PI) dtheta -= (float)TIF_TWO_PI;
+        else if (tt < -(float)TIF_PI) dtheta += (float)TIF_TWO_PI;
+    }
+    o.fu = dtheta * u_scale;
+    o.fv = dcolat * v_scale;
+    split_floor(o.fu, o.xi, o.fx);
+    split_floor(o.fv, o.yi, o.fy);
     return o;
 }
 
-// mean over channels of |bilinear(tar, (ty,tx)) - src[r,c]| with scipy mode='constant', cval=255
+// byte k of w as float via the 2^23 mantissa trick (PRMT + FADD, both full rate; I2F would use the XU pipe)
+__device__ __forceinline__ float byte_f(uint32_t w, unsigned k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | k)) - 8388608.0f;
+}
+
+// sum over channels of |bilinear(tar, end point) - src[r,c]| with scipy mode='constant', cval=255
 // (projection.py:52-55): any coordinate outside [0, n-1] reads 255 outright.
-__device__ __forceinline__ float warp_error_sum(const uint8_t* __restrict__ tar, const uint8_t* __restrict__ src_px,
-                                                float tx, float ty, int erp_h, int erp_w) {
+__device__ __forceinline__ float warp_error_sum(const uint8_t* __restrict__ tar, bool tail_image, float s0, float s1,
+                                                float s2, const Lifted& L, int r, int c, int erp_h, int erp_w) {
+    int x0 = c + L.xi, y0 = r + L.yi;
+    float fx = L.fx, fy = L.fy;
     float t0, t1, t2;
-    if (tx < 0.0f || tx > (float)(erp_w - 1) || ty < 0.0f || ty > (float)(erp_h - 1)) {
+    // inside iff 0 <= x0 + fx <= W-1 and 0 <= y0 + fy <= H-1
+    const bool inside = x0 >= 0 && y0 >= 0 && (x0 < erp_w - 1 || (x0 == erp_w - 1 && fx == 0.0f)) &&
+                        (y0 < erp_h - 1 || (y0 == erp_h - 1 && fy == 0.0f));
+    if (!inside) {
         t0 = t1 = t2 = 255.0f;
     } else {
-        float x0 = floorf(tx), y0 = floorf(ty);
-        x0 = fminf(x0, (float)(erp_w - 2));
-        y0 = fminf(y0, (float)(erp_h - 2));
-        const float fx = tx - x0, fy = ty - y0;
+        if (x0 == erp_w - 1) { x0 = erp_w - 2; fx = 1.0f; }
+        if (y0 == erp_h - 1) { y0 = erp_h - 2; fy = 1.0f; }
         const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
-        const uint8_t* r0 = tar + ((size_t)(int)y0 * erp_w + (int)x0) * 3;
+        const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
+        const uint8_t* r0 = tar + ((size_t)y0 * erp_w + x0) * 3;
         const uint8_t* r1 = r0 + (size_t)erp_w * 3;
-        t0 = bilinear_f32(__ldg(r0 + 0), __ldg(r0 + 3), __ldg(r1 + 0), __ldg(r1 + 3), wx0, fx, wy0, fy);
-        t1 = bilinear_f32(__ldg(r0 + 1), __ldg(r0 + 4), __ldg(r1 + 1), __ldg(r1 + 4), wx0, fx, wy0, fy);
-        t2 = bilinear_f32(__ldg(r0 + 2), __ldg(r0 + 5), __ldg(r1 + 2), __ldg(r1 + 5), wx0, fx, wy0, fy);
+        uint32_t lo0, hi0, lo1, hi1;
+        if (tail_image && y0 == erp_h - 2 && x0 >= erp_w - 8) {     // wide loads could leave the buffer
+            load_tap_pair_bytes(r0, lo0, hi0);
+            load_tap_pair_bytes(r1, lo1, hi1);
+        } else {
+            load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7), lo0, hi0);
+            load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 7), lo1, hi1);
+        }
+        t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
+        t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
+        t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
     }
-    return fabsf(t0 - (float)src_px[0]) + fabsf(t1 - (float)src_px[1]) + fabsf(t2 - (float)src_px[2]);
+    return fabsf(t0 - s0) + fabsf(t1 - s1) + fabsf(t2 - s2);
 }
 
 __device__ __forceinline__ void load_face_consts(FaceConst* sh, const TifFace* __restrict__ faces, int n_faces) {
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
         const TifFace& F = faces[f];
         FaceConst fc;
-        fc.theta0 = F.theta0;
         fc.sin_phi0 = F.sin_phi0;
         fc.cos_phi0 = F.cos_phi0;
         fc.xmin = F.xmin;
         fc.ymax = F.ymax;
-        fc.inv_p2g_x = 1.0 / F.p2g_x;
-        fc.inv_p2g_y = 1.0 / F.p2g_y;
+        fc.kx = 1.0 / F.p2g_x;
+        fc.ky = 1.0 / F.p2g_y;
+        fc.ky_sin = fc.ky * F.sin_phi0;
+        fc.ky_cos = fc.ky * F.cos_phi0;
         fc.pix_offset = F.pix_offset;
         fc.pad = 0;
         sh[f] = fc;
@@ -238,17 +404,22 @@ __device__ __forceinline__ void load_face_consts(FaceConst* sh, const TifFace* _
 
 // MODE 0: straightforward blend.  MODE 1: normwarp pass A (face-global warp-error sums only).
 // MODE 2: normwarp pass B (weights from the sums of pass A, blend).
-template <int MODE>
-__global__ void __launch_bounds__(256)
+// POLAR selects the float64 end-point lift; it is launched on the polar row bands only (normwarp).
+// Pixels are addressed through two segments: [seg0_start, seg0_start + seg0_len) then [seg1_start, ...).
+template <int MODE, bool POLAR>
+__global__ void __launch_bounds__(TIF_STITCH_THREADS)
 k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const double* __restrict__ col_theta,
+         const float2* __restrict__ row_sc, const float2* __restrict__ col_sc,
+         const double2* __restrict__ row_sc64, const double2* __restrict__ col_sc64,
          const double* __restrict__ face_mult_sum, const float* __restrict__ tflow,
          const uint8_t* __restrict__ erp_src, const uint8_t* __restrict__ erp_tar,
          unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, float* __restrict__ out,
-         int erp_h, int erp_w, int tangent_w, int64_t n_tangent, int batch, int wrap_around) {
+         int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around, int seg0_start, int seg0_len,
+         int seg1_start, int seg_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FaceConst* sh_face = reinterpret_cast<FaceConst*>(smem_raw);
-    // MODE 1: per-block partial sums; MODE 2: 1 / face-global mean
+    // MODE 1: per-block partial sums; MODE 2: 1 / (3 * face-global mean)
     unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_face + n_faces);
     float* sh_inv_mean = reinterpret_cast<float*>(sh_face + n_faces);
 
@@ -264,52 +435,114 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
                 const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
                 const double mean = total / (3.0 * face_mult_sum[f]);
-                inv = (float)(1.0 / mean);
+                inv = (float)(1.0 / (3.0 * mean));
             }
             sh_inv_mean[i] = inv;
         }
     }
     __syncthreads();
 
-    const int64_t n_pix = (int64_t)erp_h * erp_w;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = pix < n_pix;
+    const int n_pix = erp_h * erp_w;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < seg_total;
+    const int pix = !live ? 0 : (idx < seg0_len ? seg0_start + idx : seg1_start + (idx - seg0_len));
     int cnt = 0, r = 0, c = 0;
-    double theta_src = 0.0;
+    float theta_src = 0.0f, sin_cs = 0.0f, cos_cs = 1.0f;
+    double sin_cs64 = 0.0, cos_cs64 = 1.0;
     if (live) {
         cnt = s2_count[pix];
-        r = (int)(pix / erp_w);
-        c = (int)(pix - (int64_t)r * erp_w);
-        // sph_coord_modulo of the source longitude (projection_icosahedron.py:353)
-        theta_src = col_theta[c];
-        theta_src -= TIF_TWO_PI * floor((theta_src + TIF_PI) * (1.0 / TIF_TWO_PI));
+        r = pix / erp_w;
+        c = pix - r * erp_w;
+        theta_src = (float)col_theta[c];
+        const float2 rs = row_sc[r];        // (sin phi, cos phi) of the source row = (cos, sin) of its colatitude
+        cos_cs = rs.x;
+        sin_cs = rs.y;
     }
+    const bool polar = POLAR;
+    if (polar && live) {
+        const double2 rs = row_sc64[r];
+        cos_cs64 = rs.x;
+        sin_cs64 = rs.y;
+    }
+    const double u_scale64 = (double)erp_w / TIF_TWO_PI, v_scale64 = (double)erp_h / TIF_PI;
+    const float u_scale = (float)u_scale64, v_scale = (float)v_scale64;
     float acc_u[TIF_BATCH_CHUNK], acc_v[TIF_BATCH_CHUNK], acc_w[TIF_BATCH_CHUNK];
+    float sp[TIF_BATCH_CHUNK][3];
 #pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+        sp[bb][0] = sp[bb][1] = sp[bb][2] = 0.0f;
+    }
     const size_t image_bytes = (size_t)n_pix * 3;
+    if (MODE != 0 && live) {
+#pragma unroll
+        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+            if (b0 + bb < batch) {
+                const uint8_t* q = erp_src + (size_t)(b0 + bb) * image_bytes + (size_t)pix * 3;
+                sp[bb][0] = (float)__ldg(q);
+                sp[bb][1] = (float)__ldg(q + 1);
+                sp[bb][2] = (float)__ldg(q + 2);
+            }
+        }
+    }
 
     const int max_cnt = (MODE == 1) ? __reduce_max_sync(0xffffffffu, cnt) : cnt;
+    uint32_t e_next = (cnt > 0) ? __ldg(s2_entries + pix) : 0u;   // cnt == 0 for dead lanes
     for (int k = 0; k < max_cnt; ++k) {
         const bool has = k < cnt;
-        uint32_t e = 0;
-        if (has) e = __ldg(s2_entries + (int64_t)k * n_pix + pix);
-        const int f = (int)TIF_E_FACE(e);
-        const FaceConst& F = sh_face[f];
-        const int ix = (int)TIF_E_IX(e), iy = (int)TIF_E_IY(e);
-        const int64_t tpix = (int64_t)F.pix_offset + (int64_t)iy * tangent_w + ix;
+        const uint32_t e = e_next;
+        if (k + 1 < cnt) e_next = __ldg(s2_entries + (size_t)(k + 1) * n_pix + pix);     // prefetch the next entry
+        SampleGeom G;
+        double sin_d64 = 0.0, cos_d64 = 1.0;
+        {
+            const int f = (int)TIF_E_FACE(e);
+            const FaceConst& F = sh_face[f];
+            const int ix = (int)TIF_E_IX(e), iy = (int)TIF_E_IY(e);
+            // pixel2gnomonic of the tangent pixel centre; the flow moves it by (u kx, -v ky)
+            G.gx0 = fma((double)ix, F.kx, F.xmin);
+            const double gy0 = fma(-(double)iy, F.ky, F.ymax);
+            G.bz0 = fma(-gy0, F.sin_phi0, F.cos_phi0);
+            G.cy0 = fma(gy0, F.cos_phi0, F.sin_phi0);
+            G.kx = F.kx;
+            G.ky_sin = F.ky_sin;
+            G.ky_cos = F.ky_cos;
+            G.gx0f = (float)G.gx0;
+            G.bz0f = (float)G.bz0;
+            G.cy0f = (float)G.cy0;
+            G.kxf = (float)F.kx;
+            G.ky_sinf = (float)F.ky_sin;
+            G.ky_cosf = (float)F.ky_cos;
+            G.tpix = F.pix_offset + iy * tangent_w + ix;
+            G.face = f;
+            G.mult = (float)TIF_E_MULT(e);
+            const float2 cs = has ? __ldg(col_sc + f * erp_w + c) : make_float2(0.0f, 1.0f);
+            G.sin_d = cs.x;
+            G.cos_d = cs.y;
+            if (polar && has) {
+                const double2 cs64 = __ldg(col_sc64 + f * erp_w + c);
+                sin_d64 = cs64.x;
+                cos_d64 = cs64.y;
+            }
+        }
+        const int f = G.face;
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
             const int b = b0 + bb;
             if (b >= batch) break;
             float dsum = 0.0f;
             Lifted L;
+            L.fu = L.fv = 0.0f;
             if (has) {
-                const float2 uv = __ldg(reinterpret_cast<const float2*>(tflow) + (size_t)b * n_tangent + tpix);
-                L = lift_endpoint(F, ix, iy, uv.x, uv.y, theta_src, r, c, erp_h, erp_w, wrap_around != 0);
+                const float2 uv = __ldg(reinterpret_cast<const float2*>(tflow) + (size_t)b * n_tangent + G.tpix);
+                if (polar)
+                    L = lift_endpoint<true>(G, uv.x, uv.y, sin_cs, cos_cs, sin_cs64, cos_cs64, sin_d64, cos_d64, theta_src,
+                                            u_scale, v_scale, u_scale64, v_scale64, wrap_around != 0);
+                else
+                    L = lift_endpoint<false>(G, uv.x, uv.y, sin_cs, cos_cs, 0.0, 1.0, 0.0, 1.0, theta_src, u_scale, v_scale,
+                                             0.0, 0.0, wrap_around != 0);
                 if (MODE != 0)
-                    dsum = warp_error_sum(erp_tar + (size_t)b * image_bytes, erp_src + (size_t)b * image_bytes + (size_t)pix * 3,
-                                          L.tx, L.ty, erp_h, erp_w);
+                    dsum = warp_error_sum(erp_tar + (size_t)b * image_bytes, b == batch - 1, sp[bb][0], sp[bb][1], sp[bb][2],
+                                          L, r, c, erp_h, erp_w);
             }
             if (MODE == 0) {
                 if (has) {
@@ -321,7 +554,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // face-global sum of |diff| (x multiplicity) as order-independent fixed point.
                 // Neighbouring pixels almost always see the same face at the same k: reduce across
                 // the warp first and issue one shared-memory atomic; otherwise one per lane.
-                const unsigned fixed = has ? (unsigned)(dsum * (float)TIF_E_MULT(e) * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
+                const unsigned fixed = has ? (unsigned)(dsum * G.mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
                 const int f0 = __shfl_sync(0xffffffffu, f, 0);
                 const bool uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
                 if (uniform) {
@@ -336,9 +569,10 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             } else {
                 if (has) {
                     // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
-                    const float w = __expf(-(dsum * (1.0f / 3.0f)) * sh_inv_mean[bb * n_faces + f]);
-                    acc_u[bb] += L.fu * w;
-                    acc_v[bb] += L.fv * w;
+                    const float x = -dsum * sh_inv_mean[bb * n_faces + f];
+                    const float w = polar ? expf(x) : __expf(x);
+                    acc_u[bb] = fmaf(L.fu, w, acc_u[bb]);
+                    acc_v[bb] = fmaf(L.fv, w, acc_v[bb]);
                     acc_w[bb] += w;
                 }
             }
@@ -362,8 +596,9 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         if (b >= batch) break;
         float u = acc_u[bb], v = acc_v[bb];
         if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393
-            u = u / acc_w[bb];
-            v = v / acc_w[bb];
+            const float inv = 1.0f / acc_w[bb];
+            u *= inv;
+            v *= inv;
         }
         if (wrap_around) {            // flow_postproc.erp_of_wraparound, flow_postproc.py:28-42
             if (c < split) {
@@ -398,25 +633,43 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         return TIF_ERR_INVALID_ARG;
     }
     cudaStream_t stream = (cudaStream_t)stream_v;
-    const int threads = 256;
-    const int64_t n_pix = (int64_t)plan->erp_h * plan->erp_w;
-    dim3 grid((unsigned)((n_pix + threads - 1) / threads), (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK));
+    const int threads = TIF_STITCH_THREADS;
+    const int h = plan->erp_h, w = plan->erp_w;
+    const int n_pix = h * w;
+    const unsigned by = (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK);
     const size_t smem = sizeof(FaceConst) * plan->n_faces + sizeof(unsigned long long) * TIF_BATCH_CHUNK * plan->n_faces;
 #define STITCH_ARGS                                                                                                 \
-    plan->d_faces, plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_col_theta, plan->d_face_mult_sum,   \
-        tangent_flow, erp_src, erp_tar, (unsigned long long*)scratch, erp_flow, plan->erp_h, plan->erp_w,           \
-        plan->tangent_w, plan->tangent_pixels, batch, wrap_around
+    plan->d_faces, plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_col_theta, plan->d_row_sc,         \
+        plan->d_col_sc, plan->d_row_sc64, plan->d_col_sc64, plan->d_face_mult_sum, tangent_flow, erp_src, erp_tar, \
+        (unsigned long long*)scratch, erp_flow, h, w, plan->tangent_w, (int)plan->tangent_pixels, batch, wrap_around
+#define STITCH_GRID(n) dim3((unsigned)(((n) + threads - 1) / threads), by)
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
-        k_stitch<0><<<grid, threads, smem, stream>>>(STITCH_ARGS);
+        k_stitch<0, false><<<STITCH_GRID(n_pix), threads, smem, stream>>>(STITCH_ARGS, 0, n_pix, 0, n_pix);
     } else {
+        // rows with sin(colatitude) < TIF_POLAR_SIN at either pole take the float64 lift (separate launch so
+        // that its register footprint does not lower the occupancy of the bulk)
+        int polar_rows = 0;
+        while (polar_rows < h / 2 && sin(((double)polar_rows + 0.5) * TIF_PI / (double)h) < (double)TIF_POLAR_SIN) ++polar_rows;
+        const int n_polar = 2 * polar_rows * w, n_bulk = n_pix - n_polar;
         if (pass_mask & 1) {
             TIF_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)tif_ico2erp_scratch_bytes(plan, batch, blend), stream));
-            k_stitch<1><<<grid, threads, smem, stream>>>(STITCH_ARGS);
+            if (n_bulk > 0)
+                k_stitch<1, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
+            if (n_polar > 0)
+                k_stitch<1, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
+                                                                                   (h - polar_rows) * w, n_polar);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
-        if (pass_mask & 2) k_stitch<2><<<grid, threads, smem, stream>>>(STITCH_ARGS);
+        if (pass_mask & 2) {
+            if (n_bulk > 0)
+                k_stitch<2, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
+            if (n_polar > 0)
+                k_stitch<2, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
+                                                                                   (h - polar_rows) * w, n_polar);
+        }
     }
 #undef STITCH_ARGS
+#undef STITCH_GRID
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
 }

@@ -242,6 +242,10 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_s2_count);
     cudaFree(plan->d_s2_entries);
     cudaFree(plan->d_col_theta);
+    cudaFree(plan->d_row_sc);
+    cudaFree(plan->d_col_sc);
+    cudaFree(plan->d_row_sc64);
+    cudaFree(plan->d_col_sc64);
     cudaFree(plan->d_face_mult_sum);
     free(plan->h_faces);
     free(plan);
@@ -255,8 +259,6 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
             tif_plan_destroy(plan); \
             cudaFree(d_gx);         \
             cudaFree(d_gy);         \
-            cudaFree(d_rows);       \
-            cudaFree(d_cols);       \
             cudaFree(d_mark);       \
             cudaFree(d_status);     \
             cudaFree(d_msum);       \
@@ -310,7 +312,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     plan->h_faces = (TifFace*)malloc(sizeof(TifFace) * n_faces);
     memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
 
-    double *d_gx = nullptr, *d_gy = nullptr, *d_rows = nullptr, *d_cols = nullptr;
+    double *d_gx = nullptr, *d_gy = nullptr;
     uint8_t* d_mark = nullptr;
     int* d_status = nullptr;
     unsigned long long* d_msum = nullptr;
@@ -332,14 +334,18 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(dev_alloc(&plan->d_s2_count, n_erp, plan));
     PLAN_TRY(dev_alloc(&plan->d_col_theta, erp_w, plan));
     PLAN_TRY(dev_alloc(&plan->d_face_mult_sum, n_faces, plan));
+    PLAN_TRY(dev_alloc(&plan->d_row_sc, erp_h, plan));
+    PLAN_TRY(dev_alloc(&plan->d_col_sc, (size_t)n_faces * erp_w, plan));
+    PLAN_TRY(dev_alloc(&plan->d_row_sc64, erp_h, plan));
+    PLAN_TRY(dev_alloc(&plan->d_col_sc64, (size_t)n_faces * erp_w, plan));
+    double* d_rows = reinterpret_cast<double*>(plan->d_row_sc64);
+    double* d_cols = reinterpret_cast<double*>(plan->d_col_sc64);
     int64_t scratch_bytes = 0;
     {
         TifPlan tmp;   // scratch is not part of the plan footprint
         tmp.device_bytes = 0;
         PLAN_TRY(dev_alloc(&d_gx, (size_t)n_faces * tangent_w, &tmp));
         PLAN_TRY(dev_alloc(&d_gy, n_rows, &tmp));
-        PLAN_TRY(dev_alloc(&d_rows, (size_t)erp_h * 2, &tmp));
-        PLAN_TRY(dev_alloc(&d_cols, (size_t)n_faces * erp_w * 2, &tmp));
         PLAN_TRY(dev_alloc(&d_mark, n_tangent, &tmp));
         PLAN_TRY(dev_alloc(&d_status, 2, &tmp));
         PLAN_TRY(dev_alloc(&d_msum, n_faces + 1, &tmp));
@@ -357,7 +363,18 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_mark, 0, n_tangent, stream), "memset"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), stream), "memset"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, (n_faces + 1) * sizeof(unsigned long long), stream), "memset"));
-    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan upload"));   // h_row_face is pageable
+    {
+        // float32 copies of the separable tables for the execute kernels (rotation of the end point)
+        const size_t n_row = (size_t)erp_h, n_col = (size_t)n_faces * erp_w;
+        float2* h_f = (float2*)malloc(sizeof(float2) * (n_row + n_col));
+        for (size_t i = 0; i < n_row; ++i) h_f[i] = make_float2((float)tables->row_sincos[2 * i], (float)tables->row_sincos[2 * i + 1]);
+        for (size_t i = 0; i < n_col; ++i) h_f[n_row + i] = make_float2((float)tables->col_sincos[2 * i], (float)tables->col_sincos[2 * i + 1]);
+        cudaError_t ea = cudaMemcpyAsync(plan->d_row_sc, h_f, sizeof(float2) * n_row, cudaMemcpyHostToDevice, stream);
+        cudaError_t eb = cudaMemcpyAsync(plan->d_col_sc, h_f + n_row, sizeof(float2) * n_col, cudaMemcpyHostToDevice, stream);
+        cudaError_t ec = cudaStreamSynchronize(stream);   // h_f and h_row_face are pageable
+        free(h_f);
+        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : (eb != cudaSuccess ? eb : ec), "plan upload"));
+    }
     free(h_row_face);
 
     const int threads = 256;
@@ -414,8 +431,6 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
 
     cudaFree(d_gx);
     cudaFree(d_gy);
-    cudaFree(d_rows);
-    cudaFree(d_cols);
     cudaFree(d_mark);
     cudaFree(d_status);
     cudaFree(d_msum);
