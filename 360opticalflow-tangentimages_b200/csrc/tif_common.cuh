@@ -27,7 +27,8 @@
 
 // fixed-point scale of the normwarp face-mean accumulation (integer sums are order-independent,
 // which keeps the blend deterministic run to run)
-#define TIF_NW_FIXED_SCALE 32768.0f
+// 128 threads x 765 x 7 x 1024 < 2^32: a block's partial sum fits a native 32-bit shared atomic
+#define TIF_NW_FIXED_SCALE 1024.0f
 
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;
@@ -48,6 +49,7 @@ struct TifPlan {
     // stage 2: per ERP pixel
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
+    uint32_t* d_s2_offset;         // [H*W] exclusive prefix sum of d_s2_count: first slot of a pixel's samples
     double* d_col_theta;           // [W] theta of every ERP column
     float2* d_row_sc;              // [H] (sin phi_r, cos phi_r) in float32
     float2* d_col_sc;              // [F][W] (sin, cos)(theta_c - theta0_f) in float32

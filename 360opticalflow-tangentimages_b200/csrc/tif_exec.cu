@@ -61,19 +61,33 @@ __device__ __forceinline__ uint8_t round_u8_guarded(float t, float p00, float p0
 // address.  They are fetched with one or two aligned 8-byte loads and funnel-shifted into place
 // instead of six byte loads.  `o` = address & 7.  The caller guarantees that 16 bytes from the aligned
 // address are readable.
-__device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ p, unsigned o,
-                                              uint32_t& lo /* R0 G0 B0 R1 */, uint32_t& hi /* G1 B1 . . */) {
+struct RawPair {
+    uint2 v0, v1;
+};
+
+__device__ __forceinline__ RawPair load_raw_pair(const uint8_t* __restrict__ p, unsigned o) {
     const uint2* q = reinterpret_cast<const uint2*>(p - o);
-    const uint2 v0 = __ldg(q);
-    uint2 v1 = make_uint2(0u, 0u);
-    if (o > 2) v1 = __ldg(q + 1);                                // bytes o..o+5 leave the first 8 only then
+    RawPair r;
+    r.v0 = __ldg(q);
+    r.v1 = make_uint2(0u, 0u);
+    if (o > 2) r.v1 = __ldg(q + 1);                              // bytes o..o+5 leave the first 8 only then
+    return r;
+}
+
+__device__ __forceinline__ void align_pair(const RawPair& r, unsigned o, uint32_t& lo /* R0 G0 B0 R1 */,
+                                           uint32_t& hi /* G1 B1 . . */) {
     const bool up = o >= 4;
-    const uint32_t wa = up ? v0.y : v0.x;
-    const uint32_t wb = up ? v1.x : v0.y;
-    const uint32_t wc = up ? v1.y : v1.x;
+    const uint32_t wa = up ? r.v0.y : r.v0.x;
+    const uint32_t wb = up ? r.v1.x : r.v0.y;
+    const uint32_t wc = up ? r.v1.y : r.v1.x;
     const unsigned sh = (o & 3) * 8;
     lo = __funnelshift_r(wa, wb, sh);
     hi = __funnelshift_r(wb, wc, sh);
+}
+
+__device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ p, unsigned o, uint32_t& lo, uint32_t& hi) {
+    const RawPair r = load_raw_pair(p, o);
+    align_pair(r, o, lo, hi);
 }
 
 __device__ __forceinline__ void load_tap_pair_bytes(const uint8_t* __restrict__ p, uint32_t& lo, uint32_t& hi) {
@@ -98,6 +112,22 @@ __device__ __forceinline__ uint32_t fix_bilinear(uint32_t p00, uint32_t p01, uin
 
 __device__ __forceinline__ bool fix_undecided(uint32_t acc) {
     return ((acc + TIF_FIX_GUARD) & 0x00ffffffu) < 2u * TIF_FIX_GUARD;
+}
+
+// one RGBA output pixel from the two aligned tap pairs (R: bytes 0,3 of lo; G: byte 1 of lo, byte 0 of hi;
+// B: byte 2 of lo, byte 1 of hi)
+__device__ __forceinline__ uint32_t erp2ico_pixel(uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1, uint32_t w00,
+                                                  uint32_t w01, uint32_t w10, uint32_t w11, const double2& fr) {
+    uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
+    uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
+    uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
+    if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
+        ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
+        ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
+        ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
+    }
+    // top bytes -> R | G<<8 | B<<16 | 255<<24
+    return __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
 }
 
 template <bool ALIGNED>
@@ -132,36 +162,40 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
     // The wide loads may touch up to 15 bytes past the second tap pair; only a tap at the very end of an
     // image could leave the buffer, and only in the last image: those few pixels use byte loads.
     const bool tail = tap + row_bytes + 16 > image_bytes;
-    unsigned o0 = 0, o1 = 0;
-    if (ALIGNED) {      // image stride and base are multiples of 8: the byte phase is the same for every image
-        o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
-        o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
-    }
-#pragma unroll 2
-    for (int b = b_begin; b < b_end; ++b, r0 += image_bytes, o4 += n_pix) {
-        uint32_t lo0, hi0, lo1, hi1;
-        if (tail) {
+    if (tail) {
+        for (int b = b_begin; b < b_end; ++b, r0 += image_bytes, o4 += n_pix) {
+            uint32_t lo0, hi0, lo1, hi1;
             load_tap_pair_bytes(r0, lo0, hi0);
             load_tap_pair_bytes(r0 + row_bytes, lo1, hi1);
-        } else {
-            if (!ALIGNED) {
-                o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
-                o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
+            *o4 = erp2ico_pixel(lo0, hi0, lo1, hi1, w00, w01, w10, w11, fr);
+        }
+        return;
+    }
+    unsigned o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
+    unsigned o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
+    // the kernel is latency bound (taps are L1/L2 hits, not streams): keep the raw words of the next image in
+    // flight while the current one is blended
+    RawPair c0 = load_raw_pair(r0, o0), c1 = load_raw_pair(r0 + row_bytes, o1);
+    for (int b = b_begin; b < b_end; ++b, o4 += n_pix) {
+        RawPair n0 = c0, n1 = c1;
+        unsigned no0 = o0, no1 = o1;
+        r0 += image_bytes;
+        if (b + 1 < b_end) {
+            if (!ALIGNED) {     // image stride not a multiple of 8: the byte phase changes per image
+                no0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
+                no1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
             }
-            load_tap_pair(r0, o0, lo0, hi0);
-            load_tap_pair(r0 + row_bytes, o1, lo1, hi1);
+            n0 = load_raw_pair(r0, no0);
+            n1 = load_raw_pair(r0 + row_bytes, no1);
         }
-        // R: bytes 0,3 of lo;  G: byte 1 of lo, byte 0 of hi;  B: byte 2 of lo, byte 1 of hi
-        uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
-        uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
-        uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
-        if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
-            ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
-            ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
-            ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
-        }
-        // top bytes -> R | G<<8 | B<<16 | 255<<24
-        *o4 = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
+        uint32_t lo0, hi0, lo1, hi1;
+        align_pair(c0, o0, lo0, hi0);
+        align_pair(c1, o1, lo1, hi1);
+        *o4 = erp2ico_pixel(lo0, hi0, lo1, hi1, w00, w01, w10, w11, fr);
+        c0 = n0;
+        c1 = n1;
+        o0 = no0;
+        o1 = no1;
     }
 }
 
@@ -197,9 +231,10 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // stage 2+3: tangent flows -> ERP flow
 // ------------------------------------------------------------------------------------------------
 #define TIF_STITCH_THREADS 128
-// rows whose sin(colatitude) is below this use the float64 end-point lift when the blend samples the
-// images (normwarp): next to the poles the faces disagree by hundreds of ERP pixels, and the photometric
-// weights turn an end-point error of 1e-4 px into a flow error above the 1e-3 px tolerance
+// rows whose sin(colatitude) is below this use the float64 end-point lift: an end point next to the polar
+// axis needs the float64 products of the flow (the float32 local frame cancels there), and under normwarp
+// the faces disagree by hundreds of ERP pixels next to the poles, so the photometric weights turn an
+// end-point error of 1e-4 px into a flow error above the 1e-3 px tolerance
 #define TIF_POLAR_SIN 0.1f
 
 struct FaceConst {          // per-face constants of the end-point lift, staged in shared memory
@@ -212,8 +247,23 @@ struct FaceConst {          // per-face constants of the end-point lift, staged 
 };
 
 // atan(y/x) for x > 0 and |y| <= 0.4143 x: q + q s P(s); max abs error 2.3e-8
+// reciprocal for x in the normal range: MUFU.RCP + one Newton step (no denormal / range branches)
+__device__ __forceinline__ float rcp_newton(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+// sqrt for x > 0 in the normal range: MUFU.RSQ + one Newton step
+__device__ __forceinline__ float sqrt_newton(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float h = x * r;
+    return fmaf(0.5f * r, fmaf(-h, h, x), h);
+}
+
 __device__ __forceinline__ float atan_small(float y, float x) {
-    const float q = y * __frcp_rn(x);
+    const float q = y * rcp_newton(x);
     const float s = q * q;
     float r = 7.901539654e-02f;
     r = fmaf(r, s, -1.382412463e-01f);
@@ -243,7 +293,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     if (x > 0.0f && ay <= 0.4143f * x) return atan_small(y, x);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float q = mx > 0.0f ? mn * __frcp_rn(mx) : 0.0f;
+    const float q = mn * rcp_newton(fmaxf(mx, 1e-30f));
     float r = atan_unit(q);
     if (ay > ax) r = (float)TIF_HALF_PI - r;
     if (x < 0.0f) r = (float)TIF_PI - r;
@@ -253,8 +303,11 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 struct SampleGeom {       // per (ERP pixel, accepting face): constant over the batch
     double gx0, bz0, cy0;           // direction of the tangent pixel centre: gx, cos(phi0) - gy sin(phi0), sin(phi0) + gy cos(phi0)
     double kx, ky_sin, ky_cos;
-    float gx0f, bz0f, cy0f, kxf, ky_sinf, ky_cosf;
-    float sin_d, cos_d;             // sin / cos of (theta_src - theta0)
+    // float32 local frame of the source pixel (bulk rows): the end point is the source direction plus a small
+    // displacement (dx, dy) on the tangent plane, decomposed into east / north / radial parts
+    float d0x, d0y;                 // tangent-pixel centre minus the source pixel's own gnomonic position
+    float kxf, kyf;
+    float e1, e2, n1, n2, u1, u2, u0;
     int tpix;
     int face;
     float mult;
@@ -295,7 +348,7 @@ template <bool PRECISE>
 __device__ __forceinline__ Lifted lift_endpoint(const SampleGeom& G, float u, float v, float sin_colat_src,
                                                 float cos_colat_src, double sin_cs64, double cos_cs64, double sin_d64,
                                                 double cos_d64, float theta_src, float u_scale, float v_scale,
-                                                double u_scale64, double v_scale64, bool wrap_around) {
+                                                double u_scale64, double v_scale64, float erp_wf, bool wrap_around) {
     Lifted o;
     if (PRECISE) {
         const double a = fma((double)u, G.kx, G.gx0);
@@ -308,40 +361,49 @@ __device__ __forceinline__ Lifted lift_endpoint(const SampleGeom& G, float u, fl
         const double xc = fma(c, cos_cs64, h * sin_cs64);
         const double yc = fma(h, cos_cs64, -c * sin_cs64);
         const double dcolat = atan2(yc, xc);
-        if (!wrap_around) {
-            const double tt = (double)theta_src + dtheta;
-            if (tt >= TIF_PI) dtheta -= TIF_TWO_PI;
-            else if (tt < -TIF_PI) dtheta += TIF_TWO_PI;
-        }
+        // bilinear fractions from the wrapped (small) flow; the seam convention then moves whole images
         const double fu = dtheta * u_scale64, fv = dcolat * v_scale64;
         const double fiu = floor(fu), fiv = floor(fv);
-        o.fu = (float)fu;
-        o.fv = (float)fv;
         o.xi = (int)fiu;
         o.yi = (int)fiv;
         o.fx = (float)(fu - fiu);
         o.fy = (float)(fv - fiv);
+        o.fu = (float)fu;
+        o.fv = (float)fv;
+        if (!wrap_around) {
+            const double tt = (double)theta_src + dtheta;
+            if (tt >= TIF_PI) { o.fu -= erp_wf; o.xi -= (int)erp_wf; }
+            else if (tt < -TIF_PI) { o.fu += erp_wf; o.xi += (int)erp_wf; }
+        }
         return o;
     }
-    const float a = fmaf(u, G.kxf, G.gx0f);
-    const float b = fmaf(v, G.ky_sinf, G.bz0f);
-    const float c = fmaf(-v, G.ky_cosf, G.cy0f);
-    const float xr = fmaf(b, G.cos_d, a * G.sin_d);
-    const float yr = fmaf(a, G.cos_d, -b * G.sin_d);
-    float dtheta = atan2_fast(yr, xr);
-    const float h = sqrtf(fmaf(xr, xr, yr * yr));
-    const float xc = fmaf(c, cos_colat_src, h * sin_colat_src);
-    const float yc = fmaf(h, cos_colat_src, -c * sin_colat_src);
+    // displacement of the end point from the source pixel on the tangent plane (gnomonic units, y up)
+    const float dx = fmaf(u, G.kxf, G.d0x);
+    const float dy = fmaf(-v, G.kyf, G.d0y);
+    // east / north / radial components in the source pixel's local frame: small terms stay small, so
+    // float32 keeps ~1e-7 relative precision on the flow itself instead of on the O(1) direction vector
+    const float E = fmaf(dy, G.e1, dx * G.e2);
+    const float N = fmaf(dy, G.n1, dx * G.n2);
+    const float U = fmaf(dy, G.u1, fmaf(dx, G.u2, G.u0));
+    // sin_colat_src = cos(phi_src), cos_colat_src = sin(phi_src)
+    const float rm = fmaf(U, sin_colat_src, -N * cos_colat_src);       // horizontal part in the source meridian plane
+    const float z = fmaf(U, cos_colat_src, N * sin_colat_src);         // part along the polar axis
+    float dtheta = atan2_fast(E, rm);
+    const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
+    // h cos(colat_s) - z sin(colat_s) = -N + (h - rm) cos(colat_s), and h - rm = E^2 / (h + rm)
+    const float yc = rm > 0.0f ? fmaf(E * E, cos_colat_src * rcp_newton(h + rm), -N)
+                               : fmaf(h, cos_colat_src, -z * sin_colat_src);
+    const float xc = fmaf(z, cos_colat_src, h * sin_colat_src);
     const float dcolat = atan2_fast(yc, xc);
-    if (!wrap_around) {
-        const float tt = theta_src + dtheta;
-        if (tt >= (float)TIF_PI) dtheta -= (float)TIF_TWO_PI;
-        else if (tt < -(float)TIF_PI) dtheta += (float)TIF_TWO_PI;
-    }
     o.fu = dtheta * u_scale;
     o.fv = dcolat * v_scale;
     split_floor(o.fu, o.xi, o.fx);
     split_floor(o.fv, o.yi, o.fy);
+    if (!wrap_around) {
+        const float tt = theta_src + dtheta;
+        if (tt >= (float)TIF_PI) { o.fu -= erp_wf; o.xi -= (int)erp_wf; }
+        else if (tt < -(float)TIF_PI) { o.fu += erp_wf; o.xi += (int)erp_wf; }
+    }
     return o;
 }
 
@@ -358,19 +420,19 @@ __device__ __forceinline__ float warp_error_sum(const uint8_t* __restrict__ tar,
     float fx = L.fx, fy = L.fy;
     float t0, t1, t2;
     // inside iff 0 <= x0 + fx <= W-1 and 0 <= y0 + fy <= H-1
-    const bool inside = x0 >= 0 && y0 >= 0 && (x0 < erp_w - 1 || (x0 == erp_w - 1 && fx == 0.0f)) &&
-                        (y0 < erp_h - 1 || (y0 == erp_h - 1 && fy == 0.0f));
-    if (!inside) {
+    const bool x_ok = ((unsigned)x0 < (unsigned)(erp_w - 1)) | ((x0 == erp_w - 1) & (fx == 0.0f));
+    const bool y_ok = ((unsigned)y0 < (unsigned)(erp_h - 1)) | ((y0 == erp_h - 1) & (fy == 0.0f));
+    if (!(x_ok & y_ok)) {
         t0 = t1 = t2 = 255.0f;
     } else {
         if (x0 == erp_w - 1) { x0 = erp_w - 2; fx = 1.0f; }
         if (y0 == erp_h - 1) { y0 = erp_h - 2; fy = 1.0f; }
         const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
         const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
-        const uint8_t* r0 = tar + ((size_t)y0 * erp_w + x0) * 3;
-        const uint8_t* r1 = r0 + (size_t)erp_w * 3;
+        const uint8_t* r0 = tar + (unsigned)((y0 * erp_w + x0) * 3);
+        const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
         uint32_t lo0, hi0, lo1, hi1;
-        if (tail_image && y0 == erp_h - 2 && x0 >= erp_w - 8) {     // wide loads could leave the buffer
+        if (tail_image & (y0 == erp_h - 2) & (x0 >= erp_w - 8)) {   // wide loads could leave the buffer
             load_tap_pair_bytes(r0, lo0, hi0);
             load_tap_pair_bytes(r1, lo1, hi1);
         } else {
@@ -402,43 +464,31 @@ __device__ __forceinline__ void load_face_consts(FaceConst* sh, const TifFace* _
     }
 }
 
-// MODE 0: straightforward blend.  MODE 1: normwarp pass A (face-global warp-error sums only).
-// MODE 2: normwarp pass B (weights from the sums of pass A, blend).
+// MODE 0: straightforward blend.
+// MODE 1: normwarp pass A: lifts every accepted sample once, stores (fu, fv, sum_ch |diff|) in the sample
+//         scratch and accumulates the face-global warp-error sums; k_blend_normwarp finishes the job.
 // POLAR selects the float64 end-point lift; it is launched on the polar row bands only (normwarp).
 // Pixels are addressed through two segments: [seg0_start, seg0_start + seg0_len) then [seg1_start, ...).
 template <int MODE, bool POLAR>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS)
+__global__ void __launch_bounds__(TIF_STITCH_THREADS, POLAR ? 4 : 8)
 k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const double* __restrict__ col_theta,
          const float2* __restrict__ row_sc, const float2* __restrict__ col_sc,
          const double2* __restrict__ row_sc64, const double2* __restrict__ col_sc64,
          const double* __restrict__ face_mult_sum, const float* __restrict__ tflow,
          const uint8_t* __restrict__ erp_src, const uint8_t* __restrict__ erp_tar,
-         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, float* __restrict__ out,
-         int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around, int seg0_start, int seg0_len,
-         int seg1_start, int seg_total) {
+         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, const uint32_t* __restrict__ s2_offset,
+         float* __restrict__ nw_samples /* [B][3][S]: fu, fv, |diff| sum of every accepted sample */, int64_t n_samples,
+         float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around,
+         int seg0_start, int seg0_len, int seg1_start, int seg_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FaceConst* sh_face = reinterpret_cast<FaceConst*>(smem_raw);
-    // MODE 1: per-block partial sums; MODE 2: 1 / (3 * face-global mean)
-    unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_face + n_faces);
-    float* sh_inv_mean = reinterpret_cast<float*>(sh_face + n_faces);
+    unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_face + n_faces);      // MODE 1: per-block partial sums
 
     const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
     load_face_consts(sh_face, faces, n_faces);
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) sh_sum[i] = 0ull;
-    } else if (MODE == 2) {
-        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
-            const int bb = i / n_faces, f = i - bb * n_faces;
-            float inv = 0.0f;
-            if (b0 + bb < batch) {
-                // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
-                const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
-                const double mean = total / (3.0 * face_mult_sum[f]);
-                inv = (float)(1.0 / (3.0 * mean));
-            }
-            sh_inv_mean[i] = inv;
-        }
+        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) sh_sum[i] = 0u;
     }
     __syncthreads();
 
@@ -449,8 +499,10 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     int cnt = 0, r = 0, c = 0;
     float theta_src = 0.0f, sin_cs = 0.0f, cos_cs = 1.0f;
     double sin_cs64 = 0.0, cos_cs64 = 1.0;
+    uint32_t sample0 = 0;
     if (live) {
         cnt = s2_count[pix];
+        if (MODE == 1) sample0 = s2_offset[pix];
         r = pix / erp_w;
         c = pix - r * erp_w;
         theta_src = (float)col_theta[c];
@@ -459,8 +511,11 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         sin_cs = rs.y;
     }
     const bool polar = POLAR;
-    if (polar && live) {
+    double sin_phi64 = 0.0, cos_phi64 = 1.0;
+    if (live) {
         const double2 rs = row_sc64[r];
+        sin_phi64 = rs.x;
+        cos_phi64 = rs.y;
         cos_cs64 = rs.x;
         sin_cs64 = rs.y;
     }
@@ -506,22 +561,32 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             G.kx = F.kx;
             G.ky_sin = F.ky_sin;
             G.ky_cos = F.ky_cos;
-            G.gx0f = (float)G.gx0;
-            G.bz0f = (float)G.bz0;
-            G.cy0f = (float)G.cy0;
             G.kxf = (float)F.kx;
-            G.ky_sinf = (float)F.ky_sin;
-            G.ky_cosf = (float)F.ky_cos;
+            G.kyf = (float)F.ky;
             G.tpix = F.pix_offset + iy * tangent_w + ix;
             G.face = f;
             G.mult = (float)TIF_E_MULT(e);
-            const float2 cs = has ? __ldg(col_sc + f * erp_w + c) : make_float2(0.0f, 1.0f);
-            G.sin_d = cs.x;
-            G.cos_d = cs.y;
-            if (polar && has) {
-                const double2 cs64 = __ldg(col_sc64 + f * erp_w + c);
-                sin_d64 = cs64.x;
-                cos_d64 = cs64.y;
+            double2 cs64 = make_double2(0.0, 1.0);
+            if (has) cs64 = __ldg(col_sc64 + f * erp_w + c);        // (sin, cos)(theta_src - theta0), host numpy values
+            sin_d64 = cs64.x;
+            cos_d64 = cs64.y;
+            if (!POLAR) {
+                // the source pixel's own gnomonic position on this face (gnomonic_projection.py:36-44) and the
+                // local east / north / radial frame there, once per (pixel, face) in float64
+                const double sp = sin_phi64, cp = cos_phi64, s0 = F.sin_phi0, c0 = F.cos_phi0;
+                const double cos_c = fma(c0 * cp, cos_d64, s0 * sp);
+                const double inv = 1.0 / cos_c;
+                const double gxs = cp * sin_d64 * inv;
+                const double gys = fma(-s0 * cp, cos_d64, c0 * sp) * inv;
+                G.d0x = (float)(G.gx0 - gxs);
+                G.d0y = (float)(gy0 - gys);
+                G.u0 = (float)inv;
+                G.e1 = (float)(s0 * sin_d64);
+                G.e2 = (float)cos_d64;
+                G.n1 = (float)fma(s0 * sp, cos_d64, c0 * cp);
+                G.n2 = (float)(-sp * sin_d64);
+                G.u1 = (float)fma(-s0 * cp, cos_d64, c0 * sp);
+                G.u2 = (float)(cp * sin_d64);
             }
         }
         const int f = G.face;
@@ -536,10 +601,10 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 const float2 uv = __ldg(reinterpret_cast<const float2*>(tflow) + (size_t)b * n_tangent + G.tpix);
                 if (polar)
                     L = lift_endpoint<true>(G, uv.x, uv.y, sin_cs, cos_cs, sin_cs64, cos_cs64, sin_d64, cos_d64, theta_src,
-                                            u_scale, v_scale, u_scale64, v_scale64, wrap_around != 0);
+                                            u_scale, v_scale, u_scale64, v_scale64, (float)erp_w, wrap_around != 0);
                 else
                     L = lift_endpoint<false>(G, uv.x, uv.y, sin_cs, cos_cs, 0.0, 1.0, 0.0, 1.0, theta_src, u_scale, v_scale,
-                                             0.0, 0.0, wrap_around != 0);
+                                             0.0, 0.0, (float)erp_w, wrap_around != 0);
                 if (MODE != 0)
                     dsum = warp_error_sum(erp_tar + (size_t)b * image_bytes, b == batch - 1, sp[bb][0], sp[bb][1], sp[bb][2],
                                           L, r, c, erp_h, erp_w);
@@ -554,26 +619,20 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // face-global sum of |diff| (x multiplicity) as order-independent fixed point.
                 // Neighbouring pixels almost always see the same face at the same k: reduce across
                 // the warp first and issue one shared-memory atomic; otherwise one per lane.
+                if (has) {
+                    float* smp = nw_samples + (size_t)b * 3 * n_samples + sample0 + k;
+                    smp[0] = L.fu;
+                    smp[n_samples] = L.fv;
+                    smp[2 * n_samples] = dsum;
+                }
                 const unsigned fixed = has ? (unsigned)(dsum * G.mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
                 const int f0 = __shfl_sync(0xffffffffu, f, 0);
                 const bool uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
                 if (uniform) {
-                    // 32 lanes x (765 x 7 x 32768) overflows 32 bits: reduce as two 16-bit halves
-                    const unsigned lo = __reduce_add_sync(0xffffffffu, fixed & 0xffffu);
-                    const unsigned hi = __reduce_add_sync(0xffffffffu, fixed >> 16);
-                    if ((threadIdx.x & 31) == 0)
-                        atomicAdd(&sh_sum[bb * n_faces + f0], (unsigned long long)lo + ((unsigned long long)hi << 16));
+                    const unsigned total = __reduce_add_sync(0xffffffffu, fixed);    // <= 32 x 765 x 7 x 1024
+                    if ((threadIdx.x & 31) == 0) atomicAdd(&sh_sum[bb * n_faces + f0], total);
                 } else if (has) {
-                    atomicAdd(&sh_sum[bb * n_faces + f], (unsigned long long)fixed);
-                }
-            } else {
-                if (has) {
-                    // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
-                    const float x = -dsum * sh_inv_mean[bb * n_faces + f];
-                    const float w = polar ? expf(x) : __expf(x);
-                    acc_u[bb] = fmaf(L.fu, w, acc_u[bb]);
-                    acc_v[bb] = fmaf(L.fv, w, acc_v[bb]);
-                    acc_w[bb] += w;
+                    atomicAdd(&sh_sum[bb * n_faces + f], fixed);
                 }
             }
         }
@@ -583,7 +642,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         __syncthreads();
         for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
             const int bb = i / n_faces, f = i - bb * n_faces;
-            if (b0 + bb < batch && sh_sum[i]) atomicAdd(&nw_sums[(size_t)(b0 + bb) * n_faces + f], sh_sum[i]);
+            if (b0 + bb < batch && sh_sum[i]) atomicAdd(&nw_sums[(size_t)(b0 + bb) * n_faces + f], (unsigned long long)sh_sum[i]);
         }
         return;
     }
@@ -611,10 +670,84 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     }
 }
 
+// normwarp pass B: a streaming blend of the samples pass A stored.
+//   w = exp(-(mean_ch |diff|) / face-global mean)   (projection.py:57-58)
+//   flow = sum_f w f / sum_f w                       (projection_icosahedron.py:384-393), then erp_of_wraparound
+__global__ void __launch_bounds__(256)
+k_blend_normwarp(int n_faces, const uint8_t* __restrict__ s2_count, const uint32_t* __restrict__ s2_entries,
+                 const uint32_t* __restrict__ s2_offset, const double* __restrict__ face_mult_sum,
+                 const unsigned long long* __restrict__ nw_sums, const float* __restrict__ nw_samples, int64_t n_samples,
+                 float* __restrict__ out, int erp_h, int erp_w, int batch, int wrap_around) {
+    extern __shared__ float sh_inv_mean[];       // [TIF_BATCH_CHUNK][F]  1 / (3 * face-global mean)
+    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+    for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
+        const int bb = i / n_faces, f = i - bb * n_faces;
+        float inv = 0.0f;
+        if (b0 + bb < batch) {
+            // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
+            const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
+            const double mean = total / (3.0 * face_mult_sum[f]);
+            inv = (float)(1.0 / (3.0 * mean));
+        }
+        sh_inv_mean[i] = inv;
+    }
+    __syncthreads();
+    const int n_pix = erp_h * erp_w;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= n_pix) return;
+    const int cnt = s2_count[pix];
+    const uint32_t sample0 = s2_offset[pix];
+    const int c = pix % erp_w;
+    float acc_u[TIF_BATCH_CHUNK], acc_v[TIF_BATCH_CHUNK], acc_w[TIF_BATCH_CHUNK];
+#pragma unroll
+    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+    for (int k = 0; k < cnt; ++k) {
+        const int f = (int)TIF_E_FACE(__ldg(s2_entries + (size_t)k * n_pix + pix));
+#pragma unroll
+        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+            const int b = b0 + bb;
+            if (b >= batch) break;
+            const float* smp = nw_samples + (size_t)b * 3 * n_samples + sample0 + k;
+            const float fu = __ldg(smp), fv = __ldg(smp + n_samples), dsum = __ldg(smp + 2 * n_samples);
+            const float w = expf(-dsum * sh_inv_mean[bb * n_faces + f]);
+            acc_u[bb] = fmaf(fu, w, acc_u[bb]);
+            acc_v[bb] = fmaf(fv, w, acc_v[bb]);
+            acc_w[bb] += w;
+        }
+    }
+    const float half_w = 0.5f * (float)erp_w;
+    const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
+#pragma unroll
+    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        const int b = b0 + bb;
+        if (b >= batch) break;
+        float u = acc_u[bb], v = acc_v[bb];
+        if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393
+            const float inv = 1.0f / acc_w[bb];
+            u *= inv;
+            v *= inv;
+        }
+        if (wrap_around) {            // flow_postproc.erp_of_wraparound, flow_postproc.py:28-42
+            if (c < split) {
+                if (u > half_w) u -= (float)erp_w;
+            } else if (c < erp_w - 1) {
+                if (u < -half_w) u += (float)erp_w;
+            }
+        }
+        reinterpret_cast<float2*>(out)[(size_t)b * n_pix + pix] = make_float2(u, v);
+    }
+}
+
+// scratch = [B][F] uint64 face sums (padded to 256 bytes) + [B][3][S] float32 samples, S = accepted samples per pair
+static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
+    const size_t raw = (size_t)batch * plan->n_faces * sizeof(unsigned long long);
+    return (raw + 255) / 256 * 256;
+}
+
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
     if (blend != TIF_BLEND_NORMWARP) return 0;
-    return (int64_t)batch * plan->n_faces * (int64_t)sizeof(unsigned long long);
+    return (int64_t)(nw_sums_bytes(plan, batch) + (size_t)batch * 3 * (size_t)plan->accepted_unique * sizeof(float));
 }
 
 extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
@@ -637,22 +770,30 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const int h = plan->erp_h, w = plan->erp_w;
     const int n_pix = h * w;
     const unsigned by = (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK);
-    const size_t smem = sizeof(FaceConst) * plan->n_faces + sizeof(unsigned long long) * TIF_BATCH_CHUNK * plan->n_faces;
+    const size_t smem = sizeof(FaceConst) * plan->n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * plan->n_faces;
+    unsigned long long* nw_sums = (unsigned long long*)scratch;
+    float* nw_samples = scratch ? (float*)((unsigned char*)scratch + nw_sums_bytes(plan, batch)) : nullptr;
+    const int64_t n_samples = plan->accepted_unique;
 #define STITCH_ARGS                                                                                                 \
     plan->d_faces, plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_col_theta, plan->d_row_sc,         \
         plan->d_col_sc, plan->d_row_sc64, plan->d_col_sc64, plan->d_face_mult_sum, tangent_flow, erp_src, erp_tar, \
-        (unsigned long long*)scratch, erp_flow, h, w, plan->tangent_w, (int)plan->tangent_pixels, batch, wrap_around
+        nw_sums, plan->d_s2_offset, nw_samples, n_samples, erp_flow, h, w, plan->tangent_w,                        \
+        (int)plan->tangent_pixels, batch, wrap_around
 #define STITCH_GRID(n) dim3((unsigned)(((n) + threads - 1) / threads), by)
+    // rows with sin(colatitude) < TIF_POLAR_SIN at either pole take the float64 lift (separate launch so
+    // that its register footprint does not lower the occupancy of the bulk)
+    int polar_rows = 0;
+    while (polar_rows < h / 2 && sin(((double)polar_rows + 0.5) * TIF_PI / (double)h) < (double)TIF_POLAR_SIN) ++polar_rows;
+    const int n_polar = 2 * polar_rows * w, n_bulk = n_pix - n_polar;
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
-        k_stitch<0, false><<<STITCH_GRID(n_pix), threads, smem, stream>>>(STITCH_ARGS, 0, n_pix, 0, n_pix);
+        if (n_bulk > 0)
+            k_stitch<0, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
+        if (n_polar > 0)
+            k_stitch<0, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
+                                                                               (h - polar_rows) * w, n_polar);
     } else {
-        // rows with sin(colatitude) < TIF_POLAR_SIN at either pole take the float64 lift (separate launch so
-        // that its register footprint does not lower the occupancy of the bulk)
-        int polar_rows = 0;
-        while (polar_rows < h / 2 && sin(((double)polar_rows + 0.5) * TIF_PI / (double)h) < (double)TIF_POLAR_SIN) ++polar_rows;
-        const int n_polar = 2 * polar_rows * w, n_bulk = n_pix - n_polar;
         if (pass_mask & 1) {
-            TIF_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)tif_ico2erp_scratch_bytes(plan, batch, blend), stream));
+            TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (n_bulk > 0)
                 k_stitch<1, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
             if (n_polar > 0)
@@ -660,13 +801,11 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
                                                                                    (h - polar_rows) * w, n_polar);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
-        if (pass_mask & 2) {
-            if (n_bulk > 0)
-                k_stitch<2, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
-            if (n_polar > 0)
-                k_stitch<2, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
-                                                                                   (h - polar_rows) * w, n_polar);
-        }
+        if (pass_mask & 2)
+            k_blend_normwarp<<<dim3((unsigned)((n_pix + 255) / 256), by), 256,
+                               sizeof(float) * TIF_BATCH_CHUNK * plan->n_faces, stream>>>(
+                plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_offset, plan->d_face_mult_sum, nw_sums,
+                nw_samples, n_samples, erp_flow, h, w, batch, wrap_around);
     }
 #undef STITCH_ARGS
 #undef STITCH_GRID

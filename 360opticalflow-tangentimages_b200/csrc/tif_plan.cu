@@ -241,6 +241,7 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_s1_ey);
     cudaFree(plan->d_s2_count);
     cudaFree(plan->d_s2_entries);
+    cudaFree(plan->d_s2_offset);
     cudaFree(plan->d_col_theta);
     cudaFree(plan->d_row_sc);
     cudaFree(plan->d_col_sc);
@@ -428,6 +429,27 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(cuda_status(cudaMemcpyAsync(&h_acc, d_msum, sizeof(h_acc), cudaMemcpyDeviceToHost, stream), "read accepted"));
     PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan finish"));
     plan->accepted_unique = (int64_t)h_acc;
+    {
+        // exclusive prefix sum of the per-pixel counts (plan-time bookkeeping: 1 byte per ERP pixel through the host)
+        PLAN_TRY(dev_alloc(&plan->d_s2_offset, n_erp, plan));
+        uint8_t* h_cnt = (uint8_t*)malloc((size_t)n_erp);
+        uint32_t* h_off = (uint32_t*)malloc((size_t)n_erp * sizeof(uint32_t));
+        cudaError_t ea = cudaMemcpy(h_cnt, plan->d_s2_count, (size_t)n_erp, cudaMemcpyDeviceToHost);
+        uint32_t run = 0;
+        for (int64_t i = 0; i < n_erp; ++i) {
+            h_off[i] = run;
+            run += h_cnt[i];
+        }
+        cudaError_t eb = cudaMemcpy(plan->d_s2_offset, h_off, (size_t)n_erp * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        free(h_cnt);
+        free(h_off);
+        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "sample offsets"));
+        if ((int64_t)run != plan->accepted_unique) {
+            tif_set_error("tif_plan_create: sample offsets (%u) disagree with the accepted count (%lld)", run,
+                          (long long)plan->accepted_unique);
+            PLAN_TRY(TIF_ERR_RANGE);
+        }
+    }
 
     cudaFree(d_gx);
     cudaFree(d_gy);

@@ -454,6 +454,8 @@ def blend_faces(face_results, erp_h, wrap_around, return_debug=False):
     # the +-pi seam (u jumps by W without the seam fix) and the hard edge of mode='constant' sampling
     seam_dist = np.full((erp_h, erp_w), np.inf)
     edge_dist = np.full((erp_h, erp_w), np.inf)
+    fu_min = np.full((erp_h, erp_w), np.inf)
+    fu_max = np.full((erp_h, erp_w), -np.inf)
     debug = []
     for fr in face_results:
         r, c, w = fr["r"], fr["c"], fr["w"]
@@ -465,6 +467,8 @@ def blend_faces(face_results, erp_h, wrap_around, return_debug=False):
             np.minimum.at(seam_dist, (r, c), PI - np.abs(fr["th_t"]))
             e = np.minimum(np.minimum(np.abs(tx), np.abs(tx - (erp_w - 1))), np.minimum(np.abs(ty), np.abs(ty - (erp_h - 1))))
             np.minimum.at(edge_dist, (r, c), e)
+            np.minimum.at(fu_min, (r, c), fr["fu"])
+            np.maximum.at(fu_max, (r, c), fr["fu"])
             debug.append({"rows": r, "cols": c, "ix": fr["ix"], "iy": fr["iy"], "mult": fr["mult"],
                           "candidates": fr["candidates"], "accepted": fr["accepted"], "bbox": fr["bbox"]})
     nz = acc_w != 0.0
@@ -474,7 +478,7 @@ def blend_faces(face_results, erp_h, wrap_around, return_debug=False):
     if wrap_around:
         acc_flow = erp_of_wraparound(acc_flow)
     if return_debug:
-        return acc_flow, {"faces": debug, "seam_dist": seam_dist, "edge_dist": edge_dist}
+        return acc_flow, {"faces": debug, "seam_dist": seam_dist, "edge_dist": edge_dist, "fu_spread": fu_max - fu_min}
     return acc_flow
 
 

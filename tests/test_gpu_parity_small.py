@@ -23,6 +23,11 @@ def flow_mismatch(got, want, src, tar, flows, g, wrap, blend):
     _, dbg = tif_oracle.ico2erp_flow(flows, int(g["erp_h"]), float(g["pad"]), src, tar, wrap, blend, return_debug=True)
     excuse = np.zeros(err.shape, dtype=bool)
     excuse |= dbg["seam_dist"] < 1e-5
+    if not wrap:
+        # without the seam fix the faces of a pixel can disagree by a whole image width (one end point wrapped,
+        # another not); the reference's weighted mean of such values is meaningless and magnifies any 1e-7
+        # difference in the weights by W
+        excuse |= dbg["fu_spread"] > 0.25 * want.shape[1]
     if blend == "normwarp":
         excuse |= dbg["edge_dist"] < 1e-3
     return (err > FLOW_TOL) & ~excuse
@@ -100,11 +105,13 @@ def test_warp_meshgrid_wraparound(pkg, golden, name):
     assert np.array_equal(big[:, :, 0], g["wraparound_out"][:, :, 0])      # argument's u plane is rewritten
 
 
-def test_oracle_agrees_at_mid_size(pkg):
-    """GPU vs oracle at H=256 on noise images with a seam-crossing flow offset."""
+@pytest.mark.parametrize("smooth,offset", [(False, 0.0), (True, 25.0)])
+def test_oracle_agrees_at_mid_size(pkg, smooth, offset):
+    """GPU vs oracle at H=256: IID-noise images (the harshest case for the photometric weights), and a
+    band-limited pair with a 25 px flow offset that pushes end points across the seam and the image edge."""
     erp_h, wt, pad = 256, 120, 0.3
-    src, tar = synth.synth_images(erp_h, 21)
-    flows = synth.synth_flows(wt, 20, 25.0)
+    src, tar = synth.synth_images(erp_h, 21, smooth)
+    flows = synth.synth_flows(wt, 20, offset)
     pico = pkg.projection_icosahedron
     got = pico.erp2ico_image(tar, wt, pad, True)
     want = tif_oracle.erp2ico_image(tar, wt, pad, True)
