@@ -1,0 +1,190 @@
+"""GPU parity at BASELINE.json's full sizes: config #2 (2048x1024) against the oracle and the committed reference
+summaries, config #3 (3840x1920, warp enabled) against the reference summaries, plus size-independent properties
+(batch consistency, determinism, identities) and direct C-ABI calls."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, tif_oracle
+
+pytestmark = pytest.mark.gpu
+
+FLOW_TOL = 1e-3          # px, north_star tolerance (float32 path vs the float64 reference)
+PAD, WT = 0.3, 480
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def inputs(g):
+    src, tar = synth.synth_images(int(g["erp_h"]), int(g["seed"]), bool(g["smooth"]))
+    flows = synth.synth_flows(int(g["tangent_w"]), 20, float(g["u_offset"]))
+    return src, tar, flows
+
+
+def membership_hashes(plan):
+    """Per-face sha1 of (row, col, ix, iy, multiplicity) sorted by pixel, as oracle/make_golden.py computes it."""
+    count, entries = plan.export_stage2()
+    count = count.cpu().numpy().reshape(-1)
+    entries = entries.cpu().numpy().view(np.uint32).reshape(entries.shape[0], -1)
+    w = plan.erp_w
+    per_face = [[] for _ in range(plan.n_faces)]
+    for k in range(entries.shape[0]):
+        pix = np.nonzero(count > k)[0]
+        e = entries[k][pix]
+        face = e >> 25
+        for f in np.unique(face):
+            sel = face == f
+            per_face[int(f)].append(np.stack((pix[sel] // w, pix[sel] % w, e[sel] & 2047, (e[sel] >> 11) & 2047,
+                                              (e[sel] >> 22) & 7)).astype(np.int64))
+    out, accepted = [], []
+    for f in range(plan.n_faces):
+        a = np.concatenate(per_face[f], axis=1)
+        a = a[:, np.argsort(a[0] * w + a[1], kind="stable")]
+        out.append(sha(a.astype(np.int32)))
+        accepted.append(int(a[4].sum()))
+    return out, accepted
+
+
+@pytest.mark.parametrize("name", ["summary_h1024_noise", "summary_h640_smooth_seam", "summary_h1920_noise"])
+def test_reference_summaries(pkg, golden, name):
+    """Outputs of the live reference (hashes, strided samples, pole rows) at 1280x640, 2048x1024 and 3840x1920."""
+    g = golden(name)
+    src, tar, flows = inputs(g)
+    erp_h = int(g["erp_h"])
+    pico, fwarp = pkg.projection_icosahedron, pkg.flow_warp
+    full = np.stack(pico.erp2ico_image(src, WT, PAD, True)).astype(np.uint8)
+    assert sha(full) == str(g["ico_full_sha"])                      # every uint8 sample identical
+    assert bool((full[..., 3] == 255).all())
+    plan = pkg._geometry.get_plan(PAD, erp_h, WT)
+    hashes, accepted = membership_hashes(plan)
+    assert hashes == [str(h) for h in g["mem_sha"]]                 # membership + indices bit-exact
+    assert accepted == [int(a) for a in g["accepted"]]
+    stride = int(g["flow_stride"])
+    for blend in ("straightforward", "normwarp"):
+        tag = blend[:2]
+        f = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
+        err = np.abs(f.reshape(-1, 2)[::stride] - g["flow_%s_samples" % tag]).max(axis=1)
+        # strided samples: allow the oracle-identified discontinuity pixels (checked in full in the oracle tests)
+        assert (err > FLOW_TOL).mean() < 2e-4, (blend, err.max())
+        assert np.median(err) < 2e-5
+    # warp_backward with the reference's own float64 flow is exercised in test_config2_against_oracle
+
+
+def test_config2_against_oracle(pkg):
+    """BASELINE.json config #2: synthetic 2048x1024 pair, 20 faces, padding 0.3, both blends, GPU vs oracle in full."""
+    erp_h = 1024
+    src, tar, flows = synth.synth(erp_h, 0, WT)
+    pico, fwarp = pkg.projection_icosahedron, pkg.flow_warp
+    want_faces = tif_oracle.erp2ico_image(tar, WT, PAD, True)
+    got_faces = pico.erp2ico_image(tar, WT, PAD, True)
+    assert all(np.array_equal(a, b) for a, b in zip(got_faces, want_faces))
+    for blend in ("straightforward", "normwarp"):
+        want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend, return_debug=True)
+        got = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
+        excuse = dbg["seam_dist"] < 1e-5
+        if blend == "normwarp":
+            excuse |= dbg["edge_dist"] < 1e-3
+        err = np.abs(got - want).max(axis=2)
+        assert ((err > FLOW_TOL) & ~excuse).sum() == 0, (blend, err.max())
+        assert np.median(err) < 5e-6
+    # flow_warp evaluation on the oracle's float64 flow: uint8 identical
+    assert np.array_equal(fwarp.warp_backward(tar, want), tif_oracle.warp_backward(tar, want))
+
+
+def test_config3_warp_at_4k(pkg):
+    """BASELINE.json config #3: 3840x1920 with the flow_warp evaluation: exact uint8 warp for a float64 flow."""
+    erp_h = 1920
+    rng = np.random.default_rng(3)
+    tar = rng.integers(0, 256, (erp_h, 2 * erp_h, 3), dtype=np.uint8)
+    flow = rng.normal(0.0, 30.0, (erp_h, 2 * erp_h, 2))
+    flow[::7, ::5, 0] += 4000.0            # several periods of scipy's n-1 wrap
+    flow[::11, ::3, 1] -= 2500.0
+    assert np.array_equal(pkg.flow_warp.warp_backward(tar, flow), tif_oracle.warp_backward(tar, flow))
+
+
+def test_batch_consistency_and_determinism(pkg):
+    """Size-independent properties: a batch equals its items, repeated runs are bitwise identical (the normwarp
+    face means are integer sums), a constant image resamples to itself, zero flow warps to the identity."""
+    erp_h, wt = 512, 240
+    dev = torch.device("cuda", 0)
+    pico, fwarp, fpost = pkg.projection_icosahedron, pkg.flow_warp, pkg.flow_postproc
+    batch = 5                        # not a multiple of the kernels' batch chunk (4)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    src = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
+    tar = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
+    base = torch.from_numpy(np.stack(synth.synth_flows(wt))).to(dev)
+    flows = torch.stack([base + 0.3 * i for i in range(batch)])
+    tan = pico.erp2ico_image(src, wt, PAD)
+    assert tan.shape == (batch, 20, synth.tangent_height(wt), wt, 4) and tan.dtype == torch.uint8
+    for i in range(batch):
+        assert torch.equal(tan[i:i + 1], pico.erp2ico_image(src[i:i + 1], wt, PAD))
+    for blend in ("straightforward", "normwarp"):
+        out = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
+        assert out.shape == (batch, erp_h, 2 * erp_h, 2) and out.dtype == torch.float32
+        assert torch.equal(out, pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend))
+        for i in (0, batch - 1):
+            one = pico.ico2erp_flow(flows[i:i + 1], erp_h, PAD, src[i:i + 1], tar[i:i + 1], True, blend)
+            assert torch.equal(out[i:i + 1], one)
+        # idempotence of the final wrap: already applied by the stitch
+        again = fpost.erp_of_wraparound(out.clone())
+        assert torch.equal(again, out)
+    const = torch.full((1, erp_h, 2 * erp_h, 3), 77, dtype=torch.uint8, device=dev)
+    tc = pico.erp2ico_image(const, wt, PAD)
+    assert bool((tc[..., :3] == 77).all()) and bool((tc[..., 3] == 255).all())
+    zero = torch.zeros((batch, erp_h, 2 * erp_h, 2), dtype=torch.float32, device=dev)
+    assert torch.equal(fwarp.warp_backward(tar, zero), tar)
+    mg = fwarp.flow_warp_meshgrid(zero[..., 0].contiguous(), zero[..., 1].contiguous())
+    assert torch.equal(mg[0, 0, 3], torch.arange(2 * erp_h, device=dev, dtype=torch.float32))
+
+
+def test_host_pipeline_matches_device_path(pkg):
+    erp_h, wt, batch = 256, 120, 6
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(9)
+    src = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
+    tar = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
+    flows5 = torch.stack([torch.from_numpy(np.stack(synth.synth_flows(wt))).to(dev) * (1 + 0.1 * i) for i in range(batch)])
+    pico = pkg.projection_icosahedron
+    want = pico.ico2erp_flow(flows5, erp_h, PAD, src, tar, True, "normwarp")
+    want_tan = pico.erp2ico_image(src, wt, PAD)
+    pipe = pkg.pipeline.HostPipeline(PAD, erp_h, wt, "normwarp", True, chunk=4, slots=2, device=dev)
+    p = pipe.plan.tangent_pixels
+    h_out = torch.empty((batch, erp_h, 2 * erp_h, 2), dtype=torch.float32).pin_memory()
+    h_ts = torch.empty((batch, p, 4), dtype=torch.uint8).pin_memory()
+    h_tt = torch.empty((batch, p, 4), dtype=torch.uint8).pin_memory()
+    pipe.run(src.cpu().pin_memory(), tar.cpu().pin_memory(), flows5.reshape(batch, p, 2).cpu().pin_memory(), h_out, h_ts, h_tt)
+    assert torch.equal(h_out, want.cpu())
+    assert torch.equal(h_ts, want_tan.reshape(batch, p, 4).cpu())
+
+
+def test_direct_c_abi_calls(pkg):
+    """Through the C ABI with raw pointers (torch only owns the memory): argument validation and one resample."""
+    lib = pkg._lib.load()
+    erp_h, wt = 64, 32
+    plan = pkg._geometry.get_plan(PAD, erp_h, wt)
+    info = pkg._lib.TifPlanInfo()
+    assert lib.tif_plan_info(plan.handle, ctypes.byref(info)) == 0
+    assert (info.n_faces, info.erp_h, info.erp_w, info.tangent_w) == (20, erp_h, 2 * erp_h, wt)
+    assert info.tangent_pixels == 20 * 28 * 32 and info.max_faces_per_pixel >= 5 and info.device_bytes > 0
+    src, tar = synth.synth_images(erp_h, 3)
+    erp = torch.from_numpy(src).cuda()[None].contiguous()
+    out = torch.zeros((1, info.tangent_pixels, 4), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.tif_erp2ico_u8(plan.handle, erp.data_ptr(), 1, 1, out.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    want = np.stack(tif_oracle.erp2ico_image(src, wt, PAD, True)).astype(np.uint8)
+    assert np.array_equal(out.cpu().numpy().reshape(want.shape), want)
+    # invalid arguments are rejected with a status, not a crash
+    assert lib.tif_erp2ico_u8(None, erp.data_ptr(), 1, 1, out.data_ptr(), stream) == -1
+    assert lib.tif_erp2ico_u8(plan.handle, erp.data_ptr(), 0, 1, out.data_ptr(), stream) == -1
+    assert lib.tif_ico2erp_flow_f32(plan.handle, out.data_ptr(), None, None, 1, 7, 1, out.data_ptr(), None, stream) == -1
+    assert lib.tif_ico2erp_flow_f32(plan.handle, out.data_ptr(), None, None, 1, 1, 1, out.data_ptr(), None, stream) == -1
+    assert lib.tif_ico2erp_scratch_bytes(plan.handle, 2, 0) == 0 and lib.tif_ico2erp_scratch_bytes(plan.handle, 2, 1) > 0
+    assert lib.tif_warp_backward_u8(erp.data_ptr(), out.data_ptr(), 5, 1, erp_h, 2 * erp_h, 3, 0, out.data_ptr(), stream) == -1
