@@ -47,7 +47,8 @@ def build_library(force=False, verbose=False):
         obj = os.path.join(BUILD_DIR, unit.replace(".cu", ".o"))
         objects.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            defs = os.environ.get("TIF_NVCC_DEFS", "").split()        # experiment knobs, e.g. -DTIF_STITCH_MIN_BLOCKS=6
+            cmd = [nvcc] + ARCH + COMMON + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or res.returncode != 0:
                 print(" ".join(cmd))

@@ -11,7 +11,9 @@
 //   k_wraparound     erp_of_wraparound  flow_postproc.py:17-44
 #include "tif_common.cuh"
 
+#ifndef TIF_BATCH_CHUNK
 #define TIF_BATCH_CHUNK 4          // images per thread (plan entries amortised over the chunk)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // bilinear with scipy's uint8 rounding
@@ -58,31 +60,28 @@ __device__ __forceinline__ uint8_t round_u8_guarded(float t, float p00, float p0
 // stage 1: ERP -> tangent images
 // ------------------------------------------------------------------------------------------------
 // The two taps of one image row are 6 consecutive bytes (R0 G0 B0 R1 G1 B1) at an arbitrary byte
-// address.  They are fetched with one or two aligned 8-byte loads and funnel-shifted into place
-// instead of six byte loads.  `o` = address & 7.  The caller guarantees that 16 bytes from the aligned
-// address are readable.
+// address.  They are fetched with two or three aligned 4-byte loads and funnel-shifted into place
+// instead of six byte loads (the third word is only needed at byte phase 3).  `o` = address & 3.  The
+// caller guarantees that 12 bytes from the aligned address are readable.
 struct RawPair {
-    uint2 v0, v1;
+    uint32_t w0, w1, w2;
 };
 
 __device__ __forceinline__ RawPair load_raw_pair(const uint8_t* __restrict__ p, unsigned o) {
-    const uint2* q = reinterpret_cast<const uint2*>(p - o);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - o);
     RawPair r;
-    r.v0 = __ldg(q);
-    r.v1 = make_uint2(0u, 0u);
-    if (o > 2) r.v1 = __ldg(q + 1);                              // bytes o..o+5 leave the first 8 only then
+    r.w0 = __ldg(q);
+    r.w1 = __ldg(q + 1);
+    r.w2 = 0u;
+    if (o == 3) r.w2 = __ldg(q + 2);
     return r;
 }
 
 __device__ __forceinline__ void align_pair(const RawPair& r, unsigned o, uint32_t& lo /* R0 G0 B0 R1 */,
                                            uint32_t& hi /* G1 B1 . . */) {
-    const bool up = o >= 4;
-    const uint32_t wa = up ? r.v0.y : r.v0.x;
-    const uint32_t wb = up ? r.v1.x : r.v0.y;
-    const uint32_t wc = up ? r.v1.y : r.v1.x;
-    const unsigned sh = (o & 3) * 8;
-    lo = __funnelshift_r(wa, wb, sh);
-    hi = __funnelshift_r(wb, wc, sh);
+    const unsigned sh = o * 8;
+    lo = __funnelshift_r(r.w0, r.w1, sh);
+    hi = __funnelshift_r(r.w1, r.w2, sh);
 }
 
 __device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ p, unsigned o, uint32_t& lo, uint32_t& hi) {
@@ -130,13 +129,33 @@ __device__ __forceinline__ uint32_t erp2ico_pixel(uint32_t lo0, uint32_t hi0, ui
     return __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
 }
 
+// A warp owns an 8 x 4 tile of the tangent stack, not a 32 x 1 strip: tangent rows are tilted against ERP
+// rows (steeply on the polar faces), so a strip touches ~21 cache lines per tap load and a tile ~9.
+#define TIF_TILE_W 8
+#define TIF_TILE_H 4
+
+__device__ __forceinline__ bool tile_pixel(int64_t idx, int width, int rows, int& row, int& col) {
+    const int64_t warp = idx >> 5;
+    const int lane = (int)(idx & 31);
+    const int tiles_x = (width + TIF_TILE_W - 1) / TIF_TILE_W;
+    const int ty = (int)(warp / tiles_x), tx = (int)(warp - (int64_t)ty * tiles_x);
+    row = ty * TIF_TILE_H + lane / TIF_TILE_W;
+    col = tx * TIF_TILE_W + lane % TIF_TILE_W;
+    return row < rows && col < width;
+}
+
+__host__ __device__ __forceinline__ int64_t tile_threads(int width, int rows) {
+    return (int64_t)((width + TIF_TILE_W - 1) / TIF_TILE_W) * ((rows + TIF_TILE_H - 1) / TIF_TILE_H) * 32;
+}
+
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
-          const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int erp_h, int erp_w, int batch,
-          int batch_per_block_row, int full_face) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pix) return;
+          const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
+          int batch, int batch_per_block_row, int full_face) {
+    int trow, tcol;
+    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, tangent_w, (int)(n_pix / tangent_w), trow, tcol)) return;
+    const int64_t p = (int64_t)trow * tangent_w + tcol;
     const int b_begin = blockIdx.y * batch_per_block_row;
     const int b_end = min(batch, b_begin + batch_per_block_row);
     const uint32_t bs = s1_base[p];
@@ -161,7 +180,7 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
     const uint8_t* r0 = erp + (size_t)b_begin * image_bytes + tap;
     // The wide loads may touch up to 15 bytes past the second tap pair; only a tap at the very end of an
     // image could leave the buffer, and only in the last image: those few pixels use byte loads.
-    const bool tail = tap + row_bytes + 16 > image_bytes;
+    const bool tail = tap + row_bytes + 12 > image_bytes;
     if (tail) {
         for (int b = b_begin; b < b_end; ++b, r0 += image_bytes, o4 += n_pix) {
             uint32_t lo0, hi0, lo1, hi1;
@@ -171,8 +190,8 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
         }
         return;
     }
-    unsigned o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
-    unsigned o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
+    unsigned o0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3);
+    unsigned o1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 3);
     // the kernel is latency bound (taps are L1/L2 hits, not streams): keep the raw words of the next image in
     // flight while the current one is blended
     RawPair c0 = load_raw_pair(r0, o0), c1 = load_raw_pair(r0 + row_bytes, o1);
@@ -181,9 +200,9 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
         unsigned no0 = o0, no1 = o1;
         r0 += image_bytes;
         if (b + 1 < b_end) {
-            if (!ALIGNED) {     // image stride not a multiple of 8: the byte phase changes per image
-                no0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7);
-                no1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 7);
+            if (!ALIGNED) {     // image stride not a multiple of 4: the byte phase changes per image
+                no0 = (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3);
+                no1 = (unsigned)(reinterpret_cast<uintptr_t>(r0 + row_bytes) & 3);
             }
             n0 = load_raw_pair(r0, no0);
             n1 = load_raw_pair(r0 + row_bytes, no1);
@@ -206,7 +225,8 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         return TIF_ERR_INVALID_ARG;
     }
     const int threads = 256;
-    const unsigned blocks_x = (unsigned)((plan->tangent_pixels + threads - 1) / threads);
+    const int64_t n_threads = tile_threads(plan->tangent_w, (int)(plan->tangent_pixels / plan->tangent_w));
+    const unsigned blocks_x = (unsigned)((n_threads + threads - 1) / threads);
     // every thread walks the whole batch so that the plan entry is read once; only tiny problems
     // split the batch over blockIdx.y to fill the 148 SMs
     int rows = 1;
@@ -214,15 +234,15 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
     const int per_row = (batch + rows - 1) / rows;
     dim3 grid(blocks_x, (unsigned)((batch + per_row - 1) / per_row));
     const size_t image_bytes = (size_t)plan->erp_h * plan->erp_w * 3;
-    const bool aligned = (image_bytes % 8 == 0) && (reinterpret_cast<uintptr_t>(erp) % 8 == 0);
+    const bool aligned = (image_bytes % 4 == 0) && (reinterpret_cast<uintptr_t>(erp) % 4 == 0);
     if (aligned)
         k_erp2ico<true><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
-                                                                    plan->tangent_pixels, plan->erp_h, plan->erp_w, batch,
-                                                                    per_row, full_face_image);
+                                                                    plan->tangent_pixels, plan->tangent_w, plan->erp_h,
+                                                                    plan->erp_w, batch, per_row, full_face_image);
     else
         k_erp2ico<false><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
-                                                                     plan->tangent_pixels, plan->erp_h, plan->erp_w, batch,
-                                                                     per_row, full_face_image);
+                                                                     plan->tangent_pixels, plan->tangent_w, plan->erp_h,
+                                                                     plan->erp_w, batch, per_row, full_face_image);
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
 }
@@ -230,7 +250,12 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // ------------------------------------------------------------------------------------------------
 // stage 2+3: tangent flows -> ERP flow
 // ------------------------------------------------------------------------------------------------
+#ifndef TIF_STITCH_THREADS
 #define TIF_STITCH_THREADS 128
+#endif
+#ifndef TIF_STITCH_MIN_BLOCKS
+#define TIF_STITCH_MIN_BLOCKS 8       // 64 registers per thread: occupancy over a few spilled values
+#endif
 // rows whose sin(colatitude) is below this use the float64 end-point lift: an end point next to the polar
 // axis needs the float64 products of the flow (the float32 local frame cancels there), and under normwarp
 // the faces disagree by hundreds of ERP pixels next to the poles, so the photometric weights turn an
@@ -432,12 +457,12 @@ __device__ __forceinline__ float warp_error_sum(const uint8_t* __restrict__ tar,
         const uint8_t* r0 = tar + (unsigned)((y0 * erp_w + x0) * 3);
         const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
         uint32_t lo0, hi0, lo1, hi1;
-        if (tail_image & (y0 == erp_h - 2) & (x0 >= erp_w - 8)) {   // wide loads could leave the buffer
+        if (tail_image & (y0 == erp_h - 2) & (x0 >= erp_w - 6)) {   // wide loads could leave the buffer
             load_tap_pair_bytes(r0, lo0, hi0);
             load_tap_pair_bytes(r1, lo1, hi1);
         } else {
-            load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 7), lo0, hi0);
-            load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 7), lo1, hi1);
+            load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
+            load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
         }
         t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
         t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
@@ -467,10 +492,11 @@ __device__ __forceinline__ void load_face_consts(FaceConst* sh, const TifFace* _
 // MODE 0: straightforward blend.
 // MODE 1: normwarp pass A: lifts every accepted sample once, stores (fu, fv, sum_ch |diff|) in the sample
 //         scratch and accumulates the face-global warp-error sums; k_blend_normwarp finishes the job.
-// POLAR selects the float64 end-point lift; it is launched on the polar row bands only (normwarp).
-// Pixels are addressed through two segments: [seg0_start, seg0_start + seg0_len) then [seg1_start, ...).
+// POLAR selects the float64 end-point lift; it is launched on the polar row bands only.
+// The launch covers two row segments, [seg0_row, seg0_row + seg0_rows) then [seg1_row, ...), seg_rows rows in
+// all; a warp owns an 8 x 4 pixel tile of them (compact footprint in the tangent flows and the target image).
 template <int MODE, bool POLAR>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS, POLAR ? 4 : 8)
+__global__ void __launch_bounds__(TIF_STITCH_THREADS, POLAR ? 4 : TIF_STITCH_MIN_BLOCKS)
 k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const double* __restrict__ col_theta,
          const float2* __restrict__ row_sc, const float2* __restrict__ col_sc,
@@ -480,7 +506,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
          unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, const uint32_t* __restrict__ s2_offset,
          float* __restrict__ nw_samples /* [B][3][S]: fu, fv, |diff| sum of every accepted sample */, int64_t n_samples,
          float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around,
-         int seg0_start, int seg0_len, int seg1_start, int seg_total) {
+         int seg0_row, int seg0_rows, int seg1_row, int seg_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FaceConst* sh_face = reinterpret_cast<FaceConst*>(smem_raw);
     unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_face + n_faces);      // MODE 1: per-block partial sums
@@ -493,9 +519,9 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     __syncthreads();
 
     const int n_pix = erp_h * erp_w;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = idx < seg_total;
-    const int pix = !live ? 0 : (idx < seg0_len ? seg0_start + idx : seg1_start + (idx - seg0_len));
+    int vrow, vcol;
+    const bool live = tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, seg_rows, vrow, vcol);
+    const int pix = !live ? 0 : (vrow < seg0_rows ? seg0_row + vrow : seg1_row + (vrow - seg0_rows)) * erp_w + vcol;
     int cnt = 0, r = 0, c = 0;
     float theta_src = 0.0f, sin_cs = 0.0f, cos_cs = 1.0f;
     double sin_cs64 = 0.0, cos_cs64 = 1.0;
@@ -528,12 +554,18 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
         sp[bb][0] = sp[bb][1] = sp[bb][2] = 0.0f;
     }
-    const size_t image_bytes = (size_t)n_pix * 3;
+    // addresses inside the chunk of TIF_BATCH_CHUNK images are 32-bit offsets from per-chunk base pointers
+    // (4 images of flows / pixels / samples stay far below 4 GB), which keeps 64-bit integer maths out of the loop
+    const unsigned image_bytes = (unsigned)n_pix * 3u;
+    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
+    const uint8_t* __restrict__ tar_chunk = erp_tar + (size_t)b0 * image_bytes;
+    float* __restrict__ smp_chunk = nw_samples + (size_t)b0 * 3 * n_samples;
+    const unsigned n_smp = (unsigned)n_samples;
     if (MODE != 0 && live) {
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
             if (b0 + bb < batch) {
-                const uint8_t* q = erp_src + (size_t)(b0 + bb) * image_bytes + (size_t)pix * 3;
+                const uint8_t* q = erp_src + (size_t)b0 * image_bytes + ((unsigned)bb * image_bytes + (unsigned)pix * 3u);
                 sp[bb][0] = (float)__ldg(q);
                 sp[bb][1] = (float)__ldg(q + 1);
                 sp[bb][2] = (float)__ldg(q + 2);
@@ -598,7 +630,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             Lifted L;
             L.fu = L.fv = 0.0f;
             if (has) {
-                const float2 uv = __ldg(reinterpret_cast<const float2*>(tflow) + (size_t)b * n_tangent + G.tpix);
+                const float2 uv = __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)G.tpix));
                 if (polar)
                     L = lift_endpoint<true>(G, uv.x, uv.y, sin_cs, cos_cs, sin_cs64, cos_cs64, sin_d64, cos_d64, theta_src,
                                             u_scale, v_scale, u_scale64, v_scale64, (float)erp_w, wrap_around != 0);
@@ -606,7 +638,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                     L = lift_endpoint<false>(G, uv.x, uv.y, sin_cs, cos_cs, 0.0, 1.0, 0.0, 1.0, theta_src, u_scale, v_scale,
                                              0.0, 0.0, (float)erp_w, wrap_around != 0);
                 if (MODE != 0)
-                    dsum = warp_error_sum(erp_tar + (size_t)b * image_bytes, b == batch - 1, sp[bb][0], sp[bb][1], sp[bb][2],
+                    dsum = warp_error_sum(tar_chunk + (unsigned)bb * image_bytes, b == batch - 1, sp[bb][0], sp[bb][1], sp[bb][2],
                                           L, r, c, erp_h, erp_w);
             }
             if (MODE == 0) {
@@ -620,10 +652,10 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // Neighbouring pixels almost always see the same face at the same k: reduce across
                 // the warp first and issue one shared-memory atomic; otherwise one per lane.
                 if (has) {
-                    float* smp = nw_samples + (size_t)b * 3 * n_samples + sample0 + k;
+                    float* smp = smp_chunk + ((unsigned)bb * 3u * n_smp + sample0 + (unsigned)k);
                     smp[0] = L.fu;
-                    smp[n_samples] = L.fv;
-                    smp[2 * n_samples] = dsum;
+                    smp[n_smp] = L.fv;
+                    smp[2u * n_smp] = dsum;
                 }
                 const unsigned fixed = has ? (unsigned)(dsum * G.mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
                 const int f0 = __shfl_sync(0xffffffffu, f, 0);
@@ -779,26 +811,28 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         plan->d_col_sc, plan->d_row_sc64, plan->d_col_sc64, plan->d_face_mult_sum, tangent_flow, erp_src, erp_tar, \
         nw_sums, plan->d_s2_offset, nw_samples, n_samples, erp_flow, h, w, plan->tangent_w,                        \
         (int)plan->tangent_pixels, batch, wrap_around
-#define STITCH_GRID(n) dim3((unsigned)(((n) + threads - 1) / threads), by)
+#define STITCH_GRID(rows) dim3((unsigned)((tile_threads(w, (rows)) + threads - 1) / threads), by)
     // rows with sin(colatitude) < TIF_POLAR_SIN at either pole take the float64 lift (separate launch so
     // that its register footprint does not lower the occupancy of the bulk)
     int polar_rows = 0;
     while (polar_rows < h / 2 && sin(((double)polar_rows + 0.5) * TIF_PI / (double)h) < (double)TIF_POLAR_SIN) ++polar_rows;
-    const int n_polar = 2 * polar_rows * w, n_bulk = n_pix - n_polar;
+    polar_rows = min((polar_rows + TIF_TILE_H - 1) / TIF_TILE_H * TIF_TILE_H, h / 2);     // whole tiles
+    const int bulk_rows = h - 2 * polar_rows;
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
-        if (n_bulk > 0)
-            k_stitch<0, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
-        if (n_polar > 0)
-            k_stitch<0, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
-                                                                               (h - polar_rows) * w, n_polar);
+        if (bulk_rows > 0)
+            k_stitch<0, false><<<STITCH_GRID(bulk_rows), threads, smem, stream>>>(STITCH_ARGS, polar_rows, bulk_rows, 0, bulk_rows);
+        if (polar_rows > 0)
+            k_stitch<0, true><<<STITCH_GRID(2 * polar_rows), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows,
+                                                                                     h - polar_rows, 2 * polar_rows);
     } else {
         if (pass_mask & 1) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
-            if (n_bulk > 0)
-                k_stitch<1, false><<<STITCH_GRID(n_bulk), threads, smem, stream>>>(STITCH_ARGS, polar_rows * w, n_bulk, 0, n_bulk);
-            if (n_polar > 0)
-                k_stitch<1, true><<<STITCH_GRID(n_polar), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows * w,
-                                                                                   (h - polar_rows) * w, n_polar);
+            if (bulk_rows > 0)
+                k_stitch<1, false><<<STITCH_GRID(bulk_rows), threads, smem, stream>>>(STITCH_ARGS, polar_rows, bulk_rows, 0,
+                                                                                     bulk_rows);
+            if (polar_rows > 0)
+                k_stitch<1, true><<<STITCH_GRID(2 * polar_rows), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows,
+                                                                                         h - polar_rows, 2 * polar_rows);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
         if (pass_mask & 2)

@@ -86,55 +86,70 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every few ms through NVML while the timed region runs
+    (nvidia-smi -lms cannot sample a 100 ms region)."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.power = []
+        self._stop = False
+        self._thread = None
+        self._nvml = None
+
+    def _loop(self):
+        n = self._nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        try:
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            import threading
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    self.index = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, smax, power = [], set(), None, []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                parts = [p.strip() for p in ln.split(",")]
-                if len(parts) < 7:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    smax = float(parts[1])
-                    power.append(float(parts[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, parts[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power) if power else None)
+        self._stop = True
+        self._thread.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                       samples=len(self.samples), power_w_max=max(self.power) if self.power else None)
         return out
 
 
@@ -208,6 +223,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.02)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -260,8 +276,16 @@ def run_ours(args):
                             else ["k_stitch<normwarp pass A>", "k_blend_normwarp (pass B)"])
     weight = {k: ktimes[k]["ms"] * (2 if k == "k_erp2ico" else 1) for k in used}
     dominant = max(weight, key=weight.get)
+    traffic = None
+    try:
+        # dram__bytes_read.sum + dram__bytes_write.sum per frame pair from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("erp_h") == args.height and dominant in tr.get("bytes_per_pair", {}):
+            traffic = tr["bytes_per_pair"][dominant] * B
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ktimes[dominant]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": ktimes[dominant]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": ktimes[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": weight[dominant] / sum(weight.values()), "kernels": ktimes}
 
     # ---- end to end through the public host API (pinned host buffers, copies inside the timed region) -------
