@@ -14,9 +14,9 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import ncu_raw_summary  # noqa: E402
 import ncu_source_summary  # noqa: E402
 
-KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_stitch<(int)0", "k_stitch<straightforward>"),
-               ("k_stitch<(int)1", "k_stitch<normwarp pass A>"), ("k_blend_normwarp", "k_blend_normwarp (pass B)"),
-               ("k_lift", "k_lift")]
+KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_stitch<0", "k_stitch<straightforward>"), ("k_stitch<(int)0", "k_stitch<straightforward>"),
+               ("k_stitch<1", "k_stitch<normwarp pass A>"), ("k_stitch<(int)1", "k_stitch<normwarp pass A>"),
+               ("k_blend_normwarp", "k_blend_normwarp (pass B)"), ("k_lift", "k_lift")]
 
 
 def capture(fn, *args):
