@@ -1,5 +1,7 @@
 """Build libtif_b200.so (sm_100a) in-tree with nvcc.  No torch headers are involved: the library is
 plain CUDA runtime + the C ABI of include/tif_b200.h, so it cross-compiles on a box without a GPU."""
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -28,40 +30,56 @@ def _nvcc():
     return exe
 
 
-def _stale(target, sources):
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+def _digest(paths, extra):
+    """Content hash of the sources and flags (mtimes do not survive the copy to the GPU box)."""
+    h = hashlib.sha1()
+    for path in paths:
+        h.update(open(path, "rb").read())
+    h.update(repr(extra).encode())
+    return h.hexdigest()
 
 
 def build_library(force=False, verbose=False):
-    """Compile every CUDA unit for sm_100a and link libtif_b200.so next to this file."""
-    headers = [os.path.join(CSRC, "tif_common.cuh"), os.path.join(INCLUDE, "tif_b200.h"), os.path.abspath(__file__)]
+    """Compile every CUDA unit for sm_100a and link libtif_b200.so next to this file.
+
+    Safe to call from several processes at once (torchrun ranks): the build is serialised with a file
+    lock, skipped when the content hash of sources + flags matches the stamp of the existing library,
+    and the library is replaced atomically."""
     os.makedirs(BUILD_DIR, exist_ok=True)
-    nvcc = _nvcc()
-    objects = []
-    rebuilt = False
-    for unit, extra in UNITS.items():
-        src = os.path.join(CSRC, unit)
-        obj = os.path.join(BUILD_DIR, unit.replace(".cu", ".o"))
-        objects.append(obj)
-        if force or _stale(obj, [src] + headers):
-            defs = os.environ.get("TIF_NVCC_DEFS", "").split()        # experiment knobs, e.g. -DTIF_STITCH_MIN_BLOCKS=6
-            cmd = [nvcc] + ARCH + COMMON + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    defs = os.environ.get("TIF_NVCC_DEFS", "").split()        # experiment knobs, e.g. -DTIF_STITCH_MIN_BLOCKS=6
+    sources = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "tif_common.cuh"),
+                                                        os.path.join(INCLUDE, "tif_b200.h")]
+    want = _digest(sources, (ARCH, COMMON[:4], sorted(UNITS.items()), defs))
+    stamp = os.path.join(BUILD_DIR, "libtif_b200.stamp")
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+                return LIB_PATH
+            nvcc = _nvcc()
+            objects = []
+            for unit, extra in UNITS.items():
+                src = os.path.join(CSRC, unit)
+                obj = os.path.join(BUILD_DIR, unit.replace(".cu", ".o"))
+                objects.append(obj)
+                cmd = [nvcc] + ARCH + COMMON + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if verbose or res.returncode != 0:
+                    print(" ".join(cmd))
+                    print(res.stdout + res.stderr)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed for %s" % unit)
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objects + ["-lcudart"]
             res = subprocess.run(cmd, capture_output=True, text=True)
-            if verbose or res.returncode != 0:
-                print(" ".join(cmd))
-                print(res.stdout + res.stderr)
             if res.returncode != 0:
-                raise RuntimeError("nvcc failed for %s" % unit)
-            rebuilt = True
-    if rebuilt or force or _stale(LIB_PATH, objects):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB_PATH] + objects + ["-lcudart"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            print(res.stdout + res.stderr)
-            raise RuntimeError("nvcc link failed")
+                print(res.stdout + res.stderr)
+                raise RuntimeError("nvcc link failed")
+            os.replace(tmp, LIB_PATH)
+            with open(stamp, "w") as f:
+                f.write(want)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -186,7 +186,19 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL announces its version on stdout when the communicator is created; stdout carries exactly one
+        # JSON line, so route fd 1 to stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     entry.build()
     pkg = entry.load_package()
     ops, lib = pkg._ops, pkg._lib
