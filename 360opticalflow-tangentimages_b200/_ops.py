@@ -60,22 +60,25 @@ def _erp2ico(erp, plan, full_face_image):
 
 def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out, scratch=None, pass_mask=3):
     """tif_ico2erp_flow_f32 on the current stream into a caller-owned [B,H,W,2] float32 tensor.
-    Inputs must be contiguous; `scratch` (uint8, >= tif_ico2erp_scratch_bytes) is needed for normwarp."""
+    Inputs must be contiguous; `scratch` (uint8, >= tif_ico2erp_scratch_bytes) is allocated here when omitted."""
     _need_cuda(tangent_flow, erp_src, erp_tar, out)
     batch = tangent_flow.shape[0]
     if tangent_flow.dtype != torch.float32 or tuple(tangent_flow.shape) != (batch, p.tangent_pixels, 2) or not tangent_flow.is_contiguous():
         raise ValueError("ico2erp_flow expects contiguous float32 [B,%d,2]" % p.tangent_pixels)
     if out.dtype != torch.float32 or tuple(out.shape) != (batch, p.erp_h, p.erp_w, 2) or not out.is_contiguous():
         raise ValueError("ico2erp_flow output must be contiguous float32 [B,%d,%d,2]" % (p.erp_h, p.erp_w))
-    src_ptr = tar_ptr = scratch_ptr = None
+    src_ptr = tar_ptr = None
     if blend == _lib.BLEND_NORMWARP:
         for name, img in (("erp_src", erp_src), ("erp_tar", erp_tar)):
             if img is None or img.dtype != torch.uint8 or tuple(img.shape) != (batch, p.erp_h, p.erp_w, 3) or not img.is_contiguous():
                 raise ValueError("normwarp needs contiguous uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
-        need = p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend)
-        if scratch is None or scratch.numel() * scratch.element_size() < need:
-            raise ValueError("normwarp needs %d bytes of scratch" % need)
-        src_ptr, tar_ptr, scratch_ptr = erp_src.data_ptr(), erp_tar.data_ptr(), scratch.data_ptr()
+        src_ptr, tar_ptr = erp_src.data_ptr(), erp_tar.data_ptr()
+    need = int(p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend))
+    if scratch is None:
+        scratch = torch.empty(need, dtype=torch.uint8, device=tangent_flow.device)
+    elif scratch.numel() * scratch.element_size() < need:
+        raise ValueError("ico2erp_flow needs %d bytes of scratch" % need)
+    scratch_ptr = scratch.data_ptr()
     with torch.cuda.device(tangent_flow.device):
         _lib.check(p.lib.tif_ico2erp_flow_f32_ex(p.handle, tangent_flow.data_ptr(), src_ptr, tar_ptr, batch, int(blend),
                                                  int(wrap_around), out.data_ptr(), scratch_ptr, int(pass_mask), _stream()),
@@ -86,28 +89,13 @@ def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out,
 def _ico2erp_flow(tangent_flow, erp_src, erp_tar, plan, blend, wrap_around):
     p = _registry[plan]
     _need_cuda(tangent_flow, erp_src, erp_tar)
-    if tangent_flow.dtype != torch.float32 or tangent_flow.dim() != 3 or tangent_flow.shape[1:] != (p.tangent_pixels, 2):
-        raise ValueError("ico2erp_flow expects float32 [B,%d,2], got %s %s" %
-                         (p.tangent_pixels, tangent_flow.dtype, tuple(tangent_flow.shape)))
-    batch = tangent_flow.shape[0]
     tangent_flow = tangent_flow.contiguous()
-    src_ptr = tar_ptr = scratch_ptr = None
-    scratch = None
     if blend == _lib.BLEND_NORMWARP:
-        for name, img in (("erp_src", erp_src), ("erp_tar", erp_tar)):
-            if img is None or img.dtype != torch.uint8 or tuple(img.shape) != (batch, p.erp_h, p.erp_w, 3):
-                raise ValueError("normwarp needs uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
+        if erp_src is None or erp_tar is None:
+            raise ValueError("normwarp needs erp_src and erp_tar")
         erp_src, erp_tar = erp_src.contiguous(), erp_tar.contiguous()
-        src_ptr, tar_ptr = erp_src.data_ptr(), erp_tar.data_ptr()
-        nbytes = p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend)
-        scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=tangent_flow.device)
-        scratch_ptr = scratch.data_ptr()
-    out = torch.empty((batch, p.erp_h, p.erp_w, 2), dtype=torch.float32, device=tangent_flow.device)
-    with torch.cuda.device(tangent_flow.device):
-        _lib.check(p.lib.tif_ico2erp_flow_f32(p.handle, tangent_flow.data_ptr(), src_ptr, tar_ptr, batch, int(blend),
-                                              int(wrap_around), out.data_ptr(), scratch_ptr, _stream()),
-                   "tif_ico2erp_flow_f32")
-    return out
+    out = torch.empty((tangent_flow.shape[0], p.erp_h, p.erp_w, 2), dtype=torch.float32, device=tangent_flow.device)
+    return ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out)
 
 
 def _flow_dtype(flow):

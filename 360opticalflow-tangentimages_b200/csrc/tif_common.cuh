@@ -50,6 +50,8 @@ struct TifPlan {
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
     uint32_t* d_s2_offset;         // [H*W] exclusive prefix sum of d_s2_count: first slot of a pixel's samples
+    float2* d_s2_snap;             // [K][H*W] ERP position of the sample's tangent pixel minus the ERP pixel (x wrapped to +-W/2)
+    uint8_t* d_ref_mark;           // [P] 1 where a tangent pixel is referenced by at least one ERP pixel
     double* d_col_theta;           // [W] theta of every ERP column
     float2* d_row_sc;              // [H] (sin phi_r, cos phi_r) in float32
     float2* d_col_sc;              // [F][W] (sin, cos)(theta_c - theta0_f) in float32

@@ -250,28 +250,32 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // ------------------------------------------------------------------------------------------------
 // stage 2+3: tangent flows -> ERP flow
 // ------------------------------------------------------------------------------------------------
+// The end point of a flow vector depends only on the tangent pixel it starts from: several ERP pixels snap to
+// the same nearest tangent pixel (5.59 M accepted samples reference 1.95 M tangent pixels at 2K), and the
+// reference lifts the same end point once per sample.  Here the expensive part runs once per referenced
+// tangent pixel:
+//   k_lift    tangent pixel -> displacement of the flow end point from the pixel's own ERP position
+//             (+ the bilinear sample of the target image at the end point, for normwarp)
+//   k_gather  ERP pixel -> for every accepting face: flow = displacement + (tangent pixel position - ERP pixel),
+//             seam convention, weights, blend.  The second term is a plan constant (d_s2_snap).
 #ifndef TIF_STITCH_THREADS
-#define TIF_STITCH_THREADS 128
+#define TIF_STITCH_THREADS 256
 #endif
-#ifndef TIF_STITCH_MIN_BLOCKS
-#define TIF_STITCH_MIN_BLOCKS 8       // 64 registers per thread: occupancy over a few spilled values
-#endif
-// rows whose sin(colatitude) is below this use the float64 end-point lift: an end point next to the polar
-// axis needs the float64 products of the flow (the float32 local frame cancels there), and under normwarp
-// the faces disagree by hundreds of ERP pixels next to the poles, so the photometric weights turn an
-// end-point error of 1e-4 px into a flow error above the 1e-3 px tolerance
-#define TIF_POLAR_SIN 0.1f
+// tangent pixels (or end points) whose sin(colatitude) is below this take the float64 lift: next to the poles
+// the direction vector cancels in float32, and under normwarp the faces disagree by hundreds of ERP pixels
+// there, so the photometric weights turn a 1e-4 px error of the sampling position into a flow error above
+// the 1e-3 px tolerance
+#define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
+#define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
 
-struct FaceConst {          // per-face constants of the end-point lift, staged in shared memory
+struct LiftFace {          // per-face constants of the end-point lift, staged in shared memory
     double sin_phi0, cos_phi0;
     double xmin, ymax;
     double kx, ky;              // 1 / pixel2gnomonic ratios (gnomonic_projection.py:188-194)
-    double ky_sin, ky_cos;      // ky * sin(phi0), ky * cos(phi0)
-    int pix_offset;
+    int first_row;              // first row of the face in the tangent stack
     int pad;
 };
 
-// atan(y/x) for x > 0 and |y| <= 0.4143 x: q + q s P(s); max abs error 2.3e-8
 // reciprocal for x in the normal range: MUFU.RCP + one Newton step (no denormal / range branches)
 __device__ __forceinline__ float rcp_newton(float x) {
     float r;
@@ -287,6 +291,7 @@ __device__ __forceinline__ float sqrt_newton(float x) {
     return fmaf(0.5f * r, fmaf(-h, h, x), h);
 }
 
+// atan(y/x) for x > 0 and |y| <= 0.4143 x: q + q s P(s); max abs error 2.3e-8
 __device__ __forceinline__ float atan_small(float y, float x) {
     const float q = y * rcp_newton(x);
     const float s = q * q;
@@ -312,8 +317,8 @@ __device__ __forceinline__ float atan_unit(float q) {
     return fmaf(r, q * s, q);
 }
 
-// atan2(y, x) in (-pi, pi].  The common case of the stitch (a small angle between the flow end point
-// and its source pixel) takes the short polynomial; everything else the full octant reduction.
+// atan2(y, x) in (-pi, pi].  The common case (a small angle between the flow end point and its start) takes
+// the short polynomial; everything else the full octant reduction.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     if (x > 0.0f && ay <= 0.4143f * x) return atan_small(y, x);
@@ -324,25 +329,6 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     if (x < 0.0f) r = (float)TIF_PI - r;
     return y < 0.0f ? -r : r;
 }
-
-struct SampleGeom {       // per (ERP pixel, accepting face): constant over the batch
-    double gx0, bz0, cy0;           // direction of the tangent pixel centre: gx, cos(phi0) - gy sin(phi0), sin(phi0) + gy cos(phi0)
-    double kx, ky_sin, ky_cos;
-    // float32 local frame of the source pixel (bulk rows): the end point is the source direction plus a small
-    // displacement (dx, dy) on the tangent plane, decomposed into east / north / radial parts
-    float d0x, d0y;                 // tangent-pixel centre minus the source pixel's own gnomonic position
-    float kxf, kyf;
-    float e1, e2, n1, n2, u1, u2, u0;
-    int tpix;
-    int face;
-    float mult;
-};
-
-struct Lifted {
-    float fu, fv;         // ERP flow of this face at this pixel
-    int xi, yi;           // floor(fu), floor(fv)
-    float fx, fy;         // fu - floor(fu), fv - floor(fv): bilinear fractions of the end point
-};
 
 // floor / fraction without the XU pipe (|x| < 2^22): round to nearest with the 1.5*2^23 trick, then fix down
 __device__ __forceinline__ void split_floor(float x, int& xi, float& frac) {
@@ -355,198 +341,228 @@ __device__ __forceinline__ void split_floor(float x, int& xi, float& frac) {
     }
 }
 
-// End point of one accepted sample, projection_icosahedron.py:336-366, written as two rotations:
-//   direction of the end point  d = (gx, cos(phi0) - gy sin(phi0), sin(phi0) + gy cos(phi0))
-//       [reverse_gnomonic_projection (gnomonic_projection.py:76-85) with sin c = rho cos c divided out;
-//        gx, gy = pixel2gnomonic (:186-194) of (ix + u, iy + v)]
-//   delta_theta  = atan2 of (d.x, d.y) rotated back by (theta_src - theta0)      -> u = delta_theta * W / 2 pi
-//   delta_colat  = atan2 of (hypot(d.x, d.y), d.z) rotated back by colat_src     -> v = delta_colat * H / pi
-// Both arctangents see the small angle between end point and source pixel, so float32 keeps a relative
-// precision of 1e-7 on the flow itself.  delta_theta in (-pi, pi] is the reference's flow after its seam
-// fix (:350-361); without wrap_around the reference leaves theta_t wrapped into [-pi, pi) instead
-// (spherical_coordinates.py:237,59), restored at the end.
-//
-// PRECISE = false: float32 throughout (end point away from the poles).
-// PRECISE = true : direction and rotations in float64, CUDA's double atan2/sqrt (rows next to the poles,
-//                  where d.x, d.y cancel and a rotation by a float32 sine loses the small polar radius).
-template <bool PRECISE>
-__device__ __forceinline__ Lifted lift_endpoint(const SampleGeom& G, float u, float v, float sin_colat_src,
-                                                float cos_colat_src, double sin_cs64, double cos_cs64, double sin_d64,
-                                                double cos_d64, float theta_src, float u_scale, float v_scale,
-                                                double u_scale64, double v_scale64, float erp_wf, bool wrap_around) {
-    Lifted o;
-    if (PRECISE) {
-        const double a = fma((double)u, G.kx, G.gx0);
-        const double b = fma((double)v, G.ky_sin, G.bz0);
-        const double c = fma(-(double)v, G.ky_cos, G.cy0);
-        const double xr = fma(b, cos_d64, a * sin_d64);
-        const double yr = fma(a, cos_d64, -b * sin_d64);
-        double dtheta = atan2(yr, xr);
-        const double h = sqrt(fma(xr, xr, yr * yr));
-        const double xc = fma(c, cos_cs64, h * sin_cs64);
-        const double yc = fma(h, cos_cs64, -c * sin_cs64);
-        const double dcolat = atan2(yc, xc);
-        // bilinear fractions from the wrapped (small) flow; the seam convention then moves whole images
-        const double fu = dtheta * u_scale64, fv = dcolat * v_scale64;
-        const double fiu = floor(fu), fiv = floor(fv);
-        o.xi = (int)fiu;
-        o.yi = (int)fiv;
-        o.fx = (float)(fu - fiu);
-        o.fy = (float)(fv - fiv);
-        o.fu = (float)fu;
-        o.fv = (float)fv;
-        if (!wrap_around) {
-            const double tt = (double)theta_src + dtheta;
-            if (tt >= TIF_PI) { o.fu -= erp_wf; o.xi -= (int)erp_wf; }
-            else if (tt < -TIF_PI) { o.fu += erp_wf; o.xi += (int)erp_wf; }
-        }
-        return o;
-    }
-    // displacement of the end point from the source pixel on the tangent plane (gnomonic units, y up)
-    const float dx = fmaf(u, G.kxf, G.d0x);
-    const float dy = fmaf(-v, G.kyf, G.d0y);
-    // east / north / radial components in the source pixel's local frame: small terms stay small, so
-    // float32 keeps ~1e-7 relative precision on the flow itself instead of on the O(1) direction vector
-    const float E = fmaf(dy, G.e1, dx * G.e2);
-    const float N = fmaf(dy, G.n1, dx * G.n2);
-    const float U = fmaf(dy, G.u1, fmaf(dx, G.u2, G.u0));
-    // sin_colat_src = cos(phi_src), cos_colat_src = sin(phi_src)
-    const float rm = fmaf(U, sin_colat_src, -N * cos_colat_src);       // horizontal part in the source meridian plane
-    const float z = fmaf(U, cos_colat_src, N * sin_colat_src);         // part along the polar axis
-    float dtheta = atan2_fast(E, rm);
-    const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
-    // h cos(colat_s) - z sin(colat_s) = -N + (h - rm) cos(colat_s), and h - rm = E^2 / (h + rm)
-    const float yc = rm > 0.0f ? fmaf(E * E, cos_colat_src * rcp_newton(h + rm), -N)
-                               : fmaf(h, cos_colat_src, -z * sin_colat_src);
-    const float xc = fmaf(z, cos_colat_src, h * sin_colat_src);
-    const float dcolat = atan2_fast(yc, xc);
-    o.fu = dtheta * u_scale;
-    o.fv = dcolat * v_scale;
-    split_floor(o.fu, o.xi, o.fx);
-    split_floor(o.fv, o.yi, o.fy);
-    if (!wrap_around) {
-        const float tt = theta_src + dtheta;
-        if (tt >= (float)TIF_PI) { o.fu -= erp_wf; o.xi -= (int)erp_wf; }
-        else if (tt < -(float)TIF_PI) { o.fu += erp_wf; o.xi += (int)erp_wf; }
-    }
-    return o;
-}
-
 // byte k of w as float via the 2^23 mantissa trick (PRMT + FADD, both full rate; I2F would use the XU pipe)
 __device__ __forceinline__ float byte_f(uint32_t w, unsigned k) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | k)) - 8388608.0f;
 }
 
-// sum over channels of |bilinear(tar, end point) - src[r,c]| with scipy mode='constant', cval=255
-// (projection.py:52-55): any coordinate outside [0, n-1] reads 255 outright.
-__device__ __forceinline__ float warp_error_sum(const uint8_t* __restrict__ tar, bool tail_image, float s0, float s1,
-                                                float s2, const Lifted& L, int r, int c, int erp_h, int erp_w) {
-    int x0 = c + L.xi, y0 = r + L.yi;
-    float fx = L.fx, fy = L.fy;
-    float t0, t1, t2;
-    // inside iff 0 <= x0 + fx <= W-1 and 0 <= y0 + fy <= H-1
-    const bool x_ok = ((unsigned)x0 < (unsigned)(erp_w - 1)) | ((x0 == erp_w - 1) & (fx == 0.0f));
-    const bool y_ok = ((unsigned)y0 < (unsigned)(erp_h - 1)) | ((y0 == erp_h - 1) & (fy == 0.0f));
-    if (!(x_ok & y_ok)) {
-        t0 = t1 = t2 = 255.0f;
-    } else {
-        if (x0 == erp_w - 1) { x0 = erp_w - 2; fx = 1.0f; }
-        if (y0 == erp_h - 1) { y0 = erp_h - 2; fy = 1.0f; }
-        const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
-        const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
-        const uint8_t* r0 = tar + (unsigned)((y0 * erp_w + x0) * 3);
-        const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
-        uint32_t lo0, hi0, lo1, hi1;
-        if (tail_image & (y0 == erp_h - 2) & (x0 >= erp_w - 6)) {   // wide loads could leave the buffer
-            load_tap_pair_bytes(r0, lo0, hi0);
-            load_tap_pair_bytes(r1, lo1, hi1);
-        } else {
-            load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
-            load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
-        }
-        t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
-        t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
-        t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
-    }
-    return fabsf(t0 - s0) + fabsf(t1 - s1) + fabsf(t2 - s2);
+// float64 lift for the rare polar cases: both directions through CUDA's double atan2 / sqrt.
+// (gx0, gy0): gnomonic position of the tangent pixel; returns the longitude / colatitude differences.
+__device__ __noinline__ void lift_precise(double gx0, double gy0, double s0, double c0, double kx, double ky, float u,
+                                          float v, double* dtheta, double* dcolat) {
+    const double b0 = fma(-gy0, s0, c0), z0 = fma(gy0, c0, s0);
+    const double gx = fma((double)u, kx, gx0), gy = fma(-(double)v, ky, gy0);
+    const double b1 = fma(-gy, s0, c0), z1 = fma(gy, c0, s0);
+    double d = atan2(gx, b1) - atan2(gx0, b0);
+    if (d > TIF_PI) d -= TIF_TWO_PI;
+    else if (d <= -TIF_PI) d += TIF_TWO_PI;
+    *dtheta = d;
+    *dcolat = atan2(sqrt(fma(gx, gx, b1 * b1)), z1) - atan2(sqrt(fma(gx0, gx0, b0 * b0)), z0);
 }
 
-__device__ __forceinline__ void load_face_consts(FaceConst* sh, const TifFace* __restrict__ faces, int n_faces) {
+// Displacement of the flow end point of ONE tangent pixel, projection_icosahedron.py:336-347:
+//   pixel2gnomonic (gnomonic_projection.py:186-194) of (ix + u, iy + v), reverse_gnomonic_projection (:76-85),
+//   sph_coord_modulo + sph2erp (spherical_coordinates.py:237-238, 59-60, 122-124),
+// written in the local east / north / radial frame of the tangent pixel's own direction: the end point is that
+// direction plus the small tangent-plane step (u kx, -v ky), so
+//   delta_theta = atan2(E, rho)     delta_colat = atan2(-N + E^2 cos / (h + rho), ...)
+// see small angles and float32 keeps ~1e-7 relative precision on the displacement itself.
+// The result is (delta_theta W / 2 pi, delta_colat H / pi); k_gather adds the pixel's own ERP position.
+template <bool NW>
+__global__ void __launch_bounds__(256)
+k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
+       const uint8_t* __restrict__ ref_mark, const double* __restrict__ s1_ex, const double* __restrict__ s1_ey,
+       const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar, void* __restrict__ records, int erp_h,
+       int erp_w, int tangent_w, int n_tangent, int batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
         const TifFace& F = faces[f];
-        FaceConst fc;
-        fc.sin_phi0 = F.sin_phi0;
-        fc.cos_phi0 = F.cos_phi0;
-        fc.xmin = F.xmin;
-        fc.ymax = F.ymax;
-        fc.kx = 1.0 / F.p2g_x;
-        fc.ky = 1.0 / F.p2g_y;
-        fc.ky_sin = fc.ky * F.sin_phi0;
-        fc.ky_cos = fc.ky * F.cos_phi0;
-        fc.pix_offset = F.pix_offset;
-        fc.pad = 0;
-        sh[f] = fc;
+        LiftFace lf;
+        lf.sin_phi0 = F.sin_phi0;
+        lf.cos_phi0 = F.cos_phi0;
+        lf.xmin = F.xmin;
+        lf.ymax = F.ymax;
+        lf.kx = 1.0 / F.p2g_x;
+        lf.ky = 1.0 / F.p2g_y;
+        lf.first_row = F.pix_offset / tangent_w;
+        lf.pad = 0;
+        sh_face[f] = lf;
+    }
+    __syncthreads();
+    int trow, tcol;
+    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, tangent_w, n_tangent / tangent_w, trow, tcol)) return;
+    const int p = trow * tangent_w + tcol;
+    if (!ref_mark[p]) return;                       // no ERP pixel ever reads this tangent pixel
+    const LiftFace& F = sh_face[row_face[trow]];
+    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+
+    // ---- per tangent pixel, once for the chunk of images -------------------------------------------------
+    const double gx0 = fma((double)tcol, F.kx, F.xmin);
+    const double gy0 = fma(-(double)(trow - F.first_row), F.ky, F.ymax);
+    // own direction (east, toward the face meridian, polar axis) before normalisation
+    const float a0 = (float)gx0;
+    const float bz0 = (float)fma(-gy0, F.sin_phi0, F.cos_phi0);
+    const float cy0 = (float)fma(gy0, F.cos_phi0, F.sin_phi0);
+    const float hp2 = fmaf(a0, a0, bz0 * bz0), n2 = hp2 + cy0 * cy0;
+    const bool polar_pixel = hp2 < TIF_POLAR_SIN2 * n2;
+    const float inv_hp = rsqrtf(fmaxf(hp2, 1e-30f)), inv_n = rsqrtf(n2);
+    const float sp = cy0 * inv_n, cp = hp2 * inv_hp * inv_n;       // sin / cos of the pixel's latitude
+    const float cos_d = bz0 * inv_hp, sin_d = a0 * inv_hp;        // longitude of the pixel against the face meridian
+    const float s0 = (float)F.sin_phi0, c0 = (float)F.cos_phi0;
+    const float e1 = s0 * sin_d, e2 = cos_d;
+    const float n1 = fmaf(s0 * sp, cos_d, c0 * cp), n2c = -sp * sin_d;
+    const float u1 = fmaf(-s0 * cp, cos_d, c0 * sp), u2 = cp * sin_d;
+    const float u0 = n2 * inv_n;
+    const float kxf = (float)F.kx, kyf = (float)F.ky;
+    const float u_scale = (float)((double)erp_w / TIF_TWO_PI), v_scale = (float)((double)erp_h / TIF_PI);
+    // own ERP position (plan stage 1), split into integer and fraction for the target sample
+    int exi = 0, eyi = 0;
+    float exf = 0.0f, eyf = 0.0f;
+    double ex = 0.0, ey = 0.0;
+    if (NW) {
+        ex = s1_ex[p];
+        ey = s1_ey[p];
+        const double fxi = floor(ex), fyi = floor(ey);
+        exi = (int)fxi;
+        eyi = (int)fyi;
+        exf = (float)(ex - fxi);
+        eyf = (float)(ey - fyi);
+    }
+    const unsigned image_bytes = (unsigned)erp_h * (unsigned)erp_w * 3u;
+    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
+    const uint8_t* __restrict__ tar_chunk = NW ? erp_tar + (size_t)b0 * image_bytes : nullptr;
+
+#pragma unroll
+    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        const int b = b0 + bb;
+        if (b >= batch) break;
+        const float2 uv = __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p));
+        const float dx = uv.x * kxf, dy = -uv.y * kyf;
+        const float E = fmaf(dy, e1, dx * e2);
+        const float N = fmaf(dy, n1, dx * n2c);
+        const float U = fmaf(dy, u1, fmaf(dx, u2, u0));
+        const float rm = fmaf(U, cp, -N * sp);          // horizontal part in the pixel's meridian plane
+        const float z = fmaf(U, sp, N * cp);            // part along the polar axis
+        const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
+        float disp_x, disp_y, fx, fy;
+        int xi, yi;
+        if (polar_pixel || h < 0.1f * fabsf(z)) {       // pixel or end point within ~5.7 degrees of a pole
+            double dth, dco;
+            lift_precise(gx0, gy0, F.sin_phi0, F.cos_phi0, F.kx, F.ky, uv.x, uv.y, &dth, &dco);
+            const double px = dth * ((double)erp_w / TIF_TWO_PI), py = dco * ((double)erp_h / TIF_PI);
+            disp_x = (float)px;
+            disp_y = (float)py;
+            if (NW) {
+                const double ax = ex + px, ay = ey + py;
+                const double fax = floor(ax), fay = floor(ay);
+                xi = (int)fax;
+                yi = (int)fay;
+                fx = (float)(ax - fax);
+                fy = (float)(ay - fay);
+            }
+        } else {
+            const float dtheta = atan2_fast(E, rm);
+            // h sin(lat) - z cos(lat) = -N + (h - rm) sin(lat), and h - rm = E^2 / (h + rm)
+            const float yc = rm > 0.0f ? fmaf(E * E, sp * rcp_newton(h + rm), -N) : fmaf(h, sp, -z * cp);
+            const float xc = fmaf(z, sp, h * cp);
+            const float dcolat = atan2_fast(yc, xc);
+            disp_x = dtheta * u_scale;
+            disp_y = dcolat * v_scale;
+            if (NW) {
+                int di, dj;
+                float df, dg;
+                split_floor(disp_x, di, df);
+                split_floor(disp_y, dj, dg);
+                xi = exi + di;
+                yi = eyi + dj;
+                fx = exf + df;
+                fy = eyf + dg;
+                if (fx >= 1.0f) { fx -= 1.0f; xi += 1; }
+                if (fy >= 1.0f) { fy -= 1.0f; yi += 1; }
+            }
+        }
+        if (!NW) {
+            reinterpret_cast<float2*>(records)[(size_t)b * n_tangent + p] = make_float2(disp_x, disp_y);
+            continue;
+        }
+        // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
+        // periodic (the seam conventions only move the end point by whole image widths), the gap (W-1, W) and
+        // anything outside [0, H-1] vertically reads 255 outright
+        xi -= erp_w * (int)floorf((float)xi / (float)erp_w);        // into [0, W)
+        if (xi >= erp_w) xi -= erp_w;
+        if (xi < 0) xi += erp_w;
+        float t0, t1, t2;
+        const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx == 0.0f));
+        const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy == 0.0f));
+        if (!(x_ok & y_ok)) {
+            t0 = t1 = t2 = 255.0f;
+        } else {
+            if (xi == erp_w - 1) { xi = erp_w - 2; fx = 1.0f; }
+            if (yi == erp_h - 1) { yi = erp_h - 2; fy = 1.0f; }
+            const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
+            const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
+            const uint8_t* r0 = tar_chunk + ((unsigned)bb * image_bytes + (unsigned)((yi * erp_w + xi) * 3));
+            const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
+            uint32_t lo0, hi0, lo1, hi1;
+            if ((b == batch - 1) & (yi == erp_h - 2) & (xi >= erp_w - 6)) {     // wide loads could leave the buffer
+                load_tap_pair_bytes(r0, lo0, hi0);
+                load_tap_pair_bytes(r1, lo1, hi1);
+            } else {
+                load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
+                load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
+            }
+            t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
+            t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
+            t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
+        }
+        const unsigned long long q0 = __float2uint_rn(t0 * TIF_RGB_FIX), q1 = __float2uint_rn(t1 * TIF_RGB_FIX),
+                                 q2 = __float2uint_rn(t2 * TIF_RGB_FIX);
+        const unsigned long long packed = q0 | (q1 << 21) | (q2 << 42);
+        reinterpret_cast<uint4*>(records)[(size_t)b * n_tangent + p] =
+            make_uint4(__float_as_uint(disp_x), __float_as_uint(disp_y), (unsigned)packed, (unsigned)(packed >> 32));
     }
 }
 
-// MODE 0: straightforward blend.
-// MODE 1: normwarp pass A: lifts every accepted sample once, stores (fu, fv, sum_ch |diff|) in the sample
-//         scratch and accumulates the face-global warp-error sums; k_blend_normwarp finishes the job.
-// POLAR selects the float64 end-point lift; it is launched on the polar row bands only.
-// The launch covers two row segments, [seg0_row, seg0_row + seg0_rows) then [seg1_row, ...), seg_rows rows in
-// all; a warp owns an 8 x 4 pixel tile of them (compact footprint in the tangent flows and the target image).
-template <int MODE, bool POLAR>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS, POLAR ? 4 : TIF_STITCH_MIN_BLOCKS)
-k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
-         const uint32_t* __restrict__ s2_entries, const double* __restrict__ col_theta,
-         const float2* __restrict__ row_sc, const float2* __restrict__ col_sc,
-         const double2* __restrict__ row_sc64, const double2* __restrict__ col_sc64,
-         const double* __restrict__ face_mult_sum, const float* __restrict__ tflow,
-         const uint8_t* __restrict__ erp_src, const uint8_t* __restrict__ erp_tar,
-         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, const uint32_t* __restrict__ s2_offset,
-         float* __restrict__ nw_samples /* [B][3][S]: fu, fv, |diff| sum of every accepted sample */, int64_t n_samples,
-         float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around,
-         int seg0_row, int seg0_rows, int seg1_row, int seg_rows) {
+// MODE 0: straightforward blend.  MODE 1: normwarp pass A (face-global warp-error sums, order-independent fixed
+// point).  MODE 2: normwarp pass B (weights from the sums of pass A, blend).  One thread per ERP pixel and chunk
+// of images; a warp owns an 8 x 4 pixel tile.
+template <int MODE>
+__global__ void __launch_bounds__(TIF_STITCH_THREADS)
+k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
+         const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
+         const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
+         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, float* __restrict__ out, int erp_h, int erp_w,
+         int tangent_w, int n_tangent, int batch, int wrap_around) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FaceConst* sh_face = reinterpret_cast<FaceConst*>(smem_raw);
-    unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_face + n_faces);      // MODE 1: per-block partial sums
-
+    int* sh_offset = reinterpret_cast<int*>(smem_raw);                       // [F] first pixel of each face
+    unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_offset + n_faces);      // MODE 1: [CHUNK][F] partial sums
+    float* sh_inv_mean = reinterpret_cast<float*>(sh_offset + n_faces);      // MODE 2: [CHUNK][F] 1 / (3 mean)
     const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
-    load_face_consts(sh_face, faces, n_faces);
+    for (int f = threadIdx.x; f < n_faces; f += blockDim.x) sh_offset[f] = faces[f].pix_offset;
     if (MODE == 1) {
         for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) sh_sum[i] = 0u;
+    } else if (MODE == 2) {
+        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
+            const int bb = i / n_faces, f = i - bb * n_faces;
+            float inv = 0.0f;
+            if (b0 + bb < batch) {
+                // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
+                const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
+                const double mean = total / (3.0 * face_mult_sum[f]);
+                inv = (float)(1.0 / (3.0 * mean));
+            }
+            sh_inv_mean[i] = inv;
+        }
     }
     __syncthreads();
 
     const int n_pix = erp_h * erp_w;
-    int vrow, vcol;
-    const bool live = tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, seg_rows, vrow, vcol);
-    const int pix = !live ? 0 : (vrow < seg0_rows ? seg0_row + vrow : seg1_row + (vrow - seg0_rows)) * erp_w + vcol;
-    int cnt = 0, r = 0, c = 0;
-    float theta_src = 0.0f, sin_cs = 0.0f, cos_cs = 1.0f;
-    double sin_cs64 = 0.0, cos_cs64 = 1.0;
-    uint32_t sample0 = 0;
-    if (live) {
-        cnt = s2_count[pix];
-        if (MODE == 1) sample0 = s2_offset[pix];
-        r = pix / erp_w;
-        c = pix - r * erp_w;
-        theta_src = (float)col_theta[c];
-        const float2 rs = row_sc[r];        // (sin phi, cos phi) of the source row = (cos, sin) of its colatitude
-        cos_cs = rs.x;
-        sin_cs = rs.y;
-    }
-    const bool polar = POLAR;
-    double sin_phi64 = 0.0, cos_phi64 = 1.0;
-    if (live) {
-        const double2 rs = row_sc64[r];
-        sin_phi64 = rs.x;
-        cos_phi64 = rs.y;
-        cos_cs64 = rs.x;
-        sin_cs64 = rs.y;
-    }
-    const double u_scale64 = (double)erp_w / TIF_TWO_PI, v_scale64 = (double)erp_h / TIF_PI;
-    const float u_scale = (float)u_scale64, v_scale = (float)v_scale64;
+    int r, c;
+    const bool live = tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, erp_h, r, c);
+    const int pix = live ? r * erp_w + c : 0;
+    const int cnt = live ? (int)s2_count[pix] : 0;
+    const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
     float acc_u[TIF_BATCH_CHUNK], acc_v[TIF_BATCH_CHUNK], acc_w[TIF_BATCH_CHUNK];
     float sp[TIF_BATCH_CHUNK][3];
 #pragma unroll
@@ -554,13 +570,7 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
         sp[bb][0] = sp[bb][1] = sp[bb][2] = 0.0f;
     }
-    // addresses inside the chunk of TIF_BATCH_CHUNK images are 32-bit offsets from per-chunk base pointers
-    // (4 images of flows / pixels / samples stay far below 4 GB), which keeps 64-bit integer maths out of the loop
     const unsigned image_bytes = (unsigned)n_pix * 3u;
-    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
-    const uint8_t* __restrict__ tar_chunk = erp_tar + (size_t)b0 * image_bytes;
-    float* __restrict__ smp_chunk = nw_samples + (size_t)b0 * 3 * n_samples;
-    const unsigned n_smp = (unsigned)n_samples;
     if (MODE != 0 && live) {
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
@@ -572,92 +582,72 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             }
         }
     }
+    const float2* __restrict__ disp_chunk = reinterpret_cast<const float2*>(records) + (size_t)b0 * n_tangent;
+    const uint4* __restrict__ rec_chunk = reinterpret_cast<const uint4*>(records) + (size_t)b0 * n_tangent;
 
     const int max_cnt = (MODE == 1) ? __reduce_max_sync(0xffffffffu, cnt) : cnt;
-    uint32_t e_next = (cnt > 0) ? __ldg(s2_entries + pix) : 0u;   // cnt == 0 for dead lanes
     for (int k = 0; k < max_cnt; ++k) {
         const bool has = k < cnt;
-        const uint32_t e = e_next;
-        if (k + 1 < cnt) e_next = __ldg(s2_entries + (size_t)(k + 1) * n_pix + pix);     // prefetch the next entry
-        SampleGeom G;
-        double sin_d64 = 0.0, cos_d64 = 1.0;
-        {
-            const int f = (int)TIF_E_FACE(e);
-            const FaceConst& F = sh_face[f];
-            const int ix = (int)TIF_E_IX(e), iy = (int)TIF_E_IY(e);
-            // pixel2gnomonic of the tangent pixel centre; the flow moves it by (u kx, -v ky)
-            G.gx0 = fma((double)ix, F.kx, F.xmin);
-            const double gy0 = fma(-(double)iy, F.ky, F.ymax);
-            G.bz0 = fma(-gy0, F.sin_phi0, F.cos_phi0);
-            G.cy0 = fma(gy0, F.cos_phi0, F.sin_phi0);
-            G.kx = F.kx;
-            G.ky_sin = F.ky_sin;
-            G.ky_cos = F.ky_cos;
-            G.kxf = (float)F.kx;
-            G.kyf = (float)F.ky;
-            G.tpix = F.pix_offset + iy * tangent_w + ix;
-            G.face = f;
-            G.mult = (float)TIF_E_MULT(e);
-            double2 cs64 = make_double2(0.0, 1.0);
-            if (has) cs64 = __ldg(col_sc64 + f * erp_w + c);        // (sin, cos)(theta_src - theta0), host numpy values
-            sin_d64 = cs64.x;
-            cos_d64 = cs64.y;
-            if (!POLAR) {
-                // the source pixel's own gnomonic position on this face (gnomonic_projection.py:36-44) and the
-                // local east / north / radial frame there, once per (pixel, face) in float64
-                const double sp = sin_phi64, cp = cos_phi64, s0 = F.sin_phi0, c0 = F.cos_phi0;
-                const double cos_c = fma(c0 * cp, cos_d64, s0 * sp);
-                const double inv = 1.0 / cos_c;
-                const double gxs = cp * sin_d64 * inv;
-                const double gys = fma(-s0 * cp, cos_d64, c0 * sp) * inv;
-                G.d0x = (float)(G.gx0 - gxs);
-                G.d0y = (float)(gy0 - gys);
-                G.u0 = (float)inv;
-                G.e1 = (float)(s0 * sin_d64);
-                G.e2 = (float)cos_d64;
-                G.n1 = (float)fma(s0 * sp, cos_d64, c0 * cp);
-                G.n2 = (float)(-sp * sin_d64);
-                G.u1 = (float)fma(-s0 * cp, cos_d64, c0 * sp);
-                G.u2 = (float)(cp * sin_d64);
-            }
+        uint32_t e = 0u;
+        float2 sn = make_float2(0.0f, 0.0f);
+        if (has) {
+            e = __ldg(s2_entries + (size_t)k * n_pix + pix);
+            sn = __ldg(s2_snap + (size_t)k * n_pix + pix);
         }
-        const int f = G.face;
+        const int f = (int)TIF_E_FACE(e);
+        const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
+        const float mult = (float)TIF_E_MULT(e);
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
             const int b = b0 + bb;
             if (b >= batch) break;
-            float dsum = 0.0f;
-            Lifted L;
-            L.fu = L.fv = 0.0f;
+            float fu = 0.0f, fv = 0.0f, dsum = 0.0f;
             if (has) {
-                const float2 uv = __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)G.tpix));
-                if (polar)
-                    L = lift_endpoint<true>(G, uv.x, uv.y, sin_cs, cos_cs, sin_cs64, cos_cs64, sin_d64, cos_d64, theta_src,
-                                            u_scale, v_scale, u_scale64, v_scale64, (float)erp_w, wrap_around != 0);
-                else
-                    L = lift_endpoint<false>(G, uv.x, uv.y, sin_cs, cos_cs, 0.0, 1.0, 0.0, 1.0, theta_src, u_scale, v_scale,
-                                             0.0, 0.0, (float)erp_w, wrap_around != 0);
-                if (MODE != 0)
-                    dsum = warp_error_sum(tar_chunk + (unsigned)bb * image_bytes, b == batch - 1, sp[bb][0], sp[bb][1], sp[bb][2],
-                                          L, r, c, erp_h, erp_w);
+                float2 d;
+                uint32_t plo = 0u, phi = 0u;
+                if (MODE == 0) {
+                    d = __ldg(disp_chunk + ((unsigned)bb * (unsigned)n_tangent + tpix));
+                } else {
+                    const uint4 rec = __ldg(rec_chunk + ((unsigned)bb * (unsigned)n_tangent + tpix));
+                    d = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
+                    plo = rec.z;
+                    phi = rec.w;
+                }
+                fu = d.x + sn.x;                 // end point minus this ERP pixel, the short way round
+                fv = d.y + sn.y;
+                if (fu > half_w) fu -= wf;
+                else if (fu < -half_w) fu += wf;
+                bool x_ok = true;
+                if (wrap_around) {
+                    // the reference samples at c + fu after its seam fix (:350-361): outside [0, W-1] reads 255
+                    const float tx = (float)c + fu;
+                    x_ok = (tx >= 0.0f) & (tx <= wf - 1.0f);
+                } else {
+                    // the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
+                    fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
+                }
+                if (MODE != 0) {
+                    float t0 = 255.0f, t1 = 255.0f, t2 = 255.0f;
+                    if (x_ok) {
+                        const uint32_t q0 = plo & 0x1fffffu, q1 = (plo >> 21) | ((phi & 0x3ffu) << 11), q2 = phi >> 10;
+                        t0 = (__uint_as_float(0x4B000000u | q0) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                        t1 = (__uint_as_float(0x4B000000u | q1) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                        t2 = (__uint_as_float(0x4B000000u | q2) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                    }
+                    dsum = fabsf(t0 - sp[bb][0]) + fabsf(t1 - sp[bb][1]) + fabsf(t2 - sp[bb][2]);
+                }
             }
             if (MODE == 0) {
                 if (has) {
-                    acc_u[bb] += L.fu;
-                    acc_v[bb] += L.fv;
+                    acc_u[bb] += fu;
+                    acc_v[bb] += fv;
                     acc_w[bb] += 1.0f;
                 }
             } else if (MODE == 1) {
-                // face-global sum of |diff| (x multiplicity) as order-independent fixed point.
-                // Neighbouring pixels almost always see the same face at the same k: reduce across
-                // the warp first and issue one shared-memory atomic; otherwise one per lane.
-                if (has) {
-                    float* smp = smp_chunk + ((unsigned)bb * 3u * n_smp + sample0 + (unsigned)k);
-                    smp[0] = L.fu;
-                    smp[n_smp] = L.fv;
-                    smp[2u * n_smp] = dsum;
-                }
-                const unsigned fixed = has ? (unsigned)(dsum * G.mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
+                // face-global sum of |diff| (x multiplicity) as order-independent fixed point.  Neighbouring
+                // pixels almost always see the same face at the same k: reduce across the warp first and issue
+                // one shared-memory atomic; otherwise one per lane.
+                const unsigned fixed = has ? (unsigned)(dsum * mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
                 const int f0 = __shfl_sync(0xffffffffu, f, 0);
                 const bool uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
                 if (uniform) {
@@ -665,6 +655,14 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                     if ((threadIdx.x & 31) == 0) atomicAdd(&sh_sum[bb * n_faces + f0], total);
                 } else if (has) {
                     atomicAdd(&sh_sum[bb * n_faces + f], fixed);
+                }
+            } else {
+                if (has) {
+                    // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
+                    const float w = expf(-dsum * sh_inv_mean[bb * n_faces + f]);
+                    acc_u[bb] = fmaf(fu, w, acc_u[bb]);
+                    acc_v[bb] = fmaf(fv, w, acc_v[bb]);
+                    acc_w[bb] += w;
                 }
             }
         }
@@ -679,7 +677,6 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         return;
     }
     if (!live) return;
-    const float half_w = 0.5f * (float)erp_w;
     const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
 #pragma unroll
     for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
@@ -693,84 +690,17 @@ k_stitch(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         }
         if (wrap_around) {            // flow_postproc.erp_of_wraparound, flow_postproc.py:28-42
             if (c < split) {
-                if (u > half_w) u -= (float)erp_w;
+                if (u > half_w) u -= wf;
             } else if (c < erp_w - 1) {
-                if (u < -half_w) u += (float)erp_w;
+                if (u < -half_w) u += wf;
             }
         }
         reinterpret_cast<float2*>(out)[(size_t)b * n_pix + pix] = make_float2(u, v);
     }
 }
 
-// normwarp pass B: a streaming blend of the samples pass A stored.
-//   w = exp(-(mean_ch |diff|) / face-global mean)   (projection.py:57-58)
-//   flow = sum_f w f / sum_f w                       (projection_icosahedron.py:384-393), then erp_of_wraparound
-__global__ void __launch_bounds__(256)
-k_blend_normwarp(int n_faces, const uint8_t* __restrict__ s2_count, const uint32_t* __restrict__ s2_entries,
-                 const uint32_t* __restrict__ s2_offset, const double* __restrict__ face_mult_sum,
-                 const unsigned long long* __restrict__ nw_sums, const float* __restrict__ nw_samples, int64_t n_samples,
-                 float* __restrict__ out, int erp_h, int erp_w, int batch, int wrap_around) {
-    extern __shared__ float sh_inv_mean[];       // [TIF_BATCH_CHUNK][F]  1 / (3 * face-global mean)
-    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
-    for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
-        const int bb = i / n_faces, f = i - bb * n_faces;
-        float inv = 0.0f;
-        if (b0 + bb < batch) {
-            // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
-            const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
-            const double mean = total / (3.0 * face_mult_sum[f]);
-            inv = (float)(1.0 / (3.0 * mean));
-        }
-        sh_inv_mean[i] = inv;
-    }
-    __syncthreads();
-    const int n_pix = erp_h * erp_w;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= n_pix) return;
-    const int cnt = s2_count[pix];
-    const uint32_t sample0 = s2_offset[pix];
-    const int c = pix % erp_w;
-    float acc_u[TIF_BATCH_CHUNK], acc_v[TIF_BATCH_CHUNK], acc_w[TIF_BATCH_CHUNK];
-#pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
-    for (int k = 0; k < cnt; ++k) {
-        const int f = (int)TIF_E_FACE(__ldg(s2_entries + (size_t)k * n_pix + pix));
-#pragma unroll
-        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
-            const int b = b0 + bb;
-            if (b >= batch) break;
-            const float* smp = nw_samples + (size_t)b * 3 * n_samples + sample0 + k;
-            const float fu = __ldg(smp), fv = __ldg(smp + n_samples), dsum = __ldg(smp + 2 * n_samples);
-            const float w = expf(-dsum * sh_inv_mean[bb * n_faces + f]);
-            acc_u[bb] = fmaf(fu, w, acc_u[bb]);
-            acc_v[bb] = fmaf(fv, w, acc_v[bb]);
-            acc_w[bb] += w;
-        }
-    }
-    const float half_w = 0.5f * (float)erp_w;
-    const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
-#pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
-        const int b = b0 + bb;
-        if (b >= batch) break;
-        float u = acc_u[bb], v = acc_v[bb];
-        if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393
-            const float inv = 1.0f / acc_w[bb];
-            u *= inv;
-            v *= inv;
-        }
-        if (wrap_around) {            // flow_postproc.erp_of_wraparound, flow_postproc.py:28-42
-            if (c < split) {
-                if (u > half_w) u -= (float)erp_w;
-            } else if (c < erp_w - 1) {
-                if (u < -half_w) u += (float)erp_w;
-            }
-        }
-        reinterpret_cast<float2*>(out)[(size_t)b * n_pix + pix] = make_float2(u, v);
-    }
-}
-
-// scratch = [B][F] uint64 face sums (padded to 256 bytes) + [B][3][S] float32 samples, S = accepted samples per pair
+// scratch = [B][F] uint64 face sums (padded to 256 bytes) + one record per tangent pixel and image:
+// float2 displacement (straightforward) or uint4 displacement + packed target sample (normwarp)
 static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
     const size_t raw = (size_t)batch * plan->n_faces * sizeof(unsigned long long);
     return (raw + 255) / 256 * 256;
@@ -778,71 +708,61 @@ static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
 
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
-    if (blend != TIF_BLEND_NORMWARP) return 0;
-    return (int64_t)(nw_sums_bytes(plan, batch) + (size_t)batch * 3 * (size_t)plan->accepted_unique * sizeof(float));
+    const size_t rec = blend == TIF_BLEND_NORMWARP ? sizeof(uint4) : sizeof(float2);
+    return (int64_t)(nw_sums_bytes(plan, batch) + (size_t)batch * (size_t)plan->tangent_pixels * rec);
 }
 
 extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
                                        const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
                                        void* scratch, int pass_mask, void* stream_v) {
-    if (!plan || !tangent_flow || !erp_flow || batch <= 0) {
-        tif_set_error("tif_ico2erp_flow_f32: invalid argument");
+    if (!plan || !tangent_flow || !erp_flow || !scratch || batch <= 0) {
+        tif_set_error("tif_ico2erp_flow_f32: invalid argument (tangent_flow, erp_flow and scratch are required)");
         return TIF_ERR_INVALID_ARG;
     }
     if (blend != TIF_BLEND_STRAIGHTFORWARD && blend != TIF_BLEND_NORMWARP) {
         tif_set_error("tif_ico2erp_flow_f32: unknown blend %d", blend);
         return TIF_ERR_INVALID_ARG;
     }
-    if (blend == TIF_BLEND_NORMWARP && (!erp_src || !erp_tar || !scratch)) {
-        tif_set_error("tif_ico2erp_flow_f32: normwarp needs erp_src, erp_tar and scratch");
+    if (blend == TIF_BLEND_NORMWARP && (!erp_src || !erp_tar)) {
+        tif_set_error("tif_ico2erp_flow_f32: normwarp needs erp_src and erp_tar");
         return TIF_ERR_INVALID_ARG;
     }
     cudaStream_t stream = (cudaStream_t)stream_v;
-    const int threads = TIF_STITCH_THREADS;
-    const int h = plan->erp_h, w = plan->erp_w;
-    const int n_pix = h * w;
+    const int h = plan->erp_h, w = plan->erp_w, n_faces = plan->n_faces;
+    const int n_tangent = (int)plan->tangent_pixels;
     const unsigned by = (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK);
-    const size_t smem = sizeof(FaceConst) * plan->n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * plan->n_faces;
     unsigned long long* nw_sums = (unsigned long long*)scratch;
-    float* nw_samples = scratch ? (float*)((unsigned char*)scratch + nw_sums_bytes(plan, batch)) : nullptr;
-    const int64_t n_samples = plan->accepted_unique;
-#define STITCH_ARGS                                                                                                 \
-    plan->d_faces, plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_col_theta, plan->d_row_sc,         \
-        plan->d_col_sc, plan->d_row_sc64, plan->d_col_sc64, plan->d_face_mult_sum, tangent_flow, erp_src, erp_tar, \
-        nw_sums, plan->d_s2_offset, nw_samples, n_samples, erp_flow, h, w, plan->tangent_w,                        \
-        (int)plan->tangent_pixels, batch, wrap_around
-#define STITCH_GRID(rows) dim3((unsigned)((tile_threads(w, (rows)) + threads - 1) / threads), by)
-    // rows with sin(colatitude) < TIF_POLAR_SIN at either pole take the float64 lift (separate launch so
-    // that its register footprint does not lower the occupancy of the bulk)
-    int polar_rows = 0;
-    while (polar_rows < h / 2 && sin(((double)polar_rows + 0.5) * TIF_PI / (double)h) < (double)TIF_POLAR_SIN) ++polar_rows;
-    polar_rows = min((polar_rows + TIF_TILE_H - 1) / TIF_TILE_H * TIF_TILE_H, h / 2);     // whole tiles
-    const int bulk_rows = h - 2 * polar_rows;
+    void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
+    const dim3 lift_grid((unsigned)((tile_threads(plan->tangent_w, n_tangent / plan->tangent_w) + 255) / 256), by);
+    const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS), by);
+    const size_t lift_smem = sizeof(LiftFace) * n_faces;
+    const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * n_faces;
+#define GATHER_ARGS                                                                                                  \
+    plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
+        erp_src, nw_sums, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
+    const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
-        if (bulk_rows > 0)
-            k_stitch<0, false><<<STITCH_GRID(bulk_rows), threads, smem, stream>>>(STITCH_ARGS, polar_rows, bulk_rows, 0, bulk_rows);
-        if (polar_rows > 0)
-            k_stitch<0, true><<<STITCH_GRID(2 * polar_rows), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows,
-                                                                                     h - polar_rows, 2 * polar_rows);
+        if (!skip_lift)
+            k_lift<false><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_mark,
+                                                                 plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
+                                                                 records, h, w, plan->tangent_w, n_tangent, batch);
+        TIF_CUDA_CHECK(cudaGetLastError());
+        if (pass_mask & 3) k_gather<0><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
         if (pass_mask & 1) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
-            if (bulk_rows > 0)
-                k_stitch<1, false><<<STITCH_GRID(bulk_rows), threads, smem, stream>>>(STITCH_ARGS, polar_rows, bulk_rows, 0,
-                                                                                     bulk_rows);
-            if (polar_rows > 0)
-                k_stitch<1, true><<<STITCH_GRID(2 * polar_rows), threads, smem, stream>>>(STITCH_ARGS, 0, polar_rows,
-                                                                                         h - polar_rows, 2 * polar_rows);
+            if (!skip_lift)
+                k_lift<true><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
+                                                                    plan->d_ref_mark, plan->d_s1_ex, plan->d_s1_ey,
+                                                                    tangent_flow, erp_tar, records, h, w, plan->tangent_w,
+                                                                    n_tangent, batch);
+            TIF_CUDA_CHECK(cudaGetLastError());
+            k_gather<1><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
-        if (pass_mask & 2)
-            k_blend_normwarp<<<dim3((unsigned)((n_pix + 255) / 256), by), 256,
-                               sizeof(float) * TIF_BATCH_CHUNK * plan->n_faces, stream>>>(
-                plan->n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_offset, plan->d_face_mult_sum, nw_sums,
-                nw_samples, n_samples, erp_flow, h, w, batch, wrap_around);
+        if (pass_mask & 2) k_gather<2><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     }
-#undef STITCH_ARGS
-#undef STITCH_GRID
+#undef GATHER_ARGS
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
 }

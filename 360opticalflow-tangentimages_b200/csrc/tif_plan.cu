@@ -154,6 +154,7 @@ k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp
               const double* __restrict__ row_sincos, const double* __restrict__ col_sincos,
               uint8_t* __restrict__ count, uint32_t* __restrict__ entries, int max_k,
               uint8_t* __restrict__ ref_mark, unsigned long long* __restrict__ face_mult_sum,
+              const double* __restrict__ s1_ex, const double* __restrict__ s1_ey, float2* __restrict__ snap,
               int* __restrict__ status /* [0]=max count, [1]=range errors */) {
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pix = (int64_t)erp_h * erp_w;
@@ -192,10 +193,18 @@ k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp
                 ix = min(max(ix, 0), tangent_w - 1);
                 iy = min(max(iy, 0), F.tangent_h - 1);
             }
-            if (n < max_k)
+            const int64_t tpix = (int64_t)F.pix_offset + (int64_t)iy * tangent_w + ix;
+            if (n < max_k) {
                 entries[(int64_t)n * n_pix + pix] =
                     ((uint32_t)f << 25) | ((uint32_t)min(m, 7) << 22) | ((uint32_t)iy << 11) | (uint32_t)ix;
-            ref_mark[(int64_t)F.pix_offset + (int64_t)iy * tangent_w + ix] = 1;
+                // where the nearest tangent pixel itself sits in the ERP image (stage 1 of this plan), relative
+                // to this ERP pixel: the constant part of every flow that is gathered through this entry
+                double sx = s1_ex[tpix] - (double)c;
+                if (sx > 0.5 * erp_w) sx -= (double)erp_w;
+                else if (sx < -0.5 * erp_w) sx += (double)erp_w;
+                snap[(int64_t)n * n_pix + pix] = make_float2((float)sx, (float)(s1_ey[tpix] - (double)r));
+            }
+            ref_mark[tpix] = 1;
             atomicAdd(&face_mult_sum[f], (unsigned long long)m);
         }
         ++n;
@@ -242,6 +251,8 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_s2_count);
     cudaFree(plan->d_s2_entries);
     cudaFree(plan->d_s2_offset);
+    cudaFree(plan->d_s2_snap);
+    cudaFree(plan->d_ref_mark);
     cudaFree(plan->d_col_theta);
     cudaFree(plan->d_row_sc);
     cudaFree(plan->d_col_sc);
@@ -260,7 +271,6 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
             tif_plan_destroy(plan); \
             cudaFree(d_gx);         \
             cudaFree(d_gy);         \
-            cudaFree(d_mark);       \
             cudaFree(d_status);     \
             cudaFree(d_msum);       \
             return _s;              \
@@ -314,7 +324,6 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
 
     double *d_gx = nullptr, *d_gy = nullptr;
-    uint8_t* d_mark = nullptr;
     int* d_status = nullptr;
     unsigned long long* d_msum = nullptr;
 
@@ -335,6 +344,8 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(dev_alloc(&plan->d_s2_count, n_erp, plan));
     PLAN_TRY(dev_alloc(&plan->d_col_theta, erp_w, plan));
     PLAN_TRY(dev_alloc(&plan->d_face_mult_sum, n_faces, plan));
+    PLAN_TRY(dev_alloc(&plan->d_ref_mark, n_tangent, plan));
+    uint8_t* d_mark = plan->d_ref_mark;
     PLAN_TRY(dev_alloc(&plan->d_row_sc, erp_h, plan));
     PLAN_TRY(dev_alloc(&plan->d_col_sc, (size_t)n_faces * erp_w, plan));
     PLAN_TRY(dev_alloc(&plan->d_row_sc64, erp_h, plan));
@@ -347,7 +358,6 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         tmp.device_bytes = 0;
         PLAN_TRY(dev_alloc(&d_gx, (size_t)n_faces * tangent_w, &tmp));
         PLAN_TRY(dev_alloc(&d_gy, n_rows, &tmp));
-        PLAN_TRY(dev_alloc(&d_mark, n_tangent, &tmp));
         PLAN_TRY(dev_alloc(&d_status, 2, &tmp));
         PLAN_TRY(dev_alloc(&d_msum, n_faces + 1, &tmp));
         scratch_bytes = tmp.device_bytes;
@@ -386,7 +396,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
 
     const unsigned blocks2 = (unsigned)((n_erp + threads - 1) / threads);
     k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
-                                                         d_cols, nullptr, nullptr, 0, nullptr, nullptr, d_status);
+                                                         d_cols, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, d_status);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<count> launch"));
     int h_status[2] = {0, 0};
     PLAN_TRY(cuda_status(cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, stream), "read max count"));
@@ -397,9 +407,11 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         PLAN_TRY(TIF_ERR_RANGE);
     }
     PLAN_TRY(dev_alloc(&plan->d_s2_entries, (size_t)plan->max_faces_per_pixel * n_erp, plan));
+    PLAN_TRY(dev_alloc(&plan->d_s2_snap, (size_t)plan->max_faces_per_pixel * n_erp, plan));
     k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
                                                         d_cols, plan->d_s2_count, plan->d_s2_entries,
-                                                        plan->max_faces_per_pixel, d_mark, d_msum, d_status);
+                                                        plan->max_faces_per_pixel, d_mark, d_msum, plan->d_s1_ex, plan->d_s1_ey,
+                                                        plan->d_s2_snap, d_status);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<fill> launch"));
     k_count_marks<<<1024, 256, 0, stream>>>(d_mark, n_tangent, d_msum + n_faces);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_count_marks launch"));
@@ -453,7 +465,6 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
 
     cudaFree(d_gx);
     cudaFree(d_gy);
-    cudaFree(d_mark);
     cudaFree(d_status);
     cudaFree(d_msum);
     *plan_out = plan;

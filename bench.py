@@ -216,7 +216,7 @@ def run_ours(args):
     out = torch.empty((B, plan.erp_h, plan.erp_w, 2), dtype=torch.float32, device=device)
     scratch = torch.empty(max(int(plan.lib.tif_ico2erp_scratch_bytes(plan.handle, B, lib.BLEND_NORMWARP)), 8),
                           dtype=torch.uint8, device=device)
-    # erp2ico x2; stitch = bulk + polar-band launches (normwarp: pass A bulk + polar, then the blend kernel)
+    # erp2ico x2; stitch = k_lift + k_gather (normwarp: k_lift, k_gather<sums>, k_gather<blend>)
     launches_per_step = 4 if blend == lib.BLEND_STRAIGHTFORWARD else 5
 
     def step():
@@ -261,14 +261,18 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     hw = plan.erp_h * plan.erp_w
     P, Pref = plan.tangent_pixels, plan.referenced_tangent_pixels
+    sf, nw = lib.BLEND_STRAIGHTFORWARD, lib.BLEND_NORMWARP
+    # pass_mask: 1 = lift (+ normwarp face sums), 2 = blend, 4 = skip the lift kernel (reuse the records)
     kernels = {
         "k_erp2ico": (lambda: ops.erp2ico_out(plan, src, True, tan_src), B * (hw * 3 + P * 4)),
-        "k_stitch<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, lib.BLEND_STRAIGHTFORWARD, True, out),
-                                      B * (8 * Pref + 8 * hw)),
-        "k_stitch<normwarp pass A>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, lib.BLEND_NORMWARP, True, out, scratch, 1),
-                                      B * (8 * Pref + 6 * hw)),
-        "k_blend_normwarp (pass B)": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, lib.BLEND_NORMWARP, True, out, scratch, 2),
+        "k_lift<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 8),
+                                    B * (8 * Pref)),
+        "k_gather<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 4 | 3),
                                       B * (8 * hw)),
+        "k_lift<normwarp> + k_gather<sums>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 1),
+                                              B * (8 * Pref + 6 * hw)),
+        "k_gather<sums>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 1 | 4), B * (3 * hw)),
+        "k_gather<blend>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 2), B * (8 * hw)),
     }
     ktimes = {}
     for name, (fn, nbytes) in kernels.items():
@@ -284,8 +288,8 @@ def run_ours(args):
         ms = a.elapsed_time(b) / args.kernel_reps
         ktimes[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
                         "frac": nbytes / (ms * 1e-3) / 1e9 / peak_gbs}
-    used = ["k_erp2ico"] + (["k_stitch<straightforward>"] if blend == lib.BLEND_STRAIGHTFORWARD
-                            else ["k_stitch<normwarp pass A>", "k_blend_normwarp (pass B)"])
+    used = ["k_erp2ico"] + (["k_lift<straightforward>", "k_gather<straightforward>"] if blend == sf
+                            else ["k_lift<normwarp> + k_gather<sums>", "k_gather<blend>"])
     weight = {k: ktimes[k]["ms"] * (2 if k == "k_erp2ico" else 1) for k in used}
     dominant = max(weight, key=weight.get)
     traffic = None

@@ -149,7 +149,8 @@ int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp /*[B,H,W,3]*/, int ba
  * gather, end-point lift through pixel2gnomonic / reverse_gnomonic_projection / sph2erp, seam fix
  * (wrap_around), face weights (blend), weighted mean over faces in index order, and the final
  * flow_postproc.erp_of_wraparound when wrap_around != 0.  src/tar are only read for
- * TIF_BLEND_NORMWARP (projection.py:15-61); `scratch` must then hold tif_ico2erp_scratch_bytes().
+ * TIF_BLEND_NORMWARP (projection.py:15-61).  `scratch` (always required) must hold
+ * tif_ico2erp_scratch_bytes(): one lifted record per tangent pixel and image, plus the normwarp face sums.
  */
 int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend);
 int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow /*[B,P,2]*/,
@@ -157,8 +158,9 @@ int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow /*[B,P,2
                          int batch, int blend, int wrap_around, float* erp_flow /*[B,H,W,2]*/,
                          void* scratch, void* stream);
 
-/* Profiling aid: the same call restricted to one of the two normwarp passes (pass_mask 1 = face-global
- * warp-error sums, 2 = weights + blend using the sums already in `scratch`, 3 = both = the call above). */
+/* Profiling aid: the same call restricted to some of its kernels.  pass_mask bit 0: lift the tangent pixels and
+ * (normwarp) accumulate the face-global warp-error sums; bit 1: blend using what is already in `scratch`;
+ * bit 2: skip the lift kernel and reuse the records of an earlier call.  3 = the call above. */
 int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
                             const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
                             void* scratch, int pass_mask, void* stream);
