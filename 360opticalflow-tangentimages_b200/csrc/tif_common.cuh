@@ -52,6 +52,7 @@ struct TifPlan {
     uint32_t* d_s2_offset;         // [H*W] exclusive prefix sum of d_s2_count: first slot of a pixel's samples
     float2* d_s2_snap;             // [K][H*W] ERP position of the sample's tangent pixel minus the ERP pixel (x wrapped to +-W/2)
     uint8_t* d_ref_mark;           // [P] 1 where a tangent pixel is referenced by at least one ERP pixel
+    int32_t* d_ref_list;           // [P_ref] the referenced tangent pixels, in 8x4-tile order (work list of k_lift)
     double* d_col_theta;           // [W] theta of every ERP column
     float2* d_row_sc;              // [H] (sin phi_r, cos phi_r) in float32
     float2* d_col_sc;              // [F][W] (sin, cos)(theta_c - theta0_f) in float32

@@ -265,6 +265,9 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // the direction vector cancels in float32, and under normwarp the faces disagree by hundreds of ERP pixels
 // there, so the photometric weights turn a 1e-4 px error of the sampling position into a flow error above
 // the 1e-3 px tolerance
+#ifndef TIF_GATHER2_MIN_BLOCKS
+#define TIF_GATHER2_MIN_BLOCKS 5
+#endif
 #define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
 #define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
 
@@ -368,12 +371,15 @@ __device__ __noinline__ void lift_precise(double gx0, double gy0, double s0, dou
 //   delta_theta = atan2(E, rho)     delta_colat = atan2(-N + E^2 cos / (h + rho), ...)
 // see small angles and float32 keeps ~1e-7 relative precision on the displacement itself.
 // The result is (delta_theta W / 2 pi, delta_colat H / pi); k_gather adds the pixel's own ERP position.
+#ifndef TIF_LIFT_MIN_BLOCKS
+#define TIF_LIFT_MIN_BLOCKS 4
+#endif
 template <bool NW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TIF_LIFT_MIN_BLOCKS)
 k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
-       const uint8_t* __restrict__ ref_mark, const double* __restrict__ s1_ex, const double* __restrict__ s1_ey,
-       const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar, void* __restrict__ records, int erp_h,
-       int erp_w, int tangent_w, int n_tangent, int batch) {
+       const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
+       const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
+       void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
@@ -390,12 +396,19 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
         sh_face[f] = lf;
     }
     __syncthreads();
-    int trow, tcol;
-    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, tangent_w, n_tangent / tangent_w, trow, tcol)) return;
-    const int p = trow * tangent_w + tcol;
-    if (!ref_mark[p]) return;                       // no ERP pixel ever reads this tangent pixel
-    const LiftFace& F = sh_face[row_face[trow]];
+    // the work list holds only tangent pixels that some ERP pixel reads (half of the stack), in tile order
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_ref) return;
+    const int p = __ldg(ref_list + idx);
+    const int trow = p / tangent_w, tcol = p - trow * tangent_w;
     const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
+    // all flows of the chunk are requested before anything depends on them (the kernel is latency bound)
+    float2 uvs[TIF_BATCH_CHUNK];
+#pragma unroll
+    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb)
+        uvs[bb] = (b0 + bb < batch) ? __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p)) : make_float2(0.0f, 0.0f);
+    const LiftFace& F = sh_face[__ldg(row_face + trow)];
 
     // ---- per tangent pixel, once for the chunk of images -------------------------------------------------
     const double gx0 = fma((double)tcol, F.kx, F.xmin);
@@ -430,14 +443,16 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
         eyf = (float)(ey - fyi);
     }
     const unsigned image_bytes = (unsigned)erp_h * (unsigned)erp_w * 3u;
-    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
     const uint8_t* __restrict__ tar_chunk = NW ? erp_tar + (size_t)b0 * image_bytes : nullptr;
+    // records of one tangent pixel are interleaved over the images of the chunk: k_gather fetches them from
+    // one or two adjacent sectors instead of one sector per image
+    const size_t rec0 = ((size_t)blockIdx.y * n_tangent + p) * TIF_BATCH_CHUNK;
 
 #pragma unroll
     for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
         const int b = b0 + bb;
         if (b >= batch) break;
-        const float2 uv = __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p));
+        const float2 uv = uvs[bb];
         const float dx = uv.x * kxf, dy = -uv.y * kyf;
         const float E = fmaf(dy, e1, dx * e2);
         const float N = fmaf(dy, n1, dx * n2c);
@@ -483,7 +498,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
             }
         }
         if (!NW) {
-            reinterpret_cast<float2*>(records)[(size_t)b * n_tangent + p] = make_float2(disp_x, disp_y);
+            reinterpret_cast<float2*>(records)[rec0 + bb] = make_float2(disp_x, disp_y);
             continue;
         }
         // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
@@ -519,7 +534,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
         const unsigned long long q0 = __float2uint_rn(t0 * TIF_RGB_FIX), q1 = __float2uint_rn(t1 * TIF_RGB_FIX),
                                  q2 = __float2uint_rn(t2 * TIF_RGB_FIX);
         const unsigned long long packed = q0 | (q1 << 21) | (q2 << 42);
-        reinterpret_cast<uint4*>(records)[(size_t)b * n_tangent + p] =
+        reinterpret_cast<uint4*>(records)[rec0 + bb] =
             make_uint4(__float_as_uint(disp_x), __float_as_uint(disp_y), (unsigned)packed, (unsigned)(packed >> 32));
     }
 }
@@ -528,7 +543,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
 // point).  MODE 2: normwarp pass B (weights from the sums of pass A, blend).  One thread per ERP pixel and chunk
 // of images; a warp owns an 8 x 4 pixel tile.
 template <int MODE>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS)
+__global__ void __launch_bounds__(TIF_STITCH_THREADS, MODE == 2 ? TIF_GATHER2_MIN_BLOCKS : 6)
 k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
          const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
@@ -583,16 +598,22 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         }
     }
     const float2* __restrict__ disp_chunk = reinterpret_cast<const float2*>(records) + (size_t)b0 * n_tangent;
-    const uint4* __restrict__ rec_chunk = reinterpret_cast<const uint4*>(records) + (size_t)b0 * n_tangent;
+    const uint4* __restrict__ rec_chunk = reinterpret_cast<const uint4*>(records) + (size_t)b0 * n_tangent;   // b0 = chunk * CHUNK
 
     const int max_cnt = (MODE == 1) ? __reduce_max_sync(0xffffffffu, cnt) : cnt;
+    uint32_t e_next = 0u;
+    float2 sn_next = make_float2(0.0f, 0.0f);
+    if (cnt > 0) {
+        e_next = __ldg(s2_entries + pix);
+        sn_next = __ldg(s2_snap + pix);
+    }
     for (int k = 0; k < max_cnt; ++k) {
         const bool has = k < cnt;
-        uint32_t e = 0u;
-        float2 sn = make_float2(0.0f, 0.0f);
-        if (has) {
-            e = __ldg(s2_entries + (size_t)k * n_pix + pix);
-            sn = __ldg(s2_snap + (size_t)k * n_pix + pix);
+        const uint32_t e = e_next;
+        const float2 sn = sn_next;
+        if (k + 1 < cnt) {                           // next entry in flight while this one is blended
+            e_next = __ldg(s2_entries + (size_t)(k + 1) * n_pix + pix);
+            sn_next = __ldg(s2_snap + (size_t)(k + 1) * n_pix + pix);
         }
         const int f = (int)TIF_E_FACE(e);
         const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
@@ -606,9 +627,9 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 float2 d;
                 uint32_t plo = 0u, phi = 0u;
                 if (MODE == 0) {
-                    d = __ldg(disp_chunk + ((unsigned)bb * (unsigned)n_tangent + tpix));
+                    d = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
                 } else {
-                    const uint4 rec = __ldg(rec_chunk + ((unsigned)bb * (unsigned)n_tangent + tpix));
+                    const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
                     d = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
                     plo = rec.z;
                     phi = rec.w;
@@ -709,7 +730,8 @@ static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
     const size_t rec = blend == TIF_BLEND_NORMWARP ? sizeof(uint4) : sizeof(float2);
-    return (int64_t)(nw_sums_bytes(plan, batch) + (size_t)batch * (size_t)plan->tangent_pixels * rec);
+    const size_t padded = (size_t)(batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK * TIF_BATCH_CHUNK;      // whole chunks
+    return (int64_t)(nw_sums_bytes(plan, batch) + padded * (size_t)plan->tangent_pixels * rec);
 }
 
 extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
@@ -733,7 +755,8 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const unsigned by = (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK);
     unsigned long long* nw_sums = (unsigned long long*)scratch;
     void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
-    const dim3 lift_grid((unsigned)((tile_threads(plan->tangent_w, n_tangent / plan->tangent_w) + 255) / 256), by);
+    const int n_ref = (int)plan->referenced_tangent_pixels;
+    const dim3 lift_grid((unsigned)((n_ref + 255) / 256), by);
     const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS), by);
     const size_t lift_smem = sizeof(LiftFace) * n_faces;
     const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * n_faces;
@@ -743,8 +766,8 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD) {
         if (!skip_lift)
-            k_lift<false><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_mark,
-                                                                 plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
+            k_lift<false><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+                                                                 n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
                                                                  records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) k_gather<0><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
@@ -753,7 +776,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (!skip_lift)
                 k_lift<true><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
-                                                                    plan->d_ref_mark, plan->d_s1_ex, plan->d_s1_ey,
+                                                                    plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch);
             TIF_CUDA_CHECK(cudaGetLastError());

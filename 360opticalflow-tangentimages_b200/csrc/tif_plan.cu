@@ -253,6 +253,7 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_s2_offset);
     cudaFree(plan->d_s2_snap);
     cudaFree(plan->d_ref_mark);
+    cudaFree(plan->d_ref_list);
     cudaFree(plan->d_col_theta);
     cudaFree(plan->d_row_sc);
     cudaFree(plan->d_col_sc);
@@ -441,6 +442,34 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(cuda_status(cudaMemcpyAsync(&h_acc, d_msum, sizeof(h_acc), cudaMemcpyDeviceToHost, stream), "read accepted"));
     PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan finish"));
     plan->accepted_unique = (int64_t)h_acc;
+    {
+        // work list of the lift kernel: referenced tangent pixels in 8 x 4 tile order, so that a warp works on a
+        // compact patch of one face (plan-time bookkeeping through the host: 1 byte per tangent pixel)
+        uint8_t* h_mark = (uint8_t*)malloc((size_t)n_tangent);
+        int32_t* h_list = (int32_t*)malloc(sizeof(int32_t) * (size_t)(plan->referenced_tangent_pixels + 1));
+        cudaError_t ea = cudaMemcpy(h_mark, plan->d_ref_mark, (size_t)n_tangent, cudaMemcpyDeviceToHost);
+        int64_t n_list = 0;
+        if (ea == cudaSuccess) {
+            for (int64_t ty = 0; ty < n_rows; ty += 4)
+                for (int tx = 0; tx < tangent_w; tx += 8)
+                    for (int64_t y = ty; y < ty + 4 && y < n_rows; ++y)
+                        for (int x = tx; x < tx + 8 && x < tangent_w; ++x)
+                            if (h_mark[y * tangent_w + x] && n_list < plan->referenced_tangent_pixels)
+                                h_list[n_list++] = (int32_t)(y * tangent_w + x);
+        }
+        int st = dev_alloc(&plan->d_ref_list, (size_t)(plan->referenced_tangent_pixels + 1), plan);
+        cudaError_t eb = cudaSuccess;
+        if (st == TIF_OK) eb = cudaMemcpy(plan->d_ref_list, h_list, sizeof(int32_t) * (size_t)n_list, cudaMemcpyHostToDevice);
+        free(h_mark);
+        free(h_list);
+        PLAN_TRY(st);
+        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "referenced pixel list"));
+        if (n_list != plan->referenced_tangent_pixels) {
+            tif_set_error("tif_plan_create: referenced pixel list (%lld) disagrees with the mark count (%lld)",
+                          (long long)n_list, (long long)plan->referenced_tangent_pixels);
+            PLAN_TRY(TIF_ERR_RANGE);
+        }
+    }
     {
         // exclusive prefix sum of the per-pixel counts (plan-time bookkeeping: 1 byte per ERP pixel through the host)
         PLAN_TRY(dev_alloc(&plan->d_s2_offset, n_erp, plan));

@@ -6,7 +6,7 @@ for defs in "$@"; do
   python - "$defs" <<'PY'
 import json, sys
 d = json.load(open("/tmp/ab.json"))
-print("[%s] pairs/s %.0f  step %.3f ms  " % (sys.argv[1], d["value"], d["ms_per_step"]) + "  ".join("%s %.3f" % (k.split("<")[-1].split(">")[0][:14], v["ms"]) for k, v in d["roofline"]["kernels"].items()))
+print("[%s] pairs/s %.0f  step %.3f ms  " % (sys.argv[1], d["value"], d["ms_per_step"]) + "  ".join("%s %.3f" % (k[:22], v["ms"]) for k, v in d["roofline"]["kernels"].items()))
 PY
 done
 python 360opticalflow-tangentimages_b200/_build.py --force > /dev/null
