@@ -126,7 +126,6 @@ class HostGeometry:
         phi = -(rows * (np.pi / h) + np.pi / h * 0.5) + 0.5 * np.pi
         theta = np.where(theta == np.pi, -np.pi, theta)
         phi = np.where(phi == -0.5 * np.pi, 0.5 * np.pi, phi)
-        self.col_theta = np.ascontiguousarray(theta)
         self.row_sincos = np.ascontiguousarray(np.stack((np.sin(phi), np.cos(phi)), axis=1))
         self.col_sincos = np.zeros((n, w, 2), dtype=np.float64)
         offset = 0
@@ -164,8 +163,8 @@ class HostGeometry:
         dp = C.POINTER(C.c_double)
         t = _lib.TifPlanTables()
         self._keep = [np.ascontiguousarray(a) for a in
-                      (self.gnom_x, self.gnom_y, self.row_sincos, self.col_sincos, self.col_theta)]
-        t.gnom_x, t.gnom_y, t.row_sincos, t.col_sincos, t.col_theta = (a.ctypes.data_as(dp) for a in self._keep)
+                      (self.gnom_x, self.gnom_y, self.row_sincos, self.col_sincos)]
+        t.gnom_x, t.gnom_y, t.row_sincos, t.col_sincos = (a.ctypes.data_as(dp) for a in self._keep)
         return t
 
 

@@ -10,6 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
 
 TIF_OK = 0
+ABI_VERSION = 2
 BLEND_STRAIGHTFORWARD = 0
 BLEND_NORMWARP = 1
 WARP_WRAP = 0
@@ -39,7 +40,6 @@ class TifPlanTables(C.Structure):
     _fields_ = [
         ("gnom_x", C.POINTER(C.c_double)), ("gnom_y", C.POINTER(C.c_double)),
         ("row_sincos", C.POINTER(C.c_double)), ("col_sincos", C.POINTER(C.c_double)),
-        ("col_theta", C.POINTER(C.c_double)),
     ]
 
 
@@ -94,8 +94,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.tif_abi_version() != 1:
-        raise TifError("libtif_b200.so ABI version %d, expected 1" % lib.tif_abi_version())
+    if lib.tif_abi_version() != ABI_VERSION:
+        raise TifError("libtif_b200.so ABI version %d, expected %d" % (lib.tif_abi_version(), ABI_VERSION))
     sizes = [C.c_int32(), C.c_int32(), C.c_int32()]
     lib.tif_struct_sizes(*[C.byref(s) for s in sizes])
     expect = (C.sizeof(TifFace), C.sizeof(TifPlanTables), C.sizeof(TifPlanInfo))

@@ -3,7 +3,7 @@
 // The library has two translation units:
 //   tif_plan.cu  geometry plan: fp64, compiled with -fmad=false so that every + - * / rounds once,
 //                exactly like the numpy expressions of the reference it restates;
-//   tif_exec.cu  per-batch execute kernels: gathers, bilinear, end-point lift, blend (HBM-bound).
+//   tif_exec.cu  per-batch execute kernels: gathers, bilinear, end-point lift, blend.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -42,22 +42,15 @@ struct TifPlan {
     int32_t* d_pix_face;           // [P / Wt] face of every tangent row (ragged stacks)
     // stage 1: per tangent pixel
     uint32_t* d_s1_base;           // [P] (y0*W + x0) | TIF_S1_OUTSIDE ; taps (x0,x0+1) x (y0,y0+1) are always in range
-    float2* d_s1_frac;             // [P] bilinear fractions (fx, fy), float32 fast path
     double2* d_s1_frac64;          // [P] the same in float64 (exact scipy weights, rounding fallback)
     double* d_s1_ex;               // [P] ERP sample x after sph2erp(modulo)   (parity export)
     double* d_s1_ey;               // [P]
     // stage 2: per ERP pixel
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
-    uint32_t* d_s2_offset;         // [H*W] exclusive prefix sum of d_s2_count: first slot of a pixel's samples
     float2* d_s2_snap;             // [K][H*W] ERP position of the sample's tangent pixel minus the ERP pixel (x wrapped to +-W/2)
     uint8_t* d_ref_mark;           // [P] 1 where a tangent pixel is referenced by at least one ERP pixel
     int32_t* d_ref_list;           // [P_ref] the referenced tangent pixels, in 8x4-tile order (work list of k_lift)
-    double* d_col_theta;           // [W] theta of every ERP column
-    float2* d_row_sc;              // [H] (sin phi_r, cos phi_r) in float32
-    float2* d_col_sc;              // [F][W] (sin, cos)(theta_c - theta0_f) in float32
-    double2* d_row_sc64;           // [H] the same tables in float64 (membership test, polar rows of the stitch)
-    double2* d_col_sc64;           // [F][W]
     double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
 };
 

@@ -73,7 +73,11 @@ __device__ __forceinline__ RawPair load_raw_pair(const uint8_t* __restrict__ p, 
     r.w0 = __ldg(q);
     r.w1 = __ldg(q + 1);
     r.w2 = 0u;
+#ifdef TIF_TAP_LOAD3
+    r.w2 = __ldg(q + 2);
+#else
     if (o == 3) r.w2 = __ldg(q + 2);
+#endif
     return r;
 }
 
@@ -148,8 +152,11 @@ __host__ __device__ __forceinline__ int64_t tile_threads(int width, int rows) {
     return (int64_t)((width + TIF_TILE_W - 1) / TIF_TILE_W) * ((rows + TIF_TILE_H - 1) / TIF_TILE_H) * 32;
 }
 
+#ifndef TIF_ERP2ICO_MIN_BLOCKS
+#define TIF_ERP2ICO_MIN_BLOCKS 4
+#endif
 template <bool ALIGNED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TIF_ERP2ICO_MIN_BLOCKS)
 k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
           const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
           int batch, int batch_per_block_row, int full_face) {

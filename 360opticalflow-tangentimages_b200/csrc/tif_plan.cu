@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256)
 k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row_face,
               const double* __restrict__ gnom_x, const double* __restrict__ gnom_y,
               int erp_h, int erp_w, int tangent_w, int64_t n_pix,
-              uint32_t* __restrict__ s1_base, float2* __restrict__ s1_frac, double2* __restrict__ s1_frac64,
+              uint32_t* __restrict__ s1_base, double2* __restrict__ s1_frac64,
               double* __restrict__ s1_ex, double* __restrict__ s1_ey) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pix) return;
@@ -129,7 +129,6 @@ k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row
     uint32_t base = (uint32_t)((int64_t)y0 * erp_w + (int64_t)x0);
     if (!pip_accept(x, y, F.tri, F.eps_image)) base |= TIF_S1_OUTSIDE;
     s1_base[p] = base;
-    s1_frac[p] = make_float2((float)fx, (float)fy);
     s1_frac64[p] = make_double2(fx, fy);
 }
 
@@ -244,21 +243,14 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_faces);
     cudaFree(plan->d_pix_face);
     cudaFree(plan->d_s1_base);
-    cudaFree(plan->d_s1_frac);
     cudaFree(plan->d_s1_frac64);
     cudaFree(plan->d_s1_ex);
     cudaFree(plan->d_s1_ey);
     cudaFree(plan->d_s2_count);
     cudaFree(plan->d_s2_entries);
-    cudaFree(plan->d_s2_offset);
     cudaFree(plan->d_s2_snap);
     cudaFree(plan->d_ref_mark);
     cudaFree(plan->d_ref_list);
-    cudaFree(plan->d_col_theta);
-    cudaFree(plan->d_row_sc);
-    cudaFree(plan->d_col_sc);
-    cudaFree(plan->d_row_sc64);
-    cudaFree(plan->d_col_sc64);
     cudaFree(plan->d_face_mult_sum);
     free(plan->h_faces);
     free(plan);
@@ -272,6 +264,8 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
             tif_plan_destroy(plan); \
             cudaFree(d_gx);         \
             cudaFree(d_gy);         \
+            cudaFree(d_rows);       \
+            cudaFree(d_cols);       \
             cudaFree(d_status);     \
             cudaFree(d_msum);       \
             return _s;              \
@@ -288,7 +282,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
                                const TifPlanTables* tables, void* stream_v, TifPlan** plan_out) {
     if (!faces || !tables || !plan_out || n_faces <= 0 || n_faces > TIF_MAX_FACES || erp_h < 2 || erp_w < 2 ||
         tangent_w < 2 || tangent_w > TIF_MAX_TANGENT_DIM || !tables->gnom_x || !tables->gnom_y ||
-        !tables->row_sincos || !tables->col_sincos || !tables->col_theta) {
+        !tables->row_sincos || !tables->col_sincos) {
         tif_set_error("tif_plan_create: invalid argument");
         return TIF_ERR_INVALID_ARG;
     }
@@ -324,7 +318,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     plan->h_faces = (TifFace*)malloc(sizeof(TifFace) * n_faces);
     memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
 
-    double *d_gx = nullptr, *d_gy = nullptr;
+    double *d_gx = nullptr, *d_gy = nullptr, *d_rows = nullptr, *d_cols = nullptr;
     int* d_status = nullptr;
     unsigned long long* d_msum = nullptr;
 
@@ -338,27 +332,21 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(dev_alloc(&plan->d_faces, n_faces, plan));
     PLAN_TRY(dev_alloc(&plan->d_pix_face, n_rows, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_base, n_tangent, plan));
-    PLAN_TRY(dev_alloc(&plan->d_s1_frac, n_tangent, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_frac64, n_tangent, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_ex, n_tangent, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_ey, n_tangent, plan));
     PLAN_TRY(dev_alloc(&plan->d_s2_count, n_erp, plan));
-    PLAN_TRY(dev_alloc(&plan->d_col_theta, erp_w, plan));
     PLAN_TRY(dev_alloc(&plan->d_face_mult_sum, n_faces, plan));
     PLAN_TRY(dev_alloc(&plan->d_ref_mark, n_tangent, plan));
     uint8_t* d_mark = plan->d_ref_mark;
-    PLAN_TRY(dev_alloc(&plan->d_row_sc, erp_h, plan));
-    PLAN_TRY(dev_alloc(&plan->d_col_sc, (size_t)n_faces * erp_w, plan));
-    PLAN_TRY(dev_alloc(&plan->d_row_sc64, erp_h, plan));
-    PLAN_TRY(dev_alloc(&plan->d_col_sc64, (size_t)n_faces * erp_w, plan));
-    double* d_rows = reinterpret_cast<double*>(plan->d_row_sc64);
-    double* d_cols = reinterpret_cast<double*>(plan->d_col_sc64);
     int64_t scratch_bytes = 0;
     {
         TifPlan tmp;   // scratch is not part of the plan footprint
         tmp.device_bytes = 0;
         PLAN_TRY(dev_alloc(&d_gx, (size_t)n_faces * tangent_w, &tmp));
         PLAN_TRY(dev_alloc(&d_gy, n_rows, &tmp));
+        PLAN_TRY(dev_alloc(&d_rows, (size_t)erp_h * 2, &tmp));
+        PLAN_TRY(dev_alloc(&d_cols, (size_t)n_faces * erp_w * 2, &tmp));
         PLAN_TRY(dev_alloc(&d_status, 2, &tmp));
         PLAN_TRY(dev_alloc(&d_msum, n_faces + 1, &tmp));
         scratch_bytes = tmp.device_bytes;
@@ -371,28 +359,16 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gy, tables->gnom_y, sizeof(double) * n_rows, cudaMemcpyHostToDevice, stream), "copy gnom_y"));
     PLAN_TRY(cuda_status(cudaMemcpyAsync(d_rows, tables->row_sincos, sizeof(double) * erp_h * 2, cudaMemcpyHostToDevice, stream), "copy row table"));
     PLAN_TRY(cuda_status(cudaMemcpyAsync(d_cols, tables->col_sincos, sizeof(double) * n_faces * erp_w * 2, cudaMemcpyHostToDevice, stream), "copy column table"));
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_col_theta, tables->col_theta, sizeof(double) * erp_w, cudaMemcpyHostToDevice, stream), "copy column theta"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_mark, 0, n_tangent, stream), "memset"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), stream), "memset"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, (n_faces + 1) * sizeof(unsigned long long), stream), "memset"));
-    {
-        // float32 copies of the separable tables for the execute kernels (rotation of the end point)
-        const size_t n_row = (size_t)erp_h, n_col = (size_t)n_faces * erp_w;
-        float2* h_f = (float2*)malloc(sizeof(float2) * (n_row + n_col));
-        for (size_t i = 0; i < n_row; ++i) h_f[i] = make_float2((float)tables->row_sincos[2 * i], (float)tables->row_sincos[2 * i + 1]);
-        for (size_t i = 0; i < n_col; ++i) h_f[n_row + i] = make_float2((float)tables->col_sincos[2 * i], (float)tables->col_sincos[2 * i + 1]);
-        cudaError_t ea = cudaMemcpyAsync(plan->d_row_sc, h_f, sizeof(float2) * n_row, cudaMemcpyHostToDevice, stream);
-        cudaError_t eb = cudaMemcpyAsync(plan->d_col_sc, h_f + n_row, sizeof(float2) * n_col, cudaMemcpyHostToDevice, stream);
-        cudaError_t ec = cudaStreamSynchronize(stream);   // h_f and h_row_face are pageable
-        free(h_f);
-        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : (eb != cudaSuccess ? eb : ec), "plan upload"));
-    }
+    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan upload"));   // h_row_face is pageable
     free(h_row_face);
 
     const int threads = 256;
     k_plan_stage1<<<(unsigned)((n_tangent + threads - 1) / threads), threads, 0, stream>>>(
         plan->d_faces, plan->d_pix_face, d_gx, d_gy, erp_h, erp_w, tangent_w, n_tangent, plan->d_s1_base,
-        plan->d_s1_frac, plan->d_s1_frac64, plan->d_s1_ex, plan->d_s1_ey);
+        plan->d_s1_frac64, plan->d_s1_ex, plan->d_s1_ey);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage1 launch"));
 
     const unsigned blocks2 = (unsigned)((n_erp + threads - 1) / threads);
@@ -470,30 +446,10 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
             PLAN_TRY(TIF_ERR_RANGE);
         }
     }
-    {
-        // exclusive prefix sum of the per-pixel counts (plan-time bookkeeping: 1 byte per ERP pixel through the host)
-        PLAN_TRY(dev_alloc(&plan->d_s2_offset, n_erp, plan));
-        uint8_t* h_cnt = (uint8_t*)malloc((size_t)n_erp);
-        uint32_t* h_off = (uint32_t*)malloc((size_t)n_erp * sizeof(uint32_t));
-        cudaError_t ea = cudaMemcpy(h_cnt, plan->d_s2_count, (size_t)n_erp, cudaMemcpyDeviceToHost);
-        uint32_t run = 0;
-        for (int64_t i = 0; i < n_erp; ++i) {
-            h_off[i] = run;
-            run += h_cnt[i];
-        }
-        cudaError_t eb = cudaMemcpy(plan->d_s2_offset, h_off, (size_t)n_erp * sizeof(uint32_t), cudaMemcpyHostToDevice);
-        free(h_cnt);
-        free(h_off);
-        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "sample offsets"));
-        if ((int64_t)run != plan->accepted_unique) {
-            tif_set_error("tif_plan_create: sample offsets (%u) disagree with the accepted count (%lld)", run,
-                          (long long)plan->accepted_unique);
-            PLAN_TRY(TIF_ERR_RANGE);
-        }
-    }
-
     cudaFree(d_gx);
     cudaFree(d_gy);
+    cudaFree(d_rows);
+    cudaFree(d_cols);
     cudaFree(d_status);
     cudaFree(d_msum);
     *plan_out = plan;

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TIF_ABI_VERSION 1
+#define TIF_ABI_VERSION 2
 #define TIF_MAX_FACES 128      /* 7-bit face id in a membership entry */
 #define TIF_MAX_TANGENT_DIM 2048 /* 11-bit tangent row / column in a membership entry */
 
@@ -93,7 +93,6 @@ typedef struct TifPlanTables {
     const double* gnom_y;       /* [P / Wt]  np.linspace(ymax, ymin, Ht_f), faces concatenated (:208) */
     const double* row_sincos;   /* [H][2]    sin(phi_r), cos(phi_r), phi_r per spherical_coordinates.py:93 */
     const double* col_sincos;   /* [F][W][2] sin(theta_c - theta0_f), cos(theta_c - theta0_f) (gnomonic_projection.py:36) */
-    const double* col_theta;    /* [W]       theta_c per spherical_coordinates.py:92,99 */
 } TifPlanTables;
 
 typedef struct TifPlan TifPlan;     /* opaque; owns device tables */

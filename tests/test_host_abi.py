@@ -29,7 +29,7 @@ def test_product_face_table_matches_reference(pkg, golden):
 def test_host_geometry_tables(pkg):
     hg = pkg._geometry.HostGeometry(0.3, 64, 32)
     assert hg.tangent_h == 28 and hg.tangent_pixels == 20 * 28 * 32
-    assert hg.row_sincos.shape == (64, 2) and hg.col_sincos.shape == (20, 128, 2) and hg.col_theta.shape == (128,)
+    assert hg.row_sincos.shape == (64, 2) and hg.col_sincos.shape == (20, 128, 2)
     assert [hg.faces[f].pix_offset for f in range(3)] == [0, 28 * 32, 2 * 28 * 32]
     assert hg.faces[0].col_start == -1 and hg.faces[0].col_stop == 128 and hg.faces[0].row_start == -1
     assert pkg._geometry.tangent_image_height(480) == 416
@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layout_and_status_strings(pkg):
     lib = pkg._lib.load()
-    assert lib.tif_abi_version() == 1
+    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 2
     sizes = [ctypes.c_int32() for _ in range(3)]
     assert lib.tif_struct_sizes(*[ctypes.byref(s) for s in sizes]) == 0
     assert [s.value for s in sizes] == [ctypes.sizeof(pkg._lib.TifFace), ctypes.sizeof(pkg._lib.TifPlanTables),
