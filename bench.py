@@ -39,6 +39,7 @@ def parse_args():
                     help="face_blending_method; normwarp is the reference pipeline's default (flow_estimate.py:104)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="launch the step's kernels on one stream (no overlap)")
     ap.add_argument("--kernel-reps", type=int, default=10)
     return ap.parse_args()
 
@@ -47,7 +48,8 @@ def workload_config(args, n_gpus):
     return {"workload": "synthetic %dx%d ERP pairs, 20 tangent faces 480x416, padding 0.3, blend %s, wrap_around, "
                         "tangent flows injected (DIS excluded)" % (2 * args.height, args.height, args.blend),
             "pairs_per_gpu_per_step": args.batch, "global_pairs_per_step": args.batch * n_gpus,
-            "sharding": "batch across ranks, no data-path collective", "l2": "inputs (%.1f GB/GPU/step) exceed the 126 MB L2"
+            "sharding": "batch across ranks, no data-path collective",
+            "streams": "1 (serial)" if args.serial else "3 (resample src | resample tar | stitch overlap)", "l2": "inputs (%.1f GB/GPU/step) exceed the 126 MB L2"
             % (args.batch * (2 * args.height * 2 * args.height * 3 + 20 * 416 * 480 * 8) / 1e9)}
 
 
@@ -219,10 +221,27 @@ def run_ours(args):
     # erp2ico x2; stitch = k_lift + k_gather (normwarp: k_lift, k_gather<sums>, k_gather<blend>)
     launches_per_step = 4 if blend == lib.BLEND_STRAIGHTFORWARD else 5
 
+    # The two resamplings and the stitch are independent of each other: they run on separate streams so that
+    # their blocks share the SMs (each kernel alone is issue/latency bound and leaves slots idle).
+    side = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    fork, joins = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
+
     def step():
-        ops.erp2ico_out(plan, src, True, tan_src)
-        ops.erp2ico_out(plan, tar, True, tan_tar)
+        main = torch.cuda.current_stream()
+        if args.serial:
+            ops.erp2ico_out(plan, src, True, tan_src)
+            ops.erp2ico_out(plan, tar, True, tan_tar)
+            ops.ico2erp_flow_out(plan, flows, src, tar, blend, True, out, scratch)
+            return
+        fork.record(main)
+        for s_, img, dst, ev in ((side[0], src, tan_src, joins[0]), (side[1], tar, tan_tar, joins[1])):
+            s_.wait_event(fork)
+            with torch.cuda.stream(s_):
+                ops.erp2ico_out(plan, img, True, dst)
+                ev.record(s_)
         ops.ico2erp_flow_out(plan, flows, src, tar, blend, True, out, scratch)
+        main.wait_event(joins[0])
+        main.wait_event(joins[1])
 
     def barrier():
         if world > 1:

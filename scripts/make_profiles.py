@@ -14,9 +14,11 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import ncu_raw_summary  # noqa: E402
 import ncu_source_summary  # noqa: E402
 
-KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_stitch<0", "k_stitch<straightforward>"), ("k_stitch<(int)0", "k_stitch<straightforward>"),
-               ("k_stitch<1", "k_stitch<normwarp pass A>"), ("k_stitch<(int)1", "k_stitch<normwarp pass A>"),
-               ("k_blend_normwarp", "k_blend_normwarp (pass B)"), ("k_lift", "k_lift")]
+KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_lift<0", "k_lift<straightforward>"), ("k_lift<(bool)0", "k_lift<straightforward>"),
+               ("k_lift<1", "k_lift<normwarp>"), ("k_lift<(bool)1", "k_lift<normwarp>"),
+               ("k_gather<0", "k_gather<straightforward>"), ("k_gather<(int)0", "k_gather<straightforward>"),
+               ("k_gather<1", "k_gather<sums>"), ("k_gather<(int)1", "k_gather<sums>"),
+               ("k_gather<2", "k_gather<blend>"), ("k_gather<(int)2", "k_gather<blend>")]
 
 
 def capture(fn, *args):
