@@ -89,6 +89,54 @@ def get_icosahedron_parameters(triangle_index, padding_size=0.0):
             "triangle_points_sph": sph, "availied_ERP_area": theta_range + phi_range}
 
 
+def _unit(v):
+    return v / np.linalg.norm(v)
+
+
+def get_subdivided_parameters(face_index, padding_size=0.0, boundary_samples=256):
+    """Face dictionary of the level-1 subdivision (80 faces) -- an EXTENSION, the reference stops at 20 faces
+    (SURVEY.md Appendix E).  Built from the reference's own primitives so that nothing new enters the per-pixel
+    maths: each level-0 triangle (unpadded spherical vertices of projection_icosahedron.py:43-104) is split at its
+    edge midpoints (normalised to the sphere); children (v0,m01,m20), (m01,v1,m12), (m20,m12,v2), (m01,m12,m20);
+    face id = 4 * parent + child; tangent point = normalised centroid; padding = padding_size / 2.
+    """
+    parent, child = divmod(int(face_index), 4)
+    _, _, verts = _level0_vertices(parent)
+    v = [sc.sph2car(np.float64(t), np.float64(p)) for t, p in verts]          # +x right, +y down, +z forward
+    m01, m12, m20 = _unit(v[0] + v[1]), _unit(v[1] + v[2]), _unit(v[2] + v[0])
+    tri3d = [(v[0], m01, m20), (m01, v[1], m12), (m20, m12, v[2]), (m01, m12, m20)][child]
+    centre = sc.car2sph(np.array([_unit(tri3d[0] + tri3d[1] + tri3d[2])]))[0]
+    theta_0, phi_0 = centre[0], centre[1]
+    corners = sc.car2sph(np.array(tri3d))
+    flat = [gp.gnomonic_projection(corners[k, 0], corners[k, 1], theta_0, phi_0) for k in range(3)]
+    flat = [[p[0], p[1]] for p in flat]
+    if not polygon.is_clockwise(flat):
+        flat = flat[::-1]
+    padded = polygon.enlarge_polygon(flat, padding_size / 2.0)
+    sph = [list(gp.reverse_gnomonic_projection(p[0], p[1], theta_0, phi_0)) for p in padded]
+    # ERP bounding box from a densely sampled boundary of the padded triangle
+    bx, by = [], []
+    for k in range(3):
+        a, b = padded[k], padded[(k + 1) % 3]
+        t = np.linspace(0.0, 1.0, boundary_samples, endpoint=False)
+        bx.append(a[0] + (b[0] - a[0]) * t)
+        by.append(a[1] + (b[1] - a[1]) * t)
+    b_theta, b_phi = gp.reverse_gnomonic_projection(np.concatenate(bx), np.concatenate(by), theta_0, phi_0)
+    area = [np.amin(b_theta), np.amax(b_theta), np.amax(b_phi), np.amin(b_phi)]
+    tiny = 1e-9
+    for pole_phi in (np.pi / 2.0, -np.pi / 2.0):
+        if np.sin(phi_0) * np.sin(pole_phi) <= 0.0:           # pole on the far hemisphere of this tangent plane
+            continue
+        px, py, _ = gp.gnomonic_projection(theta_0, pole_phi, theta_0, phi_0)
+        if polygon.inside_polygon_2d(np.array([[px, py]]), padded, on_line=True, eps=tiny)[0]:
+            if pole_phi > 0:
+                area = [-np.pi, np.pi, np.pi / 2.0, np.amin(b_phi)]
+            else:
+                area = [-np.pi, np.pi, np.amax(b_phi), -np.pi / 2.0]
+    return {"tangent_point": [theta_0, phi_0], "triangle_points_tangent": padded,
+            "triangle_points_sph": sph, "availied_ERP_area": area}
+
+
 def erp_bounding_box(availied_erp_area, erp_height):
     """Integer ERP bounding box (col_start, col_stop, row_start, row_stop), src/projection_icosahedron.py:299-305."""
     col0, row0 = sc.sph2erp(availied_erp_area[0], availied_erp_area[2], erp_height, sph_modulo=False)
@@ -104,21 +152,26 @@ def erp_bounding_box(availied_erp_area, erp_height):
 
 
 class HostGeometry:
-    """Face structs + tables for one (padding, H, Wt) configuration of the 20-face icosahedron."""
+    """Face structs + tables for one (padding, H, Wt, level) configuration: the reference's 20-face icosahedron
+    (level 0) or its 80-face subdivision (level 1, extension; per-face tangent heights, ragged stack)."""
 
-    def __init__(self, padding_size, erp_height, tangent_width):
+    def __init__(self, padding_size, erp_height, tangent_width, level=0):
+        if level not in (0, 1):
+            raise ValueError("subdivision level must be 0 or 1")
+        self.level = int(level)
         self.padding_size = float(padding_size)
         self.erp_h = int(erp_height)
         self.erp_w = 2 * self.erp_h
         self.tangent_w = int(tangent_width)
-        self.tangent_h = tangent_image_height(self.tangent_w)
-        n = NUM_FACES_LEVEL0
+        self.tangent_h = tangent_image_height(self.tangent_w)          # level 0; level 1 heights are per face
+        n = NUM_FACES_LEVEL0 * (4 ** self.level)
         self.n_faces = n
         self.faces = (_lib.TifFace * n)()
         self.params = []
         h, w, wt, ht = self.erp_h, self.erp_w, self.tangent_w, self.tangent_h
         self.gnom_x = np.zeros((n, wt), dtype=np.float64)
-        self.gnom_y = np.zeros((n, ht), dtype=np.float64)
+        gnom_y_rows = []
+        self.face_heights = []
         # spherical_coordinates.py:92-100 evaluated on the column / row index vectors
         cols = np.arange(w, dtype=np.float64)
         rows = np.arange(h, dtype=np.float64)
@@ -130,12 +183,16 @@ class HostGeometry:
         self.col_sincos = np.zeros((n, w, 2), dtype=np.float64)
         offset = 0
         for f in range(n):
-            par = get_icosahedron_parameters(f, self.padding_size)
+            par = (get_icosahedron_parameters(f, self.padding_size) if self.level == 0
+                   else get_subdivided_parameters(f, self.padding_size))
             self.params.append(par)
             tri = np.array(par["triangle_points_tangent"])
             xmin, xmax = np.amin(tri[:, 0], axis=0), np.amax(tri[:, 0], axis=0)
             ymin, ymax = np.amin(tri[:, 1], axis=0), np.amax(tri[:, 1], axis=0)
             theta_0, phi_0 = par["tangent_point"]
+            if self.level == 1:      # bounding rectangle of the padded triangle at the tangent width
+                ht = int(wt * (ymax - ymin) / (xmax - xmin) + 0.5)
+            self.face_heights.append(ht)
             F = self.faces[f]
             F.theta0, F.phi0 = theta_0, phi_0
             F.sin_phi0, F.cos_phi0 = np.sin(phi_0), np.cos(phi_0)
@@ -153,11 +210,12 @@ class HostGeometry:
             F.pix_offset = offset
             offset += ht * wt
             self.gnom_x[f] = np.linspace(xmin, xmax, num=wt, endpoint=True)     # :207
-            self.gnom_y[f] = np.linspace(ymax, ymin, num=ht, endpoint=True)     # :208
+            gnom_y_rows.append(np.linspace(ymax, ymin, num=ht, endpoint=True))  # :208
             delta = theta - theta_0                                             # gnomonic_projection.py:36
             self.col_sincos[f, :, 0] = np.sin(delta)
             self.col_sincos[f, :, 1] = np.cos(delta)
         self.tangent_pixels = offset
+        self.gnom_y = np.concatenate(gnom_y_rows)
 
     def tables(self):
         dp = C.POINTER(C.c_double)
@@ -171,12 +229,15 @@ class HostGeometry:
 class Plan:
     """Device-resident geometry plan (wraps TifPlan*)."""
 
-    def __init__(self, padding_size, erp_height, tangent_width, device):
+    def __init__(self, padding_size, erp_height, tangent_width, device, level=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.TifError("no CUDA device: the tangent-image hot path has no CPU fallback")
         self.device = torch.device(device)
-        self.host = HostGeometry(padding_size, erp_height, tangent_width)
+        self.host = HostGeometry(padding_size, erp_height, tangent_width, level)
+        self.level = int(level)
+        self.face_heights = list(self.host.face_heights)
+        self.face_offsets = [int(self.host.faces[f].pix_offset) for f in range(self.host.n_faces)]
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
@@ -229,7 +290,7 @@ _plans = {}
 _plans_lock = threading.Lock()
 
 
-def get_plan(padding_size, erp_height, tangent_width, device=None):
+def get_plan(padding_size, erp_height, tangent_width, device=None, level=0):
     """Cached plan for a configuration on a device (default: current CUDA device)."""
     if device is None:
         if not torch.cuda.is_available():
@@ -238,11 +299,11 @@ def get_plan(padding_size, erp_height, tangent_width, device=None):
     device = torch.device(device)
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (float(padding_size), int(erp_height), int(tangent_width), device.index)
+    key = (float(padding_size), int(erp_height), int(tangent_width), device.index, int(level))
     with _plans_lock:
         plan = _plans.get(key)
         if plan is None:
-            plan = Plan(padding_size, erp_height, tangent_width, device)
+            plan = Plan(padding_size, erp_height, tangent_width, device, level)
             _plans[key] = plan
     return plan
 

@@ -8,7 +8,8 @@ Same names, argument meaning and return types as the reference:
                  image_erp_tar=None, wrap_around=False, face_blending_method="straightforward")
 
 numpy in -> numpy out exactly like the reference (list of 20 int64 [Ht,Wt,4] images; float64 [H,W,2]
-flow).  Torch CUDA tensors with a leading batch axis go straight through and stay on the device:
+flow).  Keyword-only extra: subdivision_level=1 selects the 80-face level-1 subdivision (an extension, the
+reference stops at 20 faces; faces then have their own heights and the lists hold 80 arrays).  Torch CUDA tensors with a leading batch axis go straight through and stay on the device:
 erp2ico_image([B,H,W,3] uint8) -> [B,20,Ht,Wt,4] uint8, ico2erp_flow([B,20,Ht,Wt,2] float32) ->
 [B,H,W,2] float32.  All per-pixel work runs in libtif_b200.so; there is no CPU fallback.
 """
@@ -18,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _geometry, _lib, _ops
-from ._geometry import get_icosahedron_parameters, tangent_image_height  # noqa: F401  (reference API)
+from ._geometry import get_icosahedron_parameters, get_subdivided_parameters, tangent_image_height  # noqa: F401
 
 log = logging.getLogger(__name__)
 
@@ -31,15 +32,23 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_image=True):
+def _split_faces(stack, plan):
+    """[..., P, C] flat tangent stack -> list of per-face [..., Ht_f, Wt, C] views (ragged at level 1)."""
+    return [stack[..., o:o + h * plan.tangent_w, :].reshape(stack.shape[:-2] + (h, plan.tangent_w, stack.shape[-1]))
+            for o, h in zip(plan.face_offsets, plan.face_heights)]
+
+
+def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_image=True, *, subdivision_level=0):
     """Project an ERP image to the 20 padded tangent images (src/projection_icosahedron.py:163-248)."""
     if isinstance(erp_image, torch.Tensor):
         if erp_image.dim() != 4:
             raise ValueError("torch input must be [B,H,W,3] uint8")
         if erp_image.shape[-1] == 4:
             erp_image = erp_image[..., 0:3]
-        plan = _geometry.get_plan(padding_size, erp_image.shape[1], tangent_image_width, erp_image.device)
+        plan = _geometry.get_plan(padding_size, erp_image.shape[1], tangent_image_width, erp_image.device, subdivision_level)
         out = _ops.ops.erp2ico(erp_image, _ops.register_plan(plan), bool(full_face_image))
+        if subdivision_level:
+            return out                    # ragged faces: flat [B,P,4]; plan.face_offsets / face_heights index it
         return out.view(erp_image.shape[0], plan.n_faces, plan.tangent_h, plan.tangent_w, 4)
 
     erp_image = np.asarray(erp_image)
@@ -52,16 +61,15 @@ def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_im
         log.error("the ERP image dimession is %s", np.shape(erp_image))     # the reference logs and continues
         raise ValueError("ERP image must be 2:1, got %s" % (erp_image.shape,))
     dev = _device()
-    plan = _geometry.get_plan(padding_size, erp_image.shape[0], tangent_image_width, dev)
+    plan = _geometry.get_plan(padding_size, erp_image.shape[0], tangent_image_width, dev, subdivision_level)
     erp_dev = torch.from_numpy(np.ascontiguousarray(erp_image)).to(dev)[None]
     out = _ops.ops.erp2ico(erp_dev, _ops.register_plan(plan), bool(full_face_image))
-    stack = out.view(plan.n_faces, plan.tangent_h, plan.tangent_w, 4).cpu().numpy()
     # the reference builds its images with np.full(..., 255): int64, 4 channels
-    return [stack[f].astype(np.int64) for f in range(plan.n_faces)]
+    return [t.astype(np.int64) for t in _split_faces(out[0].cpu().numpy(), plan)]
 
 
 def ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, image_erp_src=None, image_erp_tar=None,
-                 wrap_around=False, face_blending_method="straightforward"):
+                 wrap_around=False, face_blending_method="straightforward", *, subdivision_level=0):
     """Stitch the 20 tangent flows into an ERP flow (src/projection_icosahedron.py:251-398)."""
     if face_blending_method not in _BLENDS:
         # the reference falls through to an UnboundLocalError on face_weight_mat
@@ -70,6 +78,10 @@ def ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, ima
 
     if isinstance(tangent_flows_list, torch.Tensor):
         flows = tangent_flows_list
+        if subdivision_level:
+            # ragged faces: flat [B,P,2] stack; the tangent width cannot be read off the tensor
+            raise NotImplementedError("level-1 torch input: call _ops.ico2erp_flow_out with a plan from "
+                                      "_geometry.get_plan(..., level=1) and a flat [B,P,2] stack")
         if flows.dim() != 5 or flows.shape[-1] != 2:
             raise ValueError("torch input must be [B,20,Ht,Wt,2] float32")
         batch, n_faces, ht, wt = flows.shape[:4]
@@ -80,17 +92,21 @@ def ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, ima
         return _ops.ops.ico2erp_flow(flows.reshape(batch, plan.tangent_pixels, 2), image_erp_src, image_erp_tar,
                                      _ops.register_plan(plan), blend, bool(wrap_around))
 
-    if len(tangent_flows_list) != 20:
-        log.error("the ico face flow number is not 20")
-        raise ValueError("the ico face flow number is not 20")
+    n_expected = 20 * 4 ** int(subdivision_level)
+    if len(tangent_flows_list) != n_expected:
+        log.error("the ico face flow number is not %d", n_expected)
+        raise ValueError("the ico face flow number is not %d" % n_expected)
     ht, wt = np.shape(tangent_flows_list[0])[:2]
     if np.shape(tangent_flows_list[0])[2] != 2:
         log.error("The flow channels number is %s", np.shape(tangent_flows_list[0])[2])
         raise ValueError("tangent flows must have 2 channels")
     erp_h = int(ht * 2.0) if erp_flow_height is None else int(erp_flow_height)
     dev = _device()
-    plan = _geometry.get_plan(padding_size, erp_h, wt, dev)
-    flows = np.stack([np.asarray(f, dtype=np.float32) for f in tangent_flows_list])
+    plan = _geometry.get_plan(padding_size, erp_h, wt, dev, subdivision_level)
+    for f, h in zip(tangent_flows_list, plan.face_heights):
+        if tuple(np.shape(f)) != (h, wt, 2):
+            raise ValueError("tangent flow of shape %s, expected %s" % (np.shape(f), (h, wt, 2)))
+    flows = np.concatenate([np.asarray(f, dtype=np.float32).reshape(-1, 2) for f in tangent_flows_list])
     flows_dev = torch.from_numpy(flows).to(dev).reshape(1, plan.tangent_pixels, 2)
     src_dev = tar_dev = None
     if blend == _lib.BLEND_NORMWARP:

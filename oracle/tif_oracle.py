@@ -226,7 +226,7 @@ def enlarge_polygon(pts, offset):
 # face table -- projection_icosahedron.py:19-160
 # ------------------------------------------------------------------------------------------------
 
-def icosahedron_face(face, padding=0.0):
+def icosahedron_face(face, padding=0.0, return_vertices=False):
     """Returns dict(theta_0, phi_0, tri [3,2] padded gnomonic triangle, area [th_min, th_max, phi_rowstart, phi_rowstop])."""
     r_circ = np.sin(2 * np.pi / 5.0)
     r_in = np.sqrt(3) / 12.0 * (3 + np.sqrt(5))
@@ -263,6 +263,8 @@ def icosahedron_face(face, padding=0.0):
              (- np.pi + i * step, -np.pi / 2.0)]
     else:
         raise ValueError(face)
+    if return_vertices:
+        return v
     tri0 = [gnomonic_forward(th, ph, theta_0, phi_0) for th, ph in v]
     tri = enlarge_polygon(tri0, padding)
     sph = [list(gnomonic_reverse(p[0], p[1], theta_0, phi_0)) for p in tri]
@@ -282,6 +284,81 @@ def icosahedron_face(face, padding=0.0):
     else:
         area = [np.amin(sph_a[:, 0]), np.amax(sph_a[:, 0]), np.amax(sph_a[:, 1]), np.amin(sph_a[:, 1])]
     return {"theta_0": theta_0, "phi_0": phi_0, "tri": tri_a, "area": area}
+
+
+def _sph2car(theta, phi):
+    """spherical_coordinates.py:151-169: +x right, +y down, +z forward."""
+    return np.array([np.cos(phi) * np.sin(theta), -np.sin(phi), np.cos(phi) * np.cos(theta)])
+
+
+def _car2sph(points):
+    """spherical_coordinates.py:128-148: [N,3] cartesian -> [N,2] (theta, phi)."""
+    points = np.asarray(points, dtype=np.float64)
+    radius = np.linalg.norm(points, axis=1)
+    return np.stack((np.arctan2(points[:, 0], points[:, 2]), -np.arcsin(np.divide(points[:, 1], radius))), axis=1)
+
+
+def _is_clockwise(pts):
+    """polygon.py:43-56."""
+    total = 0
+    for i in range(len(pts)):
+        cur, nxt = pts[i], pts[(i + 1) % len(pts)]
+        total += (nxt[0] - cur[0]) * (nxt[1] + cur[1])
+    return total > 0
+
+
+def subdivided_face(face, padding=0.0, boundary_samples=256):
+    """Level-1 (80-face) subdivision, SURVEY.md Appendix E -- an EXTENSION: the reference has no such table, so
+    this is a composition of its primitives and parity for it is pinned only by self-consistency
+    (level 0 of the same machinery == the reference).  Same dictionary as icosahedron_face."""
+    parent, child = divmod(int(face), 4)
+    verts = icosahedron_face(parent, 0.0, return_vertices=True)
+    v = [_sph2car(np.float64(t), np.float64(p)) for t, p in verts]
+    mid = lambda a, b: (a + b) / np.linalg.norm(a + b)      # noqa: E731
+    m01, m12, m20 = mid(v[0], v[1]), mid(v[1], v[2]), mid(v[2], v[0])
+    tri3d = [(v[0], m01, m20), (m01, v[1], m12), (m20, m12, v[2]), (m01, m12, m20)][child]
+    c = tri3d[0] + tri3d[1] + tri3d[2]
+    theta_0, phi_0 = _car2sph(np.array([c / np.linalg.norm(c)]))[0]
+    corners = _car2sph(np.array(tri3d))
+    flat = []
+    for k in range(3):
+        x, y = gnomonic_forward(corners[k, 0], corners[k, 1], theta_0, phi_0)
+        flat.append([x, y])
+    if not _is_clockwise(flat):
+        flat = flat[::-1]
+    tri = enlarge_polygon(flat, padding / 2.0)
+    tri_a = np.array(tri)
+    bx, by = [], []
+    for k in range(3):
+        a, b = tri[k], tri[(k + 1) % 3]
+        t = np.linspace(0.0, 1.0, boundary_samples, endpoint=False)
+        bx.append(a[0] + (b[0] - a[0]) * t)
+        by.append(a[1] + (b[1] - a[1]) * t)
+    b_th, b_ph = gnomonic_reverse(np.concatenate(bx), np.concatenate(by), theta_0, phi_0)
+    area = [np.amin(b_th), np.amax(b_th), np.amax(b_ph), np.amin(b_ph)]
+    for pole in (np.pi / 2.0, -np.pi / 2.0):
+        if np.sin(phi_0) * np.sin(pole) <= 0.0:
+            continue
+        px, py = gnomonic_forward(theta_0, pole, theta_0, phi_0)
+        if inside_polygon(np.array([px]), np.array([py]), tri_a, 1e-9)[0]:
+            area = [-np.pi, np.pi, np.pi / 2.0, np.amin(b_ph)] if pole > 0 else [-np.pi, np.pi, np.amax(b_ph), -np.pi / 2.0]
+    return {"theta_0": theta_0, "phi_0": phi_0, "tri": tri_a, "area": area}
+
+
+def face_params(face, padding, level=0):
+    return icosahedron_face(face, padding) if level == 0 else subdivided_face(face, padding)
+
+
+def n_faces(level=0):
+    return NUM_FACES * 4 ** level
+
+
+def face_tangent_height(face_par, tangent_w, level=0):
+    """projection_icosahedron.py:194 at level 0; bounding rectangle of the padded triangle at level 1."""
+    if level == 0:
+        return tangent_height(tangent_w)
+    tri = face_par["tri"]
+    return int(tangent_w * (np.amax(tri[:, 1]) - np.amin(tri[:, 1])) / (np.amax(tri[:, 0]) - np.amin(tri[:, 0])) + 0.5)
 
 
 def _pyint_start(v):
@@ -322,7 +399,7 @@ def erp2ico_sample_coords(face_par, erp_h, tangent_w, tangent_h):
     return ex, ey, gxv, gyv, (xmin, xmax, ymin, ymax)
 
 
-def erp2ico_image(erp_image, tangent_w, padding=0.0, full_face_image=True, faces=range(NUM_FACES)):
+def erp2ico_image(erp_image, tangent_w, padding=0.0, full_face_image=True, faces=None, level=0):
     """Returns list of int64 [Ht,Wt,4] (RGB rounded uint8 values, alpha 255/0) like the reference."""
     erp_image = np.asarray(erp_image)
     if erp_image.ndim == 3 and erp_image.shape[2] == 4:
@@ -331,10 +408,10 @@ def erp2ico_image(erp_image, tangent_w, padding=0.0, full_face_image=True, faces
         erp_image = erp_image[:, :, None]
     erp_h = erp_image.shape[0]
     nch = erp_image.shape[2]
-    tangent_h = tangent_height(tangent_w)
     out = []
-    for f in faces:
-        par = icosahedron_face(f, padding)
+    for f in (range(n_faces(level)) if faces is None else faces):
+        par = face_params(f, padding, level)
+        tangent_h = face_tangent_height(par, tangent_w, level)
         ex, ey, gxv, gyv, (xmin, xmax, ymin, ymax) = erp2ico_sample_coords(par, erp_h, tangent_w, tangent_h)
         inside = np.ones(gxv.shape, dtype=bool)
         if not full_face_image:
@@ -389,14 +466,14 @@ def face_membership(face_par, erp_h, tangent_w, tangent_h):
     return rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta
 
 
-def stitch_face(face, flow, erp_h, padding, img_s, img_t, wrap_around, blending):
+def stitch_face(face, flow, erp_h, padding, img_s, img_t, wrap_around, blending, level=0):
     """One iteration of the reference's face loop (projection_icosahedron.py:282-381) in pull form.
     flow: float32 [Ht,Wt,2]; img_s/img_t: float64 [H,W,3] (normwarp only).
     Returns dict(r, c, fu, fv, w, ix, iy, mult, candidates, accepted, bbox, th_t, tx, ty)."""
     flow = np.asarray(flow)
     tangent_h, tangent_w = flow.shape[:2]
     erp_w = int(erp_h * 2.0)
-    par = icosahedron_face(face, padding)
+    par = face_params(face, padding, level)
     th0, ph0 = par["theta_0"], par["phi_0"]
     rows, cols, mult, acc, ix, iy, (xmin, xmax, ymin, ymax), theta_cols = \
         face_membership(par, erp_h, tangent_w, tangent_h)
@@ -483,7 +560,7 @@ def blend_faces(face_results, erp_h, wrap_around, return_debug=False):
 
 
 def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_tar=None,
-                 wrap_around=False, blending="straightforward", return_debug=False):
+                 wrap_around=False, blending="straightforward", return_debug=False, level=0):
     """Returns float64 [H, 2H, 2] (and a debug dict when asked)."""
     tangent_h = tangent_flows[0].shape[0]
     if erp_h is None:
@@ -493,7 +570,7 @@ def ico2erp_flow(tangent_flows, erp_h=None, padding=0.0, image_src=None, image_t
     if blending == "normwarp":
         img_s = np.asarray(image_src).astype(np.float64)     # the same-size `resize` (:374-377) is this cast
         img_t = np.asarray(image_tar).astype(np.float64)
-    results = [stitch_face(f, tangent_flows[f], erp_h, padding, img_s, img_t, wrap_around, blending)
+    results = [stitch_face(f, tangent_flows[f], erp_h, padding, img_s, img_t, wrap_around, blending, level)
                for f in range(len(tangent_flows))]
     return blend_faces(results, erp_h, wrap_around, return_debug)
 

@@ -115,3 +115,21 @@ def test_gather_over_gloo_world_size_2(n_items):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "GATHER_OK" in res.stdout
+
+
+def test_level1_face_table_matches_oracle(pkg):
+    """Config #5 (80 faces, extension): the product's host table and the oracle's independent restatement agree
+    bitwise, the per-face heights are SURVEY.md Appendix E's, and level 0 of the same class is the reference table."""
+    from oracle import tif_oracle
+    geo = pkg._geometry
+    for f in range(80):
+        a = geo.get_subdivided_parameters(f, 0.3)
+        b = tif_oracle.subdivided_face(f, 0.3)
+        assert a["tangent_point"][0] == b["theta_0"] and a["tangent_point"][1] == b["phi_0"]
+        assert np.array_equal(np.array(a["triangle_points_tangent"]), b["tri"])
+        assert np.array_equal(np.array(a["availied_ERP_area"]), np.array(b["area"]))
+    hg = geo.HostGeometry(0.3, 2048, 480, level=1)
+    assert hg.n_faces == 80 and sorted(set(hg.face_heights)) == [346, 416, 485, 502] and sum(hg.face_heights) == 34980
+    assert hg.gnom_y.shape == (34980,) and hg.tangent_pixels == 34980 * 480
+    hg0 = geo.HostGeometry(0.3, 64, 32, level=0)
+    assert hg0.n_faces == 20 and set(hg0.face_heights) == {28}
