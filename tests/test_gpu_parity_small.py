@@ -124,3 +124,24 @@ def test_oracle_agrees_at_mid_size(pkg, smooth, offset):
             excuse |= dbg["edge_dist"] < 1e-3
         bad = ((np.abs(g - w).max(axis=2) > FLOW_TOL) & ~excuse).sum()
         assert bad == 0, (blend, bad, np.abs(g - w).max())
+
+
+@pytest.mark.parametrize("erp_h,wt", [(90, 50), (77 * 2, 37), (66, 95)])
+def test_sizes_that_are_not_tile_multiples(pkg, erp_h, wt):
+    """Edge sizes: tangent width not a multiple of the 8-wide warp tile, ERP height not a multiple of 4, a tangent
+    image wider than the ERP is tall.  uint8 exact, membership implied by the flow parity."""
+    src, tar = synth.synth_images(erp_h, 13)
+    flows = synth.synth_flows(wt, 20, 2.0)
+    pico = pkg.projection_icosahedron
+    for full in (True, False):
+        got = pico.erp2ico_image(src, wt, 0.3, full)
+        want = tif_oracle.erp2ico_image(src, wt, 0.3, full)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    for blend in ("straightforward", "normwarp"):
+        want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, 0.3, src, tar, True, blend, return_debug=True)
+        got = pico.ico2erp_flow(flows, erp_h, 0.3, src, tar, True, blend)
+        excuse = dbg["seam_dist"] < 1e-5
+        if blend == "normwarp":
+            excuse |= dbg["edge_dist"] < 1e-3
+        assert (((np.abs(got - want).max(axis=2)) > FLOW_TOL) & ~excuse).sum() == 0
+    assert np.array_equal(pkg.flow_warp.warp_backward(tar, want), tif_oracle.warp_backward(tar, want))
