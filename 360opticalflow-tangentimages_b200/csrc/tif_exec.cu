@@ -272,8 +272,15 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // the direction vector cancels in float32, and under normwarp the faces disagree by hundreds of ERP pixels
 // there, so the photometric weights turn a 1e-4 px error of the sampling position into a flow error above
 // the 1e-3 px tolerance
+// resident blocks per SM (register caps) measured best on B200 for each gather mode
+#ifndef TIF_GATHER_MIN_BLOCKS
+#define TIF_GATHER_MIN_BLOCKS 6
+#endif
+#ifndef TIF_GATHER1_MIN_BLOCKS
+#define TIF_GATHER1_MIN_BLOCKS 5
+#endif
 #ifndef TIF_GATHER2_MIN_BLOCKS
-#define TIF_GATHER2_MIN_BLOCKS 5
+#define TIF_GATHER2_MIN_BLOCKS 4
 #endif
 #define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
 #define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
@@ -546,11 +553,16 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     }
 }
 
+// shared-memory reduction without a return value (and without the compiler's warp-aggregation wrapper)
+__device__ __forceinline__ void red_shared_add(unsigned* addr, unsigned val) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)), "r"(val) : "memory");
+}
+
 // MODE 0: straightforward blend.  MODE 1: normwarp pass A (face-global warp-error sums, order-independent fixed
 // point).  MODE 2: normwarp pass B (weights from the sums of pass A, blend).  One thread per ERP pixel and chunk
 // of images; a warp owns an 8 x 4 pixel tile.
 template <int MODE>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS, MODE == 2 ? TIF_GATHER2_MIN_BLOCKS : 6)
+__global__ void __launch_bounds__(TIF_STITCH_THREADS, MODE == 2 ? TIF_GATHER2_MIN_BLOCKS : (MODE == 1 ? TIF_GATHER1_MIN_BLOCKS : TIF_GATHER_MIN_BLOCKS))
 k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
          const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
@@ -625,45 +637,57 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         const int f = (int)TIF_E_FACE(e);
         const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
         const float mult = (float)TIF_E_MULT(e);
+        // all records of the chunk are requested before any is used (one or two adjacent sectors)
+        float2 disp[TIF_BATCH_CHUNK];
+        uint2 rgb[TIF_BATCH_CHUNK];
+#pragma unroll
+        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+            disp[bb] = make_float2(0.0f, 0.0f);
+            rgb[bb] = make_uint2(0u, 0u);
+            if (has && b0 + bb < batch) {
+                if (MODE == 0) {
+                    disp[bb] = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
+                } else {
+                    const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
+                    disp[bb] = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
+                    rgb[bb] = make_uint2(rec.z, rec.w);
+                }
+            }
+        }
+        // MODE 1: neighbouring pixels almost always see the same face at the same k; then the warp reduces its
+        // contribution first and issues one shared-memory reduction, otherwise one per lane
+        int f0 = 0;
+        bool uniform = false;
+        if (MODE == 1) {
+            f0 = __shfl_sync(0xffffffffu, f, 0);
+            uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
+        }
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
             const int b = b0 + bb;
             if (b >= batch) break;
-            float fu = 0.0f, fv = 0.0f, dsum = 0.0f;
-            if (has) {
-                float2 d;
-                uint32_t plo = 0u, phi = 0u;
-                if (MODE == 0) {
-                    d = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
-                } else {
-                    const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
-                    d = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
-                    plo = rec.z;
-                    phi = rec.w;
-                }
-                fu = d.x + sn.x;                 // end point minus this ERP pixel, the short way round
-                fv = d.y + sn.y;
-                if (fu > half_w) fu -= wf;
-                else if (fu < -half_w) fu += wf;
-                bool x_ok = true;
-                if (wrap_around) {
-                    // the reference samples at c + fu after its seam fix (:350-361): outside [0, W-1] reads 255
-                    const float tx = (float)c + fu;
-                    x_ok = (tx >= 0.0f) & (tx <= wf - 1.0f);
-                } else {
-                    // the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
-                    fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
-                }
-                if (MODE != 0) {
-                    float t0 = 255.0f, t1 = 255.0f, t2 = 255.0f;
-                    if (x_ok) {
-                        const uint32_t q0 = plo & 0x1fffffu, q1 = (plo >> 21) | ((phi & 0x3ffu) << 11), q2 = phi >> 10;
-                        t0 = (__uint_as_float(0x4B000000u | q0) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                        t1 = (__uint_as_float(0x4B000000u | q1) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                        t2 = (__uint_as_float(0x4B000000u | q2) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                    }
-                    dsum = fabsf(t0 - sp[bb][0]) + fabsf(t1 - sp[bb][1]) + fabsf(t2 - sp[bb][2]);
-                }
+            float fu = disp[bb].x + sn.x;        // end point minus this ERP pixel, the short way round
+            const float fv = disp[bb].y + sn.y;
+            if (fu > half_w) fu -= wf;
+            else if (fu < -half_w) fu += wf;
+            bool x_ok = true;
+            if (wrap_around) {
+                // the reference samples at c + fu after its seam fix (:350-361): outside [0, W-1] reads 255
+                const float tx = (float)c + fu;
+                x_ok = (tx >= 0.0f) & (tx <= wf - 1.0f);
+            } else {
+                // the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
+                fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
+            }
+            float dsum = 0.0f;
+            if (MODE != 0) {
+                const uint32_t plo = rgb[bb].x, phi = rgb[bb].y;
+                const uint32_t q0 = plo & 0x1fffffu, q1 = (plo >> 21) | ((phi & 0x3ffu) << 11), q2 = phi >> 10;
+                float t0 = (__uint_as_float(0x4B000000u | q0) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                float t1 = (__uint_as_float(0x4B000000u | q1) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                float t2 = (__uint_as_float(0x4B000000u | q2) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
+                if (!x_ok) t0 = t1 = t2 = 255.0f;
+                dsum = fabsf(t0 - sp[bb][0]) + fabsf(t1 - sp[bb][1]) + fabsf(t2 - sp[bb][2]);
             }
             if (MODE == 0) {
                 if (has) {
@@ -672,22 +696,18 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                     acc_w[bb] += 1.0f;
                 }
             } else if (MODE == 1) {
-                // face-global sum of |diff| (x multiplicity) as order-independent fixed point.  Neighbouring
-                // pixels almost always see the same face at the same k: reduce across the warp first and issue
-                // one shared-memory atomic; otherwise one per lane.
+                // face-global sum of |diff| (x multiplicity) as order-independent fixed point
                 const unsigned fixed = has ? (unsigned)(dsum * mult * TIF_NW_FIXED_SCALE + 0.5f) : 0u;
-                const int f0 = __shfl_sync(0xffffffffu, f, 0);
-                const bool uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
                 if (uniform) {
                     const unsigned total = __reduce_add_sync(0xffffffffu, fixed);    // <= 32 x 765 x 7 x 1024
-                    if ((threadIdx.x & 31) == 0) atomicAdd(&sh_sum[bb * n_faces + f0], total);
+                    if ((threadIdx.x & 31) == 0) red_shared_add(&sh_sum[bb * n_faces + f0], total);
                 } else if (has) {
-                    atomicAdd(&sh_sum[bb * n_faces + f], fixed);
+                    red_shared_add(&sh_sum[bb * n_faces + f], fixed);
                 }
             } else {
                 if (has) {
                     // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
-                    const float w = expf(-dsum * sh_inv_mean[bb * n_faces + f]);
+                    const float w = __expf(-dsum * sh_inv_mean[bb * n_faces + f]);
                     acc_u[bb] = fmaf(fu, w, acc_u[bb]);
                     acc_v[bb] = fmaf(fv, w, acc_v[bb]);
                     acc_w[bb] += w;
