@@ -518,9 +518,9 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
         // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
         // periodic (the seam conventions only move the end point by whole image widths), the gap (W-1, W) and
         // anything outside [0, H-1] vertically reads 255 outright
-        xi -= erp_w * (int)floorf((float)xi / (float)erp_w);        // into [0, W)
+        // own position in [-0.5, W - 0.5) plus a displacement of at most half a turn: one fold brings x into [0, W)
         if (xi >= erp_w) xi -= erp_w;
-        if (xi < 0) xi += erp_w;
+        else if (xi < 0) xi += erp_w;
         float t0, t1, t2;
         const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx == 0.0f));
         const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy == 0.0f));
@@ -545,11 +545,12 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
             t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
             t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
         }
-        const unsigned long long q0 = __float2uint_rn(t0 * TIF_RGB_FIX), q1 = __float2uint_rn(t1 * TIF_RGB_FIX),
-                                 q2 = __float2uint_rn(t2 * TIF_RGB_FIX);
-        const unsigned long long packed = q0 | (q1 << 21) | (q2 << 42);
+        // 21-bit fixed point (x 8192, round to nearest) through the 2^23 mantissa trick: no XU conversions
+        const uint32_t q0 = __float_as_uint(fmaf(t0, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
+        const uint32_t q1 = __float_as_uint(fmaf(t1, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
+        const uint32_t q2 = __float_as_uint(fmaf(t2, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
         reinterpret_cast<uint4*>(records)[rec0 + bb] =
-            make_uint4(__float_as_uint(disp_x), __float_as_uint(disp_y), (unsigned)packed, (unsigned)(packed >> 32));
+            make_uint4(__float_as_uint(disp_x), __float_as_uint(disp_y), q0 | (q1 << 21), (q1 >> 11) | (q2 << 10));
     }
 }
 
