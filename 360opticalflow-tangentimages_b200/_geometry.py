@@ -198,6 +198,7 @@ class HostGeometry:
             F.sin_phi0, F.cos_phi0 = np.sin(phi_0), np.cos(phi_0)
             for k in range(3):
                 F.tri[k][0], F.tri[k][1] = tri[k, 0], tri[k, 1]
+            F.n_vertices, F.n_inner = 3, 0
             F.xmin, F.xmax, F.ymin, F.ymax = xmin, xmax, ymin, ymax
             F.g2p_x = (wt - 1.0) / (xmax - xmin + 0.0 * 2.0)           # gnomonic_projection.py:141
             F.g2p_y = (ht - 1.0) / (ymax - ymin + 0.0 * 2.0)           # :145
@@ -226,15 +227,113 @@ class HostGeometry:
         return t
 
 
+CUBEMAP_TANGENT_POINTS = ((np.pi / 2.0, 0.0), (-np.pi / 2.0, 0.0), (0.0, -np.pi / 2.0), (0.0, np.pi / 2.0),
+                          (0.0, 0.0), (-np.pi, 0.0))          # +x, -x, +y, -y, +z, -z (projection_cubemap.py:33-40)
+
+
+def cubemap_face_erp_range(padding_size=0.0):
+    """Per face [[theta, phi] x TL, TR, BR, BL] of the padded square in the ERP image
+    (src/projection_cubemap.py:86-118)."""
+    pbc = 1.0 + padding_size
+    out = np.zeros((6, 4, 2), dtype=float)
+    for index, (theta_0, phi_0) in enumerate(CUBEMAP_TANGENT_POINTS):
+        if index in (0, 1, 4, 5):
+            theta_min, _ = gp.reverse_gnomonic_projection(-pbc, 0, theta_0, phi_0)
+            theta_max, _ = gp.reverse_gnomonic_projection(pbc, 0, theta_0, phi_0)
+            _, phi_max = gp.reverse_gnomonic_projection(0, pbc, theta_0, phi_0)
+            _, phi_min = gp.reverse_gnomonic_projection(0, -pbc, theta_0, phi_0)
+        else:
+            _, phi_ = gp.reverse_gnomonic_projection(-pbc, pbc, theta_0, phi_0)
+            theta_min, theta_max = -np.pi, np.pi
+            phi_max, phi_min = (phi_, -np.pi / 2) if index == 2 else (np.pi / 2, phi_)
+        out[index] = [[theta_min, phi_max], [theta_max, phi_max], [theta_max, phi_min], [theta_min, phi_min]]
+    return out
+
+
+def cubemap_erp_bounding_box(face_range, erp_height):
+    """Integer ERP bounding box of a cubemap face, src/projection_cubemap.py:202-236 (face_meshgrid), with its
+    special cases at the image borders (including the plain `if` on the last row test)."""
+    face_range = np.asarray(face_range)
+    theta_min, theta_max = face_range[:, 0].min(), face_range[:, 0].max()
+    phi_min, phi_max = face_range[:, 1].min(), face_range[:, 1].max()
+    x_min, y_max = sc.sph2erp(theta_min, phi_min, erp_height, False)
+    x_max, y_min = sc.sph2erp(theta_max, phi_max, erp_height, False)
+    x_min = 0 if theta_min == -np.pi else (int(x_min) if int(x_min) > 0 else int(x_min - 0.5))
+    x_max = erp_height * 2 - 1 if theta_max == np.pi else (int(x_max + 0.5) if int(x_max) > 0 else int(x_max))
+    y_min = 0 if phi_max == np.pi * 0.5 else (int(y_min) if int(y_min) >= 0 else int(y_min - 0.5))
+    if phi_min == -np.pi * 0.5:
+        y_max = erp_height - 1
+    y_max = int(y_max + 0.5) if int(y_max) > 0 else int(y_max)
+    return x_min, x_max, y_min, y_max
+
+
+class CubemapGeometry:
+    """Face structs + tables of the 6-face cubemap stage (src/projection_cubemap.py) for one (padding, H, S)."""
+
+    def __init__(self, padding_size, erp_height, face_size):
+        self.level, self.kind = 0, _lib.PLAN_CUBEMAP
+        self.padding_size = float(padding_size)
+        self.erp_h, self.erp_w = int(erp_height), 2 * int(erp_height)
+        self.tangent_w = self.tangent_h = int(face_size)
+        n = self.n_faces = 6
+        h, w, s = self.erp_h, self.erp_w, self.tangent_w
+        pbc = 1.0 + self.padding_size
+        self.faces = (_lib.TifFace * n)()
+        self.face_heights = [s] * n
+        cols = np.arange(w, dtype=np.float64)
+        rows = np.arange(h, dtype=np.float64)
+        theta = cols * (2 * np.pi / w) + np.pi / w - np.pi
+        phi = -(rows * (np.pi / h) + np.pi / h * 0.5) + 0.5 * np.pi
+        theta = np.where(theta == np.pi, -np.pi, theta)
+        phi = np.where(phi == -0.5 * np.pi, 0.5 * np.pi, phi)
+        self.row_sincos = np.ascontiguousarray(np.stack((np.sin(phi), np.cos(phi)), axis=1))
+        self.col_sincos = np.zeros((n, w, 2), dtype=np.float64)
+        self.gnom_x = np.tile(np.linspace(-pbc, pbc, s), (n, 1))                 # projection_cubemap.py:160
+        self.gnom_y = np.tile(np.linspace(pbc, -pbc, s), n)                      # :161
+        ranges = cubemap_face_erp_range(self.padding_size)
+        square = [[-pbc, pbc], [pbc, pbc], [pbc, -pbc], [-pbc, -pbc]]             # :294-295
+        unit = [[-1, 1], [1, 1], [1, -1], [-1, -1]]                                # projection.py:90-91 (pbc = 1)
+        for f, (theta_0, phi_0) in enumerate(CUBEMAP_TANGENT_POINTS):
+            F = self.faces[f]
+            F.theta0, F.phi0 = theta_0, phi_0
+            F.sin_phi0, F.cos_phi0 = np.sin(phi_0), np.cos(phi_0)
+            for k in range(4):
+                F.tri[k][0], F.tri[k][1] = square[k]
+                F.inner[k][0], F.inner[k][1] = unit[k]
+            F.n_vertices, F.n_inner = 4, 4
+            F.xmin, F.xmax, F.ymin, F.ymax = -pbc, pbc, -pbc, pbc
+            F.g2p_x = (s - 1.0) / (pbc - (-pbc) + 0.0 * 2.0)
+            F.g2p_y = (s - 1.0) / (pbc - (-pbc) + 0.0 * 2.0)
+            F.p2g_x = (s - 1.0) / (abs(pbc - (-pbc)) + 0.0 * 2.0)
+            F.p2g_y = (s - 1.0) / (abs(pbc - (-pbc)) + 0.0 * 2.0)
+            F.eps_stitch = 1e-4                     # default eps of inside_polygon_2d (polygon.py:59)
+            F.eps_image = 1e-4
+            F.eps_inner = 1e-7                      # projection.py:92
+            x0, x1, y0, y1 = cubemap_erp_bounding_box(ranges[f], h)
+            F.col_start, F.col_stop, F.row_start, F.row_stop = x0, x1, y0, y1
+            F.tangent_h = s
+            F.pix_offset = f * s * s
+            delta = theta - theta_0
+            self.col_sincos[f, :, 0] = np.sin(delta)
+            self.col_sincos[f, :, 1] = np.cos(delta)
+        self.tangent_pixels = n * s * s
+
+    tables = HostGeometry.tables
+
+
 class Plan:
     """Device-resident geometry plan (wraps TifPlan*)."""
 
-    def __init__(self, padding_size, erp_height, tangent_width, device, level=0):
+    def __init__(self, padding_size, erp_height, tangent_width, device, level=0, kind=_lib.PLAN_ICOSAHEDRON):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.TifError("no CUDA device: the tangent-image hot path has no CPU fallback")
         self.device = torch.device(device)
-        self.host = HostGeometry(padding_size, erp_height, tangent_width, level)
+        self.kind = int(kind)
+        if kind == _lib.PLAN_CUBEMAP:
+            self.host = CubemapGeometry(padding_size, erp_height, tangent_width)
+        else:
+            self.host = HostGeometry(padding_size, erp_height, tangent_width, level)
         self.level = int(level)
         self.face_heights = list(self.host.face_heights)
         self.face_offsets = [int(self.host.faces[f].pix_offset) for f in range(self.host.n_faces)]
@@ -242,7 +341,7 @@ class Plan:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             status = self.lib.tif_plan_create(self.host.faces, self.host.n_faces, self.host.erp_h, self.host.erp_w,
-                                              self.host.tangent_w, C.byref(self.host.tables()), stream,
+                                              self.host.tangent_w, C.byref(self.host.tables()), self.kind, stream,
                                               C.byref(handle))
         _lib.check(status, "tif_plan_create")
         self.handle = handle
@@ -290,7 +389,7 @@ _plans = {}
 _plans_lock = threading.Lock()
 
 
-def get_plan(padding_size, erp_height, tangent_width, device=None, level=0):
+def get_plan(padding_size, erp_height, tangent_width, device=None, level=0, kind=_lib.PLAN_ICOSAHEDRON):
     """Cached plan for a configuration on a device (default: current CUDA device)."""
     if device is None:
         if not torch.cuda.is_available():
@@ -299,11 +398,11 @@ def get_plan(padding_size, erp_height, tangent_width, device=None, level=0):
     device = torch.device(device)
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (float(padding_size), int(erp_height), int(tangent_width), device.index, int(level))
+    key = (float(padding_size), int(erp_height), int(tangent_width), device.index, int(level), int(kind))
     with _plans_lock:
         plan = _plans.get(key)
         if plan is None:
-            plan = Plan(padding_size, erp_height, tangent_width, device, level)
+            plan = Plan(padding_size, erp_height, tangent_width, device, level, kind)
             _plans[key] = plan
     return plan
 

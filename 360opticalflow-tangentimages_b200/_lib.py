@@ -10,9 +10,13 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
 
 TIF_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 BLEND_STRAIGHTFORWARD = 0
 BLEND_NORMWARP = 1
+BLEND_CUBEMAP_INSIDE = 2
+BLEND_CUBEMAP_WARP_ERROR = 3
+PLAN_ICOSAHEDRON = 0
+PLAN_CUBEMAP = 1
 WARP_WRAP = 0
 WARP_CONSTANT255 = 1
 DTYPE_F32 = 0
@@ -25,14 +29,15 @@ class TifFace(C.Structure):
     _fields_ = [
         ("theta0", C.c_double), ("phi0", C.c_double),
         ("sin_phi0", C.c_double), ("cos_phi0", C.c_double),
-        ("tri", (C.c_double * 2) * 3),
+        ("tri", (C.c_double * 2) * 4), ("inner", (C.c_double * 2) * 4),
         ("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
         ("g2p_x", C.c_double), ("g2p_y", C.c_double),
         ("p2g_x", C.c_double), ("p2g_y", C.c_double),
-        ("eps_stitch", C.c_double), ("eps_image", C.c_double),
+        ("eps_stitch", C.c_double), ("eps_image", C.c_double), ("eps_inner", C.c_double),
         ("col_start", C.c_int32), ("col_stop", C.c_int32),
         ("row_start", C.c_int32), ("row_stop", C.c_int32),
         ("tangent_h", C.c_int32), ("pix_offset", C.c_int32),
+        ("n_vertices", C.c_int32), ("n_inner", C.c_int32),
     ]
 
 
@@ -59,7 +64,7 @@ SYMBOLS = {
     "tif_status_string": (C.c_char_p, [C.c_int]),
     "tif_last_error": (C.c_char_p, []),
     "tif_plan_create": (C.c_int, [C.POINTER(TifFace), C.c_int, C.c_int, C.c_int, C.c_int,
-                                  C.POINTER(TifPlanTables), _VP, C.POINTER(_VP)]),
+                                  C.POINTER(TifPlanTables), C.c_int, _VP, C.POINTER(_VP)]),
     "tif_plan_destroy": (C.c_int, [_VP]),
     "tif_plan_info": (C.c_int, [_VP, C.POINTER(TifPlanInfo)]),
     "tif_plan_export_stage1": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),

@@ -68,10 +68,10 @@ def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out,
     if out.dtype != torch.float32 or tuple(out.shape) != (batch, p.erp_h, p.erp_w, 2) or not out.is_contiguous():
         raise ValueError("ico2erp_flow output must be contiguous float32 [B,%d,%d,2]" % (p.erp_h, p.erp_w))
     src_ptr = tar_ptr = None
-    if blend == _lib.BLEND_NORMWARP:
+    if blend in (_lib.BLEND_NORMWARP, _lib.BLEND_CUBEMAP_WARP_ERROR):
         for name, img in (("erp_src", erp_src), ("erp_tar", erp_tar)):
             if img is None or img.dtype != torch.uint8 or tuple(img.shape) != (batch, p.erp_h, p.erp_w, 3) or not img.is_contiguous():
-                raise ValueError("normwarp needs contiguous uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
+                raise ValueError("this blend needs contiguous uint8 %s [B,%d,%d,3]" % (name, p.erp_h, p.erp_w))
         src_ptr, tar_ptr = erp_src.data_ptr(), erp_tar.data_ptr()
     need = int(p.lib.tif_ico2erp_scratch_bytes(p.handle, batch, blend))
     if scratch is None:
@@ -90,9 +90,9 @@ def _ico2erp_flow(tangent_flow, erp_src, erp_tar, plan, blend, wrap_around):
     p = _registry[plan]
     _need_cuda(tangent_flow, erp_src, erp_tar)
     tangent_flow = tangent_flow.contiguous()
-    if blend == _lib.BLEND_NORMWARP:
+    if blend in (_lib.BLEND_NORMWARP, _lib.BLEND_CUBEMAP_WARP_ERROR):
         if erp_src is None or erp_tar is None:
-            raise ValueError("normwarp needs erp_src and erp_tar")
+            raise ValueError("this blend needs erp_src and erp_tar")
         erp_src, erp_tar = erp_src.contiguous(), erp_tar.contiguous()
     out = torch.empty((tangent_flow.shape[0], p.erp_h, p.erp_w, 2), dtype=torch.float32, device=tangent_flow.device)
     return ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out)

@@ -32,6 +32,7 @@
 
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;
+    int kind;                      // TIF_PLAN_ICOSAHEDRON | TIF_PLAN_CUBEMAP
     int64_t tangent_pixels;        // P
     int max_faces_per_pixel;       // K
     int64_t accepted_unique;

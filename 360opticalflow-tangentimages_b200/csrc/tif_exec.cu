@@ -388,12 +388,16 @@ __device__ __noinline__ void lift_precise(double gx0, double gy0, double s0, dou
 #ifndef TIF_LIFT_MIN_BLOCKS
 #define TIF_LIFT_MIN_BLOCKS 4
 #endif
-template <bool NW>
+// SAMPLE 0: displacement only.  SAMPLE 1: + float bilinear sample of the target image (normwarp: the reference
+// converts the images to float64 first).  SAMPLE 2: + the sample rounded half-up to uint8 (cubemap stage: its
+// images stay uint8, so scipy rounds every sample, projection.py:103-104).
+template <int SAMPLE>
 __global__ void __launch_bounds__(256, TIF_LIFT_MIN_BLOCKS)
 k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
        void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch) {
+    constexpr bool NW = SAMPLE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
@@ -545,6 +549,11 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
             t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
             t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
         }
+        if (SAMPLE == 2) {          // scipy uint8 output: trunc(t + 0.5)
+            t0 = floorf(t0 + 0.5f);
+            t1 = floorf(t1 + 0.5f);
+            t2 = floorf(t2 + 0.5f);
+        }
         // 21-bit fixed point (x 8192, round to nearest) through the 2^23 mantissa trick: no XU conversions
         const uint32_t q0 = __float_as_uint(fmaf(t0, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
         const uint32_t q1 = __float_as_uint(fmaf(t1, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
@@ -559,11 +568,13 @@ __device__ __forceinline__ void red_shared_add(unsigned* addr, unsigned val) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)), "r"(val) : "memory");
 }
 
+// MODE 3 / 4: cubemap2erp_flow weights (projection.py:64-117): 1 inside the unpadded square else 0 / 0.95 over the
+// L2 norm of the per-channel warp error; no face-global mean, a single pass.
 // MODE 0: straightforward blend.  MODE 1: normwarp pass A (face-global warp-error sums, order-independent fixed
 // point).  MODE 2: normwarp pass B (weights from the sums of pass A, blend).  One thread per ERP pixel and chunk
 // of images; a warp owns an 8 x 4 pixel tile.
 template <int MODE>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS, MODE == 2 ? TIF_GATHER2_MIN_BLOCKS : (MODE == 1 ? TIF_GATHER1_MIN_BLOCKS : TIF_GATHER_MIN_BLOCKS))
+__global__ void __launch_bounds__(TIF_STITCH_THREADS, (MODE == 2 || MODE == 4) ? TIF_GATHER2_MIN_BLOCKS : (MODE == 1 ? TIF_GATHER1_MIN_BLOCKS : TIF_GATHER_MIN_BLOCKS))
 k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
          const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
@@ -606,7 +617,8 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         sp[bb][0] = sp[bb][1] = sp[bb][2] = 0.0f;
     }
     const unsigned image_bytes = (unsigned)n_pix * 3u;
-    if (MODE != 0 && live) {
+    constexpr bool USES_IMAGES = (MODE == 1 || MODE == 2 || MODE == 4);
+    if (USES_IMAGES && live) {
 #pragma unroll
         for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
             if (b0 + bb < batch) {
@@ -646,7 +658,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             disp[bb] = make_float2(0.0f, 0.0f);
             rgb[bb] = make_uint2(0u, 0u);
             if (has && b0 + bb < batch) {
-                if (MODE == 0) {
+                if (!USES_IMAGES) {
                     disp[bb] = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
                 } else {
                     const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
@@ -680,15 +692,17 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
                 fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
             }
-            float dsum = 0.0f;
-            if (MODE != 0) {
+            float dsum = 0.0f, dnorm2 = 0.0f;
+            if (USES_IMAGES) {
                 const uint32_t plo = rgb[bb].x, phi = rgb[bb].y;
                 const uint32_t q0 = plo & 0x1fffffu, q1 = (plo >> 21) | ((phi & 0x3ffu) << 11), q2 = phi >> 10;
                 float t0 = (__uint_as_float(0x4B000000u | q0) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
                 float t1 = (__uint_as_float(0x4B000000u | q1) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
                 float t2 = (__uint_as_float(0x4B000000u | q2) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
                 if (!x_ok) t0 = t1 = t2 = 255.0f;
-                dsum = fabsf(t0 - sp[bb][0]) + fabsf(t1 - sp[bb][1]) + fabsf(t2 - sp[bb][2]);
+                const float d0 = t0 - sp[bb][0], d1 = t1 - sp[bb][1], d2 = t2 - sp[bb][2];
+                dsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+                dnorm2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
             }
             if (MODE == 0) {
                 if (has) {
@@ -705,10 +719,18 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 } else if (has) {
                     red_shared_add(&sh_sum[bb * n_faces + f], fixed);
                 }
-            } else {
+            } else if (MODE == 2) {
                 if (has) {
                     // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
                     const float w = __expf(-dsum * sh_inv_mean[bb * n_faces + f]);
+                    acc_u[bb] = fmaf(fu, w, acc_u[bb]);
+                    acc_v[bb] = fmaf(fv, w, acc_v[bb]);
+                    acc_w[bb] += w;
+                }
+            } else {
+                if (has) {
+                    // MODE 3: the plan's inner-square flag (projection.py:87-93); MODE 4: 0.95 / ||diff||_2 (:109-113)
+                    const float w = (MODE == 3) ? mult : (dnorm2 == 0.0f ? 1.0f : 0.95f * rsqrtf(dnorm2));
                     acc_u[bb] = fmaf(fu, w, acc_u[bb]);
                     acc_v[bb] = fmaf(fv, w, acc_v[bb]);
                     acc_w[bb] += w;
@@ -757,7 +779,7 @@ static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
 
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
-    const size_t rec = blend == TIF_BLEND_NORMWARP ? sizeof(uint4) : sizeof(float2);
+    const size_t rec = (blend == TIF_BLEND_NORMWARP || blend == TIF_BLEND_CUBEMAP_WARP_ERROR) ? sizeof(uint4) : sizeof(float2);
     const size_t padded = (size_t)(batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK * TIF_BATCH_CHUNK;      // whole chunks
     return (int64_t)(nw_sums_bytes(plan, batch) + padded * (size_t)plan->tangent_pixels * rec);
 }
@@ -769,12 +791,13 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         tif_set_error("tif_ico2erp_flow_f32: invalid argument (tangent_flow, erp_flow and scratch are required)");
         return TIF_ERR_INVALID_ARG;
     }
-    if (blend != TIF_BLEND_STRAIGHTFORWARD && blend != TIF_BLEND_NORMWARP) {
+    if (blend < TIF_BLEND_STRAIGHTFORWARD || blend > TIF_BLEND_CUBEMAP_WARP_ERROR) {
         tif_set_error("tif_ico2erp_flow_f32: unknown blend %d", blend);
         return TIF_ERR_INVALID_ARG;
     }
-    if (blend == TIF_BLEND_NORMWARP && (!erp_src || !erp_tar)) {
-        tif_set_error("tif_ico2erp_flow_f32: normwarp needs erp_src and erp_tar");
+    const bool uses_images = blend == TIF_BLEND_NORMWARP || blend == TIF_BLEND_CUBEMAP_WARP_ERROR;
+    if (uses_images && (!erp_src || !erp_tar)) {
+        tif_set_error("tif_ico2erp_flow_f32: this blend needs erp_src and erp_tar");
         return TIF_ERR_INVALID_ARG;
     }
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -792,18 +815,30 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
         erp_src, nw_sums, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
-    if (blend == TIF_BLEND_STRAIGHTFORWARD) {
+    if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
         if (!skip_lift)
-            k_lift<false><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<0><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                                  n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
                                                                  records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
-        if (pass_mask & 3) k_gather<0><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        if (pass_mask & 3) {
+            if (blend == TIF_BLEND_STRAIGHTFORWARD)
+                k_gather<0><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+            else
+                k_gather<3><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        }
+    } else if (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) {
+        if (!skip_lift)
+            k_lift<2><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+                                                             n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
+                                                             records, h, w, plan->tangent_w, n_tangent, batch);
+        TIF_CUDA_CHECK(cudaGetLastError());
+        if (pass_mask & 3) k_gather<4><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
         if (pass_mask & 1) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (!skip_lift)
-                k_lift<true><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
+                k_lift<1><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
                                                                     plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch);

@@ -56,12 +56,12 @@ extern "C" const char* tif_status_string(int status) {
 // ------------------------------------------------------------------------------------------------
 // point-in-polygon, polygon.py:59-118 with on_line=True (ray cast, inclusive y range, eps-wide edges)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool pip_accept(double px, double py, const double (*tri)[2], double eps) {
+__device__ __forceinline__ bool pip_accept(double px, double py, const double (*tri)[2], int n, double eps) {
     bool inside = false, online = false;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < n; ++k) {
+        const int k2 = (k + 1 == n) ? 0 : k + 1;
         const double x1 = tri[k][0], y1 = tri[k][1];
-        const double x2 = tri[(k + 1) % 3][0], y2 = tri[(k + 1) % 3][1];
+        const double x2 = tri[k2][0], y2 = tri[k2][1];
         bool t = (py >= fmin(y1, y2)) && (py <= fmax(y1, y2)) && (px <= fmax(x1, x2));
         double ix;
         if (fabs(y1 - y2) <= eps) {
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool pip_accept(double px, double py, const double (*
 __global__ void __launch_bounds__(256)
 k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row_face,
               const double* __restrict__ gnom_x, const double* __restrict__ gnom_y,
-              int erp_h, int erp_w, int tangent_w, int64_t n_pix,
+              int erp_h, int erp_w, int tangent_w, int64_t n_pix, int kind,
               uint32_t* __restrict__ s1_base, double2* __restrict__ s1_frac64,
               double* __restrict__ s1_ex, double* __restrict__ s1_ey) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,6 +107,7 @@ k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row
         phi = F.phi0;
         theta = F.theta0;
     }
+    const double theta_raw = theta, phi_raw = phi;
     // sph2erp(sph_modulo=True), spherical_coordinates.py:59-60,122-124
     theta = np_remainder(theta + TIF_PI, 2 * TIF_PI) - TIF_PI;
     phi = -(np_remainder(-phi + 0.5 * TIF_PI, TIF_PI) - 0.5 * TIF_PI);
@@ -115,11 +116,23 @@ k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row
     s1_ex[p] = ex;
     s1_ey[p] = ey;
 
+    // resampling position: the icosahedron stage samples at the pixel-centre coordinates above; the cubemap stage
+    // (projection_cubemap.py:169-178) uses x = (theta+pi)/(2 pi) W, y = (pi/2-phi)/pi H of the continuous theta
+    // with a single fold into the image
+    double rx = ex, ry = ey;
+    if (kind == TIF_PLAN_CUBEMAP) {
+        rx = ((theta_raw + TIF_PI) / (2 * TIF_PI)) * erp_w;
+        ry = (-phi_raw + TIF_PI / 2.0) / TIF_PI * erp_h;
+        if (rx < 0) rx = rx + erp_w;
+        if (rx >= erp_w) rx = rx - erp_w;
+        if (ry < 0) ry = ry + erp_h;
+        if (ry >= erp_h) ry = ry - erp_h;
+    }
     // scipy map_coordinates(order=1, mode='wrap'): period n-1, taps floor(c), floor(c)+1.
     // The base tap is clamped to n-2 (fraction 1.0 when c == n-1 exactly) so both taps are always
     // in range; the product with scipy's zero weight is unchanged.
-    const double cx = scipy_wrap(ex, erp_w);
-    const double cy = scipy_wrap(ey, erp_h);
+    const double cx = scipy_wrap(rx, erp_w);
+    const double cy = scipy_wrap(ry, erp_h);
     double x0 = floor(cx), y0 = floor(cy);
     if (x0 > (double)(erp_w - 2)) x0 = (double)(erp_w - 2);
     if (y0 > (double)(erp_h - 2)) y0 = (double)(erp_h - 2);
@@ -127,7 +140,7 @@ k_plan_stage1(const TifFace* __restrict__ faces, const int32_t* __restrict__ row
     if (y0 < 0.0) y0 = 0.0;
     const double fx = cx - x0, fy = cy - y0;
     uint32_t base = (uint32_t)((int64_t)y0 * erp_w + (int64_t)x0);
-    if (!pip_accept(x, y, F.tri, F.eps_image)) base |= TIF_S1_OUTSIDE;
+    if (!pip_accept(x, y, F.tri, F.n_vertices, F.eps_image)) base |= TIF_S1_OUTSIDE;
     s1_base[p] = base;
     s1_frac64[p] = make_double2(fx, fy);
 }
@@ -149,7 +162,7 @@ __device__ __forceinline__ int wrapped_multiplicity(int start, int stop, int v, 
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp_w, int tangent_w,
+k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp_w, int tangent_w, int kind,
               const double* __restrict__ row_sincos, const double* __restrict__ col_sincos,
               uint8_t* __restrict__ count, uint32_t* __restrict__ entries, int max_k,
               uint8_t* __restrict__ ref_mark, unsigned long long* __restrict__ face_mult_sum,
@@ -180,13 +193,15 @@ k_plan_stage2(const TifFace* __restrict__ faces, int n_faces, int erp_h, int erp
             x = cos_phi * sin_d / cos_c;
             y = (F.cos_phi0 * sin_phi - F.sin_phi0 * cos_phi * cos_d) / cos_c;
         }
-        if (!pip_accept(x, y, F.tri, F.eps_stitch)) continue;
+        if (!pip_accept(x, y, F.tri, F.n_vertices, F.eps_stitch)) continue;
         if (FILL) {
             // gnomonic2pixel, gnomonic_projection.py:141-147 (padding_size 0.0, padded range)
             const double fx = (x - F.xmin + 0.0) * F.g2p_x + 0.5;
             const double fy = -(y - F.ymax - 0.0) * F.g2p_y + 0.5;
             int ix = (int)fx, iy = (int)fy;          // astype(int): truncation toward zero
-            const int m = mr * mc;
+            int m = mr * mc;
+            if (kind == TIF_PLAN_CUBEMAP)       // no face-global mean there: the field carries the inner-square flag
+                m = (F.n_inner > 0 && pip_accept(x, y, F.inner, F.n_inner, F.eps_inner)) ? 1 : 0;
             if (ix < 0 || ix >= tangent_w || iy < 0 || iy >= F.tangent_h || m > 7) {
                 atomicAdd(&status[1], 1);
                 ix = min(max(ix, 0), tangent_w - 1);
@@ -279,12 +294,22 @@ static int cuda_status(cudaError_t e, const char* what) {
 }
 
 extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int erp_w, int tangent_w,
-                               const TifPlanTables* tables, void* stream_v, TifPlan** plan_out) {
+                               const TifPlanTables* tables, int kind, void* stream_v, TifPlan** plan_out) {
     if (!faces || !tables || !plan_out || n_faces <= 0 || n_faces > TIF_MAX_FACES || erp_h < 2 || erp_w < 2 ||
         tangent_w < 2 || tangent_w > TIF_MAX_TANGENT_DIM || !tables->gnom_x || !tables->gnom_y ||
         !tables->row_sincos || !tables->col_sincos) {
         tif_set_error("tif_plan_create: invalid argument");
         return TIF_ERR_INVALID_ARG;
+    }
+    if (kind != TIF_PLAN_ICOSAHEDRON && kind != TIF_PLAN_CUBEMAP) {
+        tif_set_error("tif_plan_create: unknown plan kind %d", kind);
+        return TIF_ERR_INVALID_ARG;
+    }
+    for (int f = 0; f < n_faces; ++f) {
+        if (faces[f].n_vertices < 3 || faces[f].n_vertices > 4 || faces[f].n_inner < 0 || faces[f].n_inner > 4) {
+            tif_set_error("tif_plan_create: face %d has %d vertices / %d inner vertices", f, faces[f].n_vertices, faces[f].n_inner);
+            return TIF_ERR_INVALID_ARG;
+        }
     }
     if ((int64_t)erp_h * erp_w >= (int64_t)1 << 31) {
         tif_set_error("tif_plan_create: ERP larger than 2^31 pixels");
@@ -315,6 +340,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     plan->erp_w = erp_w;
     plan->tangent_w = tangent_w;
     plan->tangent_pixels = n_tangent;
+    plan->kind = kind;
     plan->h_faces = (TifFace*)malloc(sizeof(TifFace) * n_faces);
     memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
 
@@ -367,12 +393,12 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
 
     const int threads = 256;
     k_plan_stage1<<<(unsigned)((n_tangent + threads - 1) / threads), threads, 0, stream>>>(
-        plan->d_faces, plan->d_pix_face, d_gx, d_gy, erp_h, erp_w, tangent_w, n_tangent, plan->d_s1_base,
+        plan->d_faces, plan->d_pix_face, d_gx, d_gy, erp_h, erp_w, tangent_w, n_tangent, kind, plan->d_s1_base,
         plan->d_s1_frac64, plan->d_s1_ex, plan->d_s1_ey);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage1 launch"));
 
     const unsigned blocks2 = (unsigned)((n_erp + threads - 1) / threads);
-    k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
+    k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, d_rows,
                                                          d_cols, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, d_status);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<count> launch"));
     int h_status[2] = {0, 0};
@@ -385,7 +411,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     }
     PLAN_TRY(dev_alloc(&plan->d_s2_entries, (size_t)plan->max_faces_per_pixel * n_erp, plan));
     PLAN_TRY(dev_alloc(&plan->d_s2_snap, (size_t)plan->max_faces_per_pixel * n_erp, plan));
-    k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, d_rows,
+    k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, d_rows,
                                                         d_cols, plan->d_s2_count, plan->d_s2_entries,
                                                         plan->max_faces_per_pixel, d_mark, d_msum, plan->d_s1_ex, plan->d_s1_ey,
                                                         plan->d_s2_snap, d_status);

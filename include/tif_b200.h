@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TIF_ABI_VERSION 2
+#define TIF_ABI_VERSION 3
 #define TIF_MAX_FACES 128      /* 7-bit face id in a membership entry */
 #define TIF_MAX_TANGENT_DIM 2048 /* 11-bit tangent row / column in a membership entry */
 
@@ -52,6 +52,14 @@ typedef enum TifStatus {
 /* face_blending_method of ico2erp_flow (projection_icosahedron.py:251,368-381) */
 #define TIF_BLEND_STRAIGHTFORWARD 0
 #define TIF_BLEND_NORMWARP 1
+/* weights of cubemap2erp_flow (projection_cubemap.py:333-345, projection.py:64-117): 1 inside the unpadded
+ * square / 0 outside, or 0.95 / ||tar(end point) - src||_2 on uint8-rounded samples */
+#define TIF_BLEND_CUBEMAP_INSIDE 2
+#define TIF_BLEND_CUBEMAP_WARP_ERROR 3
+
+/* plan kinds (tif_plan_create flags): which reference stage the face table belongs to */
+#define TIF_PLAN_ICOSAHEDRON 0     /* projection_icosahedron.py: sph2erp pixel centres, triangle faces */
+#define TIF_PLAN_CUBEMAP 1         /* projection_cubemap.py: x = (theta+pi)/(2 pi) W resampling grid, square faces */
 
 /* boundary rule of warp_backward (flow_warp.py:82-86): 3-D input -> scipy 'wrap' (period n-1),
  * 2-D input -> scipy 'constant' with cval 255 */
@@ -70,17 +78,21 @@ typedef enum TifStatus {
 typedef struct TifFace {
     double theta0, phi0;            /* tangent point */
     double sin_phi0, cos_phi0;      /* np.sin / np.cos of phi0 */
-    double tri[3][2];               /* padded triangle, gnomonic (x, y), reference vertex order */
+    double tri[4][2];               /* padded face polygon, gnomonic (x, y), reference vertex order (3 or 4 used) */
+    double inner[4][2];             /* cubemap: the unpadded square of the "straightforward" weights (projection.py:87-93) */
     double xmin, xmax, ymin, ymax;  /* gnomonic bounding box of the padded triangle */
     double g2p_x, g2p_y;            /* (Wt-1)/(xmax-xmin), (Ht-1)/(ymax-ymin): gnomonic2pixel ratios
                                        (gnomonic_projection.py:141,145) */
     double p2g_x, p2g_y;            /* (Wt-1)/|xmax-xmin|, (Ht-1)/|ymax-ymin|: pixel2gnomonic ratios (:188,192) */
     double eps_stitch;              /* |xmax-xmin| / (2*Wt)   (projection_icosahedron.py:296) */
     double eps_image;               /* (xmax-xmin) / Wt       (:215, full_face_image=False) */
+    double eps_inner;               /* cubemap: 1e-7 (projection.py:92) */
     int32_t col_start, col_stop;    /* integer ERP bounding box (:299-305); may leave the image */
     int32_t row_start, row_stop;
     int32_t tangent_h;              /* Ht of this face */
     int32_t pix_offset;             /* first pixel of this face in the tangent stack */
+    int32_t n_vertices;             /* 3 (icosahedron) or 4 (cubemap) */
+    int32_t n_inner;                /* 0, or 4 for the cubemap's inner square */
 } TifFace;
 
 /*
@@ -121,7 +133,7 @@ const char* tif_last_error(void);
  * and ico2erp_flow (:282-329), which the reference recomputes for every face of every call.
  */
 int tif_plan_create(const TifFace* faces /*host*/, int n_faces, int erp_h, int erp_w, int tangent_w,
-                    const TifPlanTables* tables /*host*/, void* stream, TifPlan** plan_out);
+                    const TifPlanTables* tables /*host*/, int kind /*TIF_PLAN_*/, void* stream, TifPlan** plan_out);
 int tif_plan_destroy(TifPlan* plan);
 int tif_plan_info(const TifPlan* plan, TifPlanInfo* info /*host*/);
 
@@ -129,7 +141,8 @@ int tif_plan_info(const TifPlan* plan, TifPlanInfo* info /*host*/);
  * stage 1: float ERP sample coordinate of each tangent pixel after sph2erp(modulo) (:225), and the
  *          inside-padded-triangle flag used by full_face_image=False (:214-218).
  * stage 2: per ERP pixel the number of accepting faces and, plane k, the packed entry
- *          face<<25 | multiplicity<<22 | iy<<11 | ix  (faces in ascending order). */
+ *          face<<25 | multiplicity<<22 | iy<<11 | ix  (faces in ascending order).  In a cubemap plan the 3-bit
+ *          field holds the inside-the-unpadded-square flag instead of the multiplicity. */
 int tif_plan_export_stage1(const TifPlan* plan, double* erp_x /*[P]*/, double* erp_y /*[P]*/,
                            uint8_t* inside /*[P]*/, void* stream);
 int tif_plan_export_stage2(const TifPlan* plan, uint8_t* count /*[H*W]*/, uint32_t* entries /*[K][H*W]*/,

@@ -178,15 +178,63 @@ def summary_case(ref, name, erp_h, tangent_w, pad, seed, smooth, u_offset, warp=
     print(name, "written")
 
 
+def cubemap_flows(size, seed):
+    """Smooth per-face flows for the cubemap stage, float32 [S,S,2] x 6."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    flows = []
+    for f in range(6):
+        a, b = rng.uniform(1, 3, 2)
+        u = 3.0 * np.sin(2 * np.pi * (xx / size + f / 6.0)) + a
+        v = 2.0 * np.cos(2 * np.pi * (yy / size - f / 6.0)) - b
+        flows.append(np.stack((u, v), -1).astype(np.float32))
+    return flows
+
+
+def cubemap_case(name, erp_h, pad, seed, smooth, full):
+    """Outputs of the live reference's cubemap stage (projection_cubemap.py): full arrays for small sizes,
+    hashes + strided samples otherwise."""
+    import importlib
+    ref_shim.load_reference()
+    pc = importlib.import_module("projection_cubemap")
+    src, tar = synth.synth_images(erp_h, seed, smooth)
+    faces = pc.erp2cubemap_image(src, pad)
+    size = faces[0].shape[0]
+    assert all(f.dtype == np.float64 and f.shape == (size, size, 3) for f in faces)
+    flows = cubemap_flows(size, seed)
+    out = dict(erp_h=erp_h, pad=pad, seed=seed, smooth=int(smooth), size=size, sha_src=sha(src), sha_tar=sha(tar),
+               sha_flows=sha(np.stack(flows)))
+    stack = np.stack(faces)
+    assert np.array_equal(stack, np.round(stack)) and stack.min() >= 0 and stack.max() <= 255
+    plain = pc.cubemap2erp_flow(flows, None, erp_h, pad, None, None, True)
+    weighted = pc.cubemap2erp_flow(flows, None, erp_h, pad, src, tar, True)
+    if full:
+        out.update(faces=stack.astype(np.uint8), flow_plain=plain, flow_weighted=weighted)
+    else:
+        st = stride_for(erp_h * 2 * erp_h)
+        out.update(faces_sha=sha(stack.astype(np.uint8)), flow_stride=st, flow_plain_samples=plain.reshape(-1, 2)[::st].copy(),
+                   flow_weighted_samples=weighted.reshape(-1, 2)[::st].copy(), flow_plain_sum=plain.reshape(-1, 2).sum(0))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "written")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
+    if "--cubemap-only" in sys.argv:
+        cubemap_case("cubemap_h64_pad04", 64, 0.4, 3, False, True)
+        cubemap_case("cubemap_h96_pad00_smooth", 96, 0.0, 5, True, True)
+        cubemap_case("cubemap_summary_h1024", 1024, 0.4, 0, False, False)
+        return
     face_tables(ref)
     small_case(ref, "small_h64_noise", 64, 32, 0.3, 3, False, 0.0)
     small_case(ref, "small_h80_smooth_seam", 80, 40, 0.3, 5, True, 12.0)
     small_case(ref, "small_h48_pad01", 48, 24, 0.1, 7, False, 0.0)
     summary_case(ref, "summary_h1024_noise", 1024, 480, 0.3, 0, False, 0.0)
     summary_case(ref, "summary_h640_smooth_seam", 640, 480, 0.3, 11, True, 40.0)
+    cubemap_case("cubemap_h64_pad04", 64, 0.4, 3, False, True)
+    cubemap_case("cubemap_h96_pad00_smooth", 96, 0.0, 5, True, True)
+    cubemap_case("cubemap_summary_h1024", 1024, 0.4, 0, False, False)
     if "--large" in sys.argv:
         summary_case(ref, "summary_h1920_noise", 1920, 480, 0.3, 1, False, 0.0)
         summary_case(ref, "summary_h2048_smooth", 2048, 480, 0.3, 2, True, 0.0)

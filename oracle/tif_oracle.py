@@ -629,3 +629,159 @@ def warp_backward(image_target, of_forward):
     else:
         out[:, :] = map_coordinates_order1(image_target, yn, xn, "constant", 255)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cubemap stage -- projection_cubemap.py
+# ------------------------------------------------------------------------------------------------
+
+CUBEMAP_CENTRES = ((PI / 2.0, 0.0), (-PI / 2.0, 0.0), (0.0, -PI / 2.0), (0.0, PI / 2.0), (0.0, 0.0), (-PI, 0.0))
+
+
+def cubemap_face_ranges(padding=0.0):
+    """projection_cubemap.py:86-118: per face [theta_min, theta_max, phi_max, phi_min] of the padded square."""
+    pbc = 1.0 + padding
+    out = []
+    for index, (theta_0, phi_0) in enumerate(CUBEMAP_CENTRES):
+        if index in (0, 1, 4, 5):
+            theta_min, _ = gnomonic_reverse(-pbc, 0, theta_0, phi_0)
+            theta_max, _ = gnomonic_reverse(pbc, 0, theta_0, phi_0)
+            _, phi_max = gnomonic_reverse(0, pbc, theta_0, phi_0)
+            _, phi_min = gnomonic_reverse(0, -pbc, theta_0, phi_0)
+        else:
+            _, phi_ = gnomonic_reverse(-pbc, pbc, theta_0, phi_0)
+            theta_min, theta_max = -PI, PI
+            if index == 2:
+                phi_max, phi_min = phi_, -PI / 2
+            else:
+                phi_max, phi_min = PI / 2, phi_
+        out.append((theta_min, theta_max, phi_max, phi_min))
+    return out
+
+
+def cubemap_erp_bbox(face_range, erp_h):
+    """projection_cubemap.py:190-244 (face_meshgrid): integer (x_min, x_max, y_min, y_max), special-cased at the
+    image borders.  Note the reference's `if` (not `elif`) on the last branch, kept here."""
+    theta_min, theta_max, phi_max, phi_min = face_range
+    x_min, y_max = sph2erp(theta_min, phi_min, erp_h, False)
+    x_max, y_min = sph2erp(theta_max, phi_max, erp_h, False)
+    if theta_min == -PI:
+        x_min = 0
+    elif int(x_min) > 0:
+        x_min = int(x_min)
+    else:
+        x_min = int(x_min - 0.5)
+    if theta_max == PI:
+        x_max = erp_h * 2 - 1
+    elif int(x_max) > 0:
+        x_max = int(x_max + 0.5)
+    else:
+        x_max = int(x_max)
+    if phi_max == PI * 0.5:
+        y_min = 0
+    elif int(y_min) >= 0:
+        y_min = int(y_min)
+    else:
+        y_min = int(y_min - 0.5)
+    if phi_min == -PI * 0.5:
+        y_max = erp_h - 1
+    if int(y_max) > 0:
+        y_max = int(y_max + 0.5)
+    else:
+        y_max = int(y_max)
+    return x_min, x_max, y_min, y_max
+
+
+def erp2cubemap_image(erp_image, padding=0.0, face_size=None):
+    """projection_cubemap.py:127-187: six float64 [S,S,C] faces (uint8 inputs give uint8-rounded values)."""
+    erp_image = np.asarray(erp_image)
+    erp_h, erp_w, nch = erp_image.shape
+    if face_size is None:
+        face_size = int(erp_w / 4.0)
+    pbc = 1.0 + padding
+    out = []
+    for theta_0, phi_0 in CUBEMAP_CENTRES:
+        x, y = np.meshgrid(np.linspace(-pbc, pbc, face_size), np.linspace(pbc, -pbc, face_size))
+        th, ph = gnomonic_reverse(x, y, theta_0, phi_0)
+        ex = ((th + PI) / (2 * PI)) * erp_w
+        ey = (-ph + PI / 2.0) / PI * erp_h
+        ex = np.where(ex < 0, ex + erp_w, ex)
+        ex = np.where(ex >= erp_w, ex - erp_w, ex)
+        ey = np.where(ey < 0, ey + erp_h, ey)
+        ey = np.where(ey >= erp_h, ey - erp_h, ey)
+        face = np.zeros((face_size, face_size, nch), dtype=float)
+        for ch in range(nch):
+            face[:, :, ch] = map_coordinates_order1(erp_image[:, :, ch], ey, ex, "wrap")
+        out.append(face)
+    return out
+
+
+def cubemap2erp_flow(cubemap_flows, erp_h=None, padding=0.0, image_src=None, image_tar=None, return_debug=False):
+    """projection_cubemap.py:246-357 (face_flows_wraparound=None; the `wrap_around` argument of the reference is
+    never read).  Weights: 0.95 / ||tar(end point) - src||_2 when both images are given (projection.py:94-113),
+    else 1 inside the unpadded square [-1,1]^2 and 0 outside (:87-93)."""
+    size = cubemap_flows[0].shape[0]
+    if erp_h is None:
+        erp_h = size * 2.0
+    erp_h = int(erp_h)
+    erp_w = int(erp_h * 2.0)
+    acc_flow = np.zeros((erp_h, erp_w, 2), dtype=np.float64)
+    acc_w = np.zeros((erp_h, erp_w), dtype=np.float64)
+    pbc = 1.0 + padding
+    square = np.array([[-pbc, pbc], [pbc, pbc], [pbc, -pbc], [-pbc, -pbc]])
+    unit = np.array([[-1, 1], [1, 1], [1, -1], [-1, -1]])
+    ranges = cubemap_face_ranges(padding)
+    debug = []
+    for f in range(6):
+        theta_0, phi_0 = CUBEMAP_CENTRES[f]
+        x_min, x_max, y_min, y_max = cubemap_erp_bbox(ranges[f], erp_h)
+        cols = np.remainder(np.linspace(x_min, x_max, x_max - x_min + 1), erp_w)
+        rows = np.remainder(np.linspace(y_min, y_max, y_max - y_min + 1), erp_h)
+        theta, phi = erp2sph_axes(cols, rows, erp_h)
+        gx, gy = gnomonic_forward(theta[None, :], phi[:, None], theta_0, phi_0)
+        acc = inside_polygon(gx, gy, square, 1e-4)
+        rr, cc = np.nonzero(acc)
+        r = rows[rr].astype(np.int64)
+        c = cols[cc].astype(np.int64)
+        gxa, gya = gx[rr, cc], gy[rr, cc]
+        ix = ((gxa + pbc + 0.0) * ((size - 1.0) / (pbc + pbc + 0.0)) + 0.5).astype(np.int64)
+        iy = (-(gya - pbc - 0.0) * ((size - 1.0) / (pbc + pbc + 0.0)) + 0.5).astype(np.int64)
+        flow = np.asarray(cubemap_flows[f])
+        inr = (ix >= 0) & (ix <= size - 1) & (iy >= 0) & (iy <= size - 1)      # mode='constant', cval=0.0
+        u = np.where(inr, flow[np.clip(iy, 0, size - 1), np.clip(ix, 0, size - 1), 0], 0.0)
+        v = np.where(inr, flow[np.clip(iy, 0, size - 1), np.clip(ix, 0, size - 1), 1], 0.0)
+        px = ix + u
+        py = iy + v
+        ratio = (size - 1.0) / (abs(pbc + pbc) + 0.0 * 2.0)
+        tgx = px / ratio + (-pbc) - 0.0
+        tgy = - py / ratio + pbc + 0.0
+        th_t, ph_t = gnomonic_reverse(tgx, tgy, theta_0, phi_0)
+        tx, ty = sph2erp(th_t, ph_t, erp_h, True)
+        fu = tx - cols[cc]
+        fv = ty - rows[rr]
+        if image_src is not None and image_tar is not None:
+            d = np.zeros((fu.shape[0], 3), dtype=np.float64)
+            for ch in range(3):
+                ts = map_coordinates_order1(np.asarray(image_tar)[:, :, ch], ty, tx, "constant", 255)
+                ss = np.asarray(image_src)[r, c, ch]
+                # uint8 images: map_coordinates returns uint8 and the reference stores it into a float array
+                d[:, ch] = np.absolute(ts.astype(np.float64) - ss.astype(np.float64))
+            norm = np.linalg.norm(d, axis=1)
+            w = np.ones(fu.shape[0], dtype=np.float64)
+            nzw = norm != 0.0
+            w[nzw] = 0.95 / norm[nzw]
+        else:
+            w = inside_polygon(gxa, gya, unit, 1e-7).astype(np.float64)
+        acc_flow[r, c, 0] += fu * w
+        acc_flow[r, c, 1] += fv * w
+        acc_w[r, c] += w
+        if return_debug:
+            debug.append({"rows": r, "cols": c, "ix": ix, "iy": iy, "bbox": (x_min, x_max, y_min, y_max),
+                          "inner": inside_polygon(gxa, gya, unit, 1e-7), "th_t": th_t, "tx": tx, "ty": ty})
+    nz = acc_w != 0
+    for ch in range(2):
+        plane = acc_flow[:, :, ch]
+        plane[nz] = plane[nz] / acc_w[nz]
+    if return_debug:
+        return acc_flow, debug
+    return acc_flow

@@ -48,14 +48,14 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layout_and_status_strings(pkg):
     lib = pkg._lib.load()
-    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 2
+    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 3
     sizes = [ctypes.c_int32() for _ in range(3)]
     assert lib.tif_struct_sizes(*[ctypes.byref(s) for s in sizes]) == 0
     assert [s.value for s in sizes] == [ctypes.sizeof(pkg._lib.TifFace), ctypes.sizeof(pkg._lib.TifPlanTables),
                                         ctypes.sizeof(pkg._lib.TifPlanInfo)]
     assert lib.tif_status_string(0) == b"TIF_OK" and lib.tif_status_string(-4) == b"TIF_ERR_RANGE"
     # argument validation happens before any CUDA call
-    assert lib.tif_plan_create(None, 0, 0, 0, 0, None, None, None) == -1
+    assert lib.tif_plan_create(None, 0, 0, 0, 0, None, 0, None, None) == -1
     assert b"invalid argument" in lib.tif_last_error()
 
 
