@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 UNITS = {
     "tif_plan.cu": ["-fmad=false"],
     "tif_exec.cu": [],
+    "tif_rotate.cu": [],
 }
 
 

@@ -76,6 +76,10 @@ SYMBOLS = {
     "tif_warp_backward_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_warp_backward_f32": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_flow_warp_meshgrid": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "tif_rotation_motion_vector_f64": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "tif_flow_cross_covariance_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "tif_flow_cross_covariance": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "tif_flow_rotate_endpoint": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_erp_of_wraparound": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _VP]),
 }
 

@@ -152,6 +152,51 @@ def _erp_of_wraparound_(erp_flow, u_threshold):
     return erp_flow
 
 
+def rotation_motion_vector(rotation, height, width, wraparound, device):
+    """tif_rotation_motion_vector_f64: [H,W,2] float64 CUDA tensor for a 3x3 rotation (host numpy / list)."""
+    import ctypes as C
+    import numpy as np
+    rot = np.ascontiguousarray(np.asarray(rotation, dtype=np.float64).reshape(9))
+    out = torch.empty((int(height), int(width), 2), dtype=torch.float64, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.tif_rotation_motion_vector_f64(rot.ctypes.data_as(C.POINTER(C.c_double)), int(height), int(width),
+                                                      int(bool(wraparound)), out.data_ptr(), _stream()),
+                   "tif_rotation_motion_vector_f64")
+    return out
+
+
+def flow_cross_covariance(flow):
+    """tif_flow_cross_covariance: [B,9] float64 CUDA tensor for a [B,H,W,2] flow."""
+    _need_cuda(flow)
+    if flow.dim() != 4 or flow.shape[-1] != 2:
+        raise ValueError("flow_cross_covariance expects [B,H,W,2]")
+    flow = flow.contiguous()
+    b, h, w, _ = flow.shape
+    lib = _lib.load()
+    out = torch.empty((b, 9), dtype=torch.float64, device=flow.device)
+    scratch = torch.empty(max(int(lib.tif_flow_cross_covariance_scratch_bytes(b, h, w)), 8), dtype=torch.uint8, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(lib.tif_flow_cross_covariance(flow.data_ptr(), _flow_dtype(flow), b, h, w, out.data_ptr(), scratch.data_ptr(),
+                                                 _stream()), "tif_flow_cross_covariance")
+    return out
+
+
+def flow_rotate_endpoint(flow, rotation_field, wraparound):
+    """tif_flow_rotate_endpoint: flow [B,H,W,2] (float32/64), rotation_field [H,W,2] float64 -> like flow."""
+    _need_cuda(flow, rotation_field)
+    flow, rotation_field = flow.contiguous(), rotation_field.contiguous()
+    b, h, w, _ = flow.shape
+    if rotation_field.dtype != torch.float64 or tuple(rotation_field.shape) != (h, w, 2):
+        raise ValueError("rotation_field must be float64 [H,W,2]")
+    out = torch.empty_like(flow)
+    lib = _lib.load()
+    with torch.cuda.device(flow.device):
+        _lib.check(lib.tif_flow_rotate_endpoint(flow.data_ptr(), _flow_dtype(flow), rotation_field.data_ptr(), b, h, w,
+                                                int(bool(wraparound)), out.data_ptr(), _stream()), "tif_flow_rotate_endpoint")
+    return out
+
+
 _libimpl = torch.library.Library("tangentflow", "IMPL", "CUDA")
 _libimpl.impl("erp2ico", _erp2ico)
 _libimpl.impl("ico2erp_flow", _ico2erp_flow)

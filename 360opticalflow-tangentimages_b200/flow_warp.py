@@ -3,9 +3,11 @@
     flow_warp_meshgrid(motion_flow_u, motion_flow_v)   -> [2,H,W]
     warp_backward(image_target, of_forward)            -> image like image_target
 
+    flow2rotation_3d(erp_flow, mask_method="center")   -> 3x3 rotation matrix          (row f2)
+    global_rotation_warping(erp_image, erp_flow, forward_warp=True, rotation_type="3D")  (row f2)
+
 numpy in -> numpy out with the reference's dtypes; torch CUDA tensors with a leading batch axis stay
-on the device.  The rotation-estimation functions of the reference (flow2rotation_*,
-global_rotation_warping) are out of scope.
+on the device.  flow2rotation_2d (the "2D" rotation type, scipy.stats based) is not on the accelerated path.
 """
 import numpy as np
 import torch
@@ -60,3 +62,40 @@ def warp_backward(image_target, of_forward):
     out = _ops.ops.warp_backward(img_dev, torch.from_numpy(flow).to(dev)[None], mode)[0].cpu().numpy()
     out = out.astype(image_target.dtype, copy=False)
     return out if image_target.ndim == 3 else out[:, :, 0]
+
+
+def rotation_from_covariance(h_mat):
+    """R = V U^T from the SVD of the 3x3 cross covariance (src/pointcloud_utils.py:31-32); 9 numbers, on the host."""
+    u, _, vt = np.linalg.svd(np.asarray(h_mat, dtype=np.float64).reshape(3, 3))
+    return np.dot(vt.T, u.T)
+
+
+def flow2rotation_3d(erp_flow, mask_method="center"):
+    """Rotation between two ERP images from their flow (src/flow_warp.py:91-133): cross covariance of the pixel
+    directions and the flow end-point directions over the middle half of the rows (device reduction), then SVD."""
+    if mask_method != "center":
+        raise NotImplementedError("flow2rotation_3d: only mask_method='center' is on the accelerated path")
+    if isinstance(erp_flow, torch.Tensor):
+        h = _ops.flow_cross_covariance(erp_flow if erp_flow.dim() == 4 else erp_flow[None])
+        mats = np.stack([rotation_from_covariance(m) for m in h.cpu().numpy()])
+        return mats if erp_flow.dim() == 4 else mats[0]
+    flow = np.ascontiguousarray(erp_flow)
+    if flow.dtype not in (np.float32, np.float64):
+        flow = flow.astype(np.float64)
+    h = _ops.flow_cross_covariance(torch.from_numpy(flow).to(_device())[None])
+    return rotation_from_covariance(h[0].cpu().numpy())
+
+
+def global_rotation_warping(erp_image, erp_flow, forward_warp=True, rotation_type="3D"):
+    """Rotate the ERP image by the global rotation of the flow (src/flow_warp.py:190-229).  Returns the rotated
+    image and the rotation matrix."""
+    if rotation_type != "3D":
+        raise NotImplementedError("global_rotation_warping: rotation_type %r is not on the accelerated path" % (rotation_type,))
+    rotation_mat = flow2rotation_3d(erp_flow)
+    if not forward_warp:
+        rotation_mat = rotation_mat.T
+    from . import spherical_coordinates as sc
+    erp_image_rot = sc.rotate_erp_array(erp_image, rotation_mat=rotation_mat)
+    if erp_image.dtype == np.uint8:
+        erp_image_rot = erp_image_rot.astype(np.uint8)
+    return erp_image_rot, rotation_mat

@@ -1,9 +1,9 @@
 """Host-side spherical helpers with the reference's names and argument meaning (src/spherical_coordinates.py).
 
 Used on the host for the face table and the per-row / per-column tables of the plan; the per-pixel
-arithmetic of the hot path lives in csrc/tif_plan.cu and csrc/tif_exec.cu.  The rotation helpers of
-the reference (rotate_erp_array, rotation2erp_motion_vector, rot_*) belong to the de-rotation stages
-and are out of scope.
+arithmetic of the hot path lives in csrc/tif_plan.cu and csrc/tif_exec.cu.  The rotation helpers
+(rotate_erp_array, rotation2erp_motion_vector: row f2 of SURVEY.md section 8) run on the device through
+csrc/tif_rotate.cu; rot_sph2mat / rot_mat2sph are 3x3 host conversions.
 """
 import numpy as np
 
@@ -82,3 +82,49 @@ def sph_wraparound(src_theta, tar_theta):
     minus = long_line & (src_theta < 0) & (tar_theta > 0)
     plus = long_line & (src_theta > 0) & (tar_theta < 0)
     return minus, plus
+
+
+def rotation2erp_motion_vector(array_size, rotation_matrix=None, wraparound=False):
+    """ERP flow [H,W,2] float64 of a rigid rotation of the sphere (src/spherical_coordinates.py:185-218); computed
+    per pixel on the device (k_rotation_mv)."""
+    import torch
+    from . import _lib, _ops
+    if not torch.cuda.is_available():
+        raise _lib.TifError("no CUDA device: rotation2erp_motion_vector has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return _ops.rotation_motion_vector(rotation_matrix, array_size[0], array_size[1], wraparound, dev).cpu().numpy()
+
+
+def rotate_erp_array(erp_image, rotation_mat=None):
+    """Rotate an ERP image (src/spherical_coordinates.py:172-182): backward warp by the motion vector of R^T; both
+    steps stay on the device, the float64 flow keeps scipy's uint8 rounding exact."""
+    import torch
+    from . import _lib, _ops
+    if not torch.cuda.is_available():
+        raise _lib.TifError("no CUDA device: rotate_erp_array has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    erp_image = np.asarray(erp_image)
+    h, w = erp_image.shape[:2]
+    flow = _ops.rotation_motion_vector(np.asarray(rotation_mat).T, h, w, False, dev)
+    if erp_image.ndim == 3:
+        mode, img = _lib.WARP_WRAP, erp_image
+    else:
+        mode, img = _lib.WARP_CONSTANT255, erp_image[:, :, None]
+    if img.dtype == np.uint8:
+        img_dev = torch.from_numpy(np.ascontiguousarray(img)).to(dev)[None]
+    else:
+        img_dev = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)[None]
+    out = _ops.ops.warp_backward(img_dev, flow[None], mode)[0].cpu().numpy().astype(erp_image.dtype, copy=False)
+    return out if erp_image.ndim == 3 else out[:, :, 0]
+
+
+def rot_sph2mat(theta, phi, degrees_=True):
+    """src/spherical_coordinates.py:221-224."""
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_euler("xyz", [phi, theta, 0], degrees=degrees_).as_matrix()
+
+
+def rot_mat2sph(rot_mat, degrees_=True):
+    """src/spherical_coordinates.py:227-231."""
+    from scipy.spatial.transform import Rotation
+    return tuple(Rotation.from_matrix(rot_mat).as_euler("xyz", degrees=degrees_)[:2])

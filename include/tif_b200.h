@@ -191,6 +191,27 @@ int tif_warp_backward_f32(const float* image /*[B,H,W,C]*/, const void* flow, in
 int tif_flow_warp_meshgrid(const void* flow_u /*[B,H,W]*/, const void* flow_v /*[B,H,W]*/, int dtype,
                            int batch, int h, int w, void* out /*[B,2,H,W] same dtype*/, void* stream);
 
+/*
+ * Global rotation (row f2 of SURVEY.md section 8): the de-rotation steps either side of the tangent-image path.
+ *
+ * tif_rotation_motion_vector_f64   spherical_coordinates.rotation2erp_motion_vector (spherical_coordinates.py:185-218):
+ *     ERP flow [H,W,2] float64 of a rigid rotation (`rotation` = 9 HOST doubles, row major).  rotate_erp_array
+ *     (:172-182) is this with R^T followed by tif_warp_backward_* with the float64 flow.
+ * tif_flow_cross_covariance        the 3x3 matrix S^T T of flow_warp.flow2rotation_3d (flow_warp.py:103-127,
+ *     pointcloud_utils.py:29): unit vectors of the pixel centres and of the flow end points over rows
+ *     [H/4, 3H/4).  `out` [B,9] float64 on the device; deterministic two-level reduction through `scratch`
+ *     (tif_flow_cross_covariance_scratch_bytes).  The 3x3 SVD that follows is 9 numbers and stays with the caller.
+ * tif_flow_rotate_endpoint         projection.flow_rotate_endpoint (projection.py:120-159): `rotation_field` is the
+ *     [H,W,2] float64 output of tif_rotation_motion_vector_f64(R, wraparound=1).
+ */
+int tif_rotation_motion_vector_f64(const double* rotation /*host, 9*/, int h, int w, int wraparound,
+                                   double* out /*[H,W,2]*/, void* stream);
+int64_t tif_flow_cross_covariance_scratch_bytes(int batch, int h, int w);
+int tif_flow_cross_covariance(const void* flow /*[B,H,W,2]*/, int dtype, int batch, int h, int w, double* out /*[B,9]*/,
+                              void* scratch, void* stream);
+int tif_flow_rotate_endpoint(const void* flow /*[B,H,W,2]*/, int dtype, const double* rotation_field /*[H,W,2]*/,
+                             int batch, int h, int w, int wraparound, void* out /*[B,H,W,2] same dtype*/, void* stream);
+
 /* flow_postproc.erp_of_wraparound (flow_postproc.py:17-44), in place on [B,H,W,2]. */
 int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold, void* stream);
 

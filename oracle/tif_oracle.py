@@ -785,3 +785,102 @@ def cubemap2erp_flow(cubemap_flows, erp_h=None, padding=0.0, image_src=None, ima
     if return_debug:
         return acc_flow, debug
     return acc_flow
+
+
+# ------------------------------------------------------------------------------------------------
+# global rotation -- flow_warp.py:91-133,190-229, spherical_coordinates.py:128-218,
+# projection.py:120-159, pointcloud_utils.py:10-32
+# ------------------------------------------------------------------------------------------------
+
+def erp2sph_grid(x, y, erp_h):
+    """spherical_coordinates.py:64-101 on full arrays (sph_modulo=False)."""
+    width = erp_h * 2
+    theta = x * (2 * PI / width) + PI / width - PI
+    phi = -(y * (PI / erp_h) + PI / erp_h * 0.5) + 0.5 * PI
+    theta = np.where(theta == PI, -PI, theta)
+    phi = np.where(phi == -0.5 * PI, 0.5 * PI, phi)
+    return theta, phi
+
+
+def sph2car_grid(theta, phi):
+    """spherical_coordinates.py:151-169 with radius 1.0: [3, ...]."""
+    return np.stack((1.0 * np.cos(phi) * np.sin(theta), -1.0 * np.sin(phi), 1.0 * np.cos(phi) * np.cos(theta)), axis=0)
+
+
+def rotation2erp_motion_vector(array_size, rotation_matrix, wraparound=False):
+    """spherical_coordinates.py:185-218: ERP flow of a rigid rotation of the sphere, [H,W,2] float64."""
+    h, w = array_size
+    vx, vy = np.meshgrid(np.linspace(0, w, w, endpoint=False), np.linspace(0, h, h, endpoint=False))
+    theta, phi = erp2sph_grid(vx, vy, h)
+    xyz = sph2car_grid(theta, phi)
+    rot = np.dot(rotation_matrix, xyz.reshape((3, -1)))
+    sph = _car2sph(rot.T).T
+    rx, ry = sph2erp(sph[0, :], sph[1, :], h, False)
+    mx = rx.reshape((h, w)) - vx
+    my = ry.reshape((h, w)) - vy
+    if wraparound:
+        tar_theta = sph[0, :].reshape((h, w))
+        long_line = np.abs(tar_theta - theta) > PI
+        minus = long_line & (theta < 0) & (tar_theta > 0)
+        plus = long_line & (theta > 0) & (tar_theta < 0)
+        mx[minus] = mx[minus] - w
+        mx[plus] = mx[plus] + w
+    return np.stack((mx, my), -1)
+
+
+def rotate_erp_array(erp_image, rotation_mat):
+    """spherical_coordinates.py:172-182."""
+    return warp_backward(erp_image, rotation2erp_motion_vector(erp_image.shape[0:2], rotation_mat.T))
+
+
+def flow_cross_covariance(erp_flow):
+    """The 3x3 matrix H = S^T T of flow_warp.flow2rotation_3d (flow_warp.py:103-127) + pointcloud_utils.py:29:
+    unit vectors of the pixel centres (S) and of the flow end points (T) over the middle half of the rows."""
+    h, w = erp_flow.shape[:2]
+    tar = flow_warp_meshgrid(erp_flow[:, :, 0], erp_flow[:, :, 1])
+    xa, ya = np.meshgrid(np.linspace(0, w - 1, w), np.linspace(0, h - 1, h))
+    st, sp = erp2sph_grid(xa, ya, h)
+    tt, tp = erp2sph_grid(tar[0], tar[1], h)
+    r0, r1 = int(h * 0.25), int(h * 0.75)
+    s3 = sph2car_grid(st[r0:r1], sp[r0:r1])
+    t3 = sph2car_grid(tt[r0:r1], tp[r0:r1])
+    s3 = np.swapaxes(s3.reshape((3, -1)), 0, 1)
+    t3 = np.swapaxes(t3.reshape((3, -1)), 0, 1)
+    return np.dot(s3.T, t3)
+
+
+def rotation_from_covariance(hmat):
+    """pointcloud_utils.py:31-32."""
+    u, _, vt = np.linalg.svd(hmat)
+    return np.dot(vt.T, u.T)
+
+
+def flow2rotation_3d(erp_flow):
+    """flow_warp.py:91-133 (mask_method='center')."""
+    return rotation_from_covariance(flow_cross_covariance(erp_flow))
+
+
+def global_rotation_warping(erp_image, erp_flow, forward_warp=True):
+    """flow_warp.py:190-229 with rotation_type='3D'."""
+    rotation_mat = flow2rotation_3d(erp_flow)
+    if not forward_warp:
+        rotation_mat = rotation_mat.T
+    out = rotate_erp_array(erp_image, rotation_mat)
+    if erp_image.dtype == np.uint8:
+        out = out.astype(np.uint8)
+    return out, rotation_mat
+
+
+def flow_rotate_endpoint(optical_flow, rotation_matrix, wraparound=False):
+    """projection.py:120-159 for a rotation matrix."""
+    h, w = optical_flow.shape[:2]
+    sx, sy = np.meshgrid(np.linspace(0, w, w, endpoint=False), np.linspace(0, h, h, endpoint=False))
+    ex, ey = erp_pixles_modulo(sx + optical_flow[:, :, 0], sy + optical_flow[:, :, 1], w, h)
+    field = rotation2erp_motion_vector((h, w), rotation_matrix, wraparound=True)
+    ru = map_coordinates_order1(field[:, :, 0], ey, ex, "wrap")
+    rv = map_coordinates_order1(field[:, :, 1], ey, ex, "wrap")
+    ex, ey = erp_pixles_modulo(ex + ru, ey + rv, w, h)
+    out = np.stack((ex - sx, ey - sy), axis=-1)
+    if wraparound:
+        out = erp_of_wraparound(out)
+    return out
