@@ -13,8 +13,8 @@ from . import polygon, spherical_coordinates, gnomonic_projection  # noqa: F401
 __all__ = ["projection_icosahedron", "flow_warp", "flow_postproc", "gnomonic_projection",
            "spherical_coordinates", "polygon", "install_dropin", "sharding"]
 
-_LAZY = ("projection_icosahedron", "projection_cubemap", "projection", "flow_warp", "flow_postproc", "_geometry", "_ops",
-         "sharding", "pipeline")
+_LAZY = ("projection_icosahedron", "projection_cubemap", "projection", "flow_warp", "flow_postproc", "flow_evaluate", "flow_io",
+         "_geometry", "_ops", "sharding", "pipeline")
 
 
 def __getattr__(name):

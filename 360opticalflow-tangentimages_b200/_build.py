@@ -21,6 +21,7 @@ UNITS = {
     "tif_plan.cu": ["-fmad=false"],
     "tif_exec.cu": [],
     "tif_rotate.cu": [],
+    "tif_metrics.cu": [],
 }
 
 

@@ -212,6 +212,22 @@ int tif_flow_cross_covariance(const void* flow /*[B,H,W,2]*/, int dtype, int bat
 int tif_flow_rotate_endpoint(const void* flow /*[B,H,W,2]*/, int dtype, const double* rotation_field /*[H,W,2]*/,
                              int batch, int h, int w, int wraparound, void* out /*[B,H,W,2] same dtype*/, void* stream);
 
+/*
+ * Flow metrics (row f3): flow_evaluate.{available_pixel, EPE_mat, RMSE_mat, AAE_mat} (flow_evaluate.py:23-217).
+ * Per-pixel error matrices of an evaluated flow against a ground truth (both [B,H,W,2], float32 or float64):
+ * `epe` = end-point error (planar Euclidean, or great-circle distance of the two end points when spherical != 0),
+ * `aae` (nullable) = planar angular error |atan2(cross, dot)|, `valid` = available_pixel of the ground truth
+ * (and of `mask` [B,H,W] uint8 when given).  Where the ground truth is unusable both flows count as zero.
+ * tif_reduce_f64 sums n doubles per image (power 1) or their squares (power 2) deterministically:
+ * EPE = sum(epe)/sum(valid), RMSE = sqrt(sum(epe^2)/sum(valid)), AAE = sum(aae)/sum(valid).
+ */
+int tif_flow_error_mats(const void* gt, const void* eva, int dtype, const uint8_t* mask /*nullable*/, int batch, int h,
+                        int w, int spherical, double* epe /*[B,H,W]*/, double* aae /*[B,H,W] nullable*/,
+                        uint8_t* valid /*[B,H,W]*/, void* stream);
+int64_t tif_reduce_f64_scratch_bytes(int batch);
+int tif_reduce_f64(const double* x /*[B,n]*/, int batch, int64_t n, int power, double* out /*[B]*/, void* scratch,
+                   void* stream);
+
 /* flow_postproc.erp_of_wraparound (flow_postproc.py:17-44), in place on [B,H,W,2]. */
 int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold, void* stream);
 

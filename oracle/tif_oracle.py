@@ -884,3 +884,60 @@ def flow_rotate_endpoint(optical_flow, rotation_matrix, wraparound=False):
     if wraparound:
         out = erp_of_wraparound(out)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# metrics -- flow_evaluate.py:23-217
+# ------------------------------------------------------------------------------------------------
+
+def available_pixel(flow, of_mask=None, unknown_value=1e7):
+    """flow_evaluate.py:23-54, operator precedence of `index_unlarge` included."""
+    u, v = flow[:, :, 0], flow[:, :, 1]
+    with np.errstate(invalid="ignore"):
+        unlarge = np.logical_not(abs(u) > unknown_value) | (abs(v) > unknown_value)
+        unnan = np.logical_not(np.isnan(u) | np.isnan(v))
+        unzero = (np.absolute(u) > 0) | (np.absolute(v) > 0)
+    valid = unlarge & unnan & unzero
+    if of_mask is not None:
+        valid = valid & of_mask
+    return valid
+
+
+def great_circle_distance_uv(t1, p1, t2, p2):
+    """spherical_coordinates.py:28-52."""
+    a = np.sin((p2 - p1) * 0.5) ** 2 + np.cos(p1) * np.cos(p2) * np.sin((t2 - t1) * 0.5) ** 2
+    return np.abs(1 * (2 * np.arctan2(np.sqrt(a), np.sqrt(1 - a))))
+
+
+def epe_mat(gt, ev, spherical=False, of_mask=None):
+    """flow_evaluate.py:70-104 (and RMSE_mat :118-153).  Works on copies; the reference zeroes its inputs in place."""
+    gt, ev = np.array(gt, dtype=np.float64), np.array(ev, dtype=np.float64)
+    ok = available_pixel(gt, of_mask)
+    gt[~ok] = 0
+    ev[~ok] = 0
+    if spherical:
+        h = gt.shape[0]
+        g = flow_warp_meshgrid(gt[:, :, 0], gt[:, :, 1])
+        e = flow_warp_meshgrid(ev[:, :, 0], ev[:, :, 1])
+        gth, gph = erp2sph_grid(g[0], g[1], h)
+        eth, eph = erp2sph_grid(e[0], e[1], h)
+        return great_circle_distance_uv(gth, gph, eth, eph), ok
+    return np.sqrt((gt[:, :, 0] - ev[:, :, 0]) ** 2 + (gt[:, :, 1] - ev[:, :, 1]) ** 2), ok
+
+
+def aae_mat(gt, ev, of_mask=None):
+    """flow_evaluate.py:167-217, planar branch."""
+    gt, ev = np.array(gt, dtype=np.float64), np.array(ev, dtype=np.float64)
+    ok = available_pixel(gt, of_mask)
+    gt[~ok] = 0
+    ev[~ok] = 0
+    cross = gt[:, :, 0] * ev[:, :, 1] - gt[:, :, 1] * ev[:, :, 0]
+    dot = gt[:, :, 0] * ev[:, :, 0] + gt[:, :, 1] * ev[:, :, 1]
+    return abs(np.arctan2(cross, dot)), ok
+
+
+def flow_metrics(gt, ev, spherical=False, of_mask=None):
+    """EPE, RMSE, AAE as flow_evaluate.py:57-67,107-115,156-164 compute them (AAE: always planar, unmasked)."""
+    e, ok = epe_mat(gt, ev, spherical, of_mask)
+    a, ok_a = aae_mat(gt, ev, None)
+    return np.sum(e) / np.sum(ok), np.sqrt(np.sum(np.square(e)) / np.sum(ok)), np.sum(a) / np.sum(ok_a)
