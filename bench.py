@@ -326,7 +326,7 @@ def run_ours(args):
     # ---- end to end through the public host API (pinned host buffers, copies inside the timed region) -------
     e2e = None
     if not args.no_e2e:
-        pipe = pkg.pipeline.HostPipeline(PAD, args.height, TANGENT_W, args.blend, True, chunk=4, slots=3, device=device)
+        pipe = pkg.pipeline.HostPipeline(PAD, args.height, TANGENT_W, args.blend, True, chunk=2, slots=4, device=device)
         h_src, h_tar, h_flows = (t.cpu().pin_memory() for t in (src, tar, flows))
         h_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
         h_ts = torch.empty(tan_src.shape, dtype=torch.uint8).pin_memory()
