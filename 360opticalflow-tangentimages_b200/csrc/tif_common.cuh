@@ -30,6 +30,12 @@
 // 128 threads x 765 x 7 x 1024 < 2^32: a block's partial sum fits a native 32-bit shared atomic
 #define TIF_NW_FIXED_SCALE 1024.0f
 
+// stage-1 staging: a block owns a TIF_S1_TILE x TIF_S1_TILE patch of the tangent stack; the ERP rows its taps
+// touch are bulk-copied (cp.async.bulk + mbarrier) into one of TIF_S1_STAGES shared-memory buffers per image
+#define TIF_S1_TILE 16
+#define TIF_S1_STAGE_BYTES 6144
+#define TIF_S1_STAGES 3
+
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;
     int kind;                      // TIF_PLAN_ICOSAHEDRON | TIF_PLAN_CUBEMAP
@@ -46,6 +52,10 @@ struct TifPlan {
     double2* d_s1_frac64;          // [P] the same in float64 (exact scipy weights, rounding fallback)
     double* d_s1_ex;               // [P] ERP sample x after sph2erp(modulo)   (parity export)
     double* d_s1_ey;               // [P]
+    uint2* d_s1_tiles;             // [tiles_y * tiles_x] {first byte of the tile's ERP footprint in an image (16-byte
+                                   //  aligned), rows | row bytes << 16}; rows == 0: footprint too large, direct gathers
+    int s1_tiles_x, s1_tiles_y;
+    int64_t s1_staged_tiles;
     // stage 2: per ERP pixel
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order

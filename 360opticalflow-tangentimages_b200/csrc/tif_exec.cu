@@ -102,11 +102,14 @@ __device__ __forceinline__ void load_tap_pair_bytes(const uint8_t* __restrict__ 
 
 // Fixed-point bilinear: weights scaled by 2^24 (exactly rounded from the float64 scipy weights), so the
 // top byte of p00 W00 + p01 W01 + p10 W10 + p11 W11 + 2^23 is scipy's trunc(t + 0.5).  The fixed-point
-// sum is within 3.1e-5 of t; if t + 0.5 lies within 2^-11 of an integer the exact float64 expression
-// decides instead (about 1e-3 of the samples).
+// sum is within 255 * 4 * 2^-25 = 3.1e-5 (510 units of 2^-24) of t, and scipy's own float64 sum within
+// 1e-13; if t + 0.5 lies within 1024 units (2^-14) of an integer the exact float64 expression decides
+// instead (3.7e-4 of the pixels, i.e. about one warp in 85 takes the slow branch).
 #define TIF_FIX_ONE 16777216.0
 #define TIF_FIX_HALF 0x00800000u
-#define TIF_FIX_GUARD 0x00002000u
+#ifndef TIF_FIX_GUARD
+#define TIF_FIX_GUARD 0x00000400u
+#endif
 
 __device__ __forceinline__ uint32_t fix_bilinear(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, uint32_t w00,
                                                  uint32_t w01, uint32_t w10, uint32_t w11) {
@@ -155,16 +158,15 @@ __host__ __device__ __forceinline__ int64_t tile_threads(int width, int rows) {
 #ifndef TIF_ERP2ICO_MIN_BLOCKS
 #define TIF_ERP2ICO_MIN_BLOCKS 4
 #endif
+#ifndef TIF_ERP2ICO_THREADS
+#define TIF_ERP2ICO_THREADS 256
+#endif
+// one tangent pixel, all images [b_begin, b_end): taps gathered straight from global memory
 template <bool ALIGNED>
-__global__ void __launch_bounds__(256, TIF_ERP2ICO_MIN_BLOCKS)
-k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
-          const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
-          int batch, int batch_per_block_row, int full_face) {
-    int trow, tcol;
-    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, tangent_w, (int)(n_pix / tangent_w), trow, tcol)) return;
-    const int64_t p = (int64_t)trow * tangent_w + tcol;
-    const int b_begin = blockIdx.y * batch_per_block_row;
-    const int b_end = min(batch, b_begin + batch_per_block_row);
+__device__ __forceinline__ void erp2ico_direct(int64_t p, const uint32_t* __restrict__ s1_base,
+                                               const double2* __restrict__ s1_frac64, const uint8_t* __restrict__ erp,
+                                               uint8_t* __restrict__ out, int64_t n_pix, int erp_h, int erp_w, int b_begin,
+                                               int b_end, int full_face) {
     const uint32_t bs = s1_base[p];
     const size_t image_bytes = (size_t)erp_h * erp_w * 3;
     const size_t row_bytes = (size_t)erp_w * 3;
@@ -225,13 +227,148 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
     }
 }
 
+template <bool ALIGNED>
+__global__ void __launch_bounds__(TIF_ERP2ICO_THREADS, TIF_ERP2ICO_MIN_BLOCKS)
+k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
+          const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
+          int batch, int batch_per_block_row, int full_face) {
+    int trow, tcol;
+    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, tangent_w, (int)(n_pix / tangent_w), trow, tcol)) return;
+    const int b_begin = blockIdx.y * batch_per_block_row;
+    erp2ico_direct<ALIGNED>((int64_t)trow * tangent_w + tcol, s1_base, s1_frac64, erp, out, n_pix, erp_h, erp_w, b_begin,
+                            min(batch, b_begin + batch_per_block_row), full_face);
+}
+
+// ---- staged variant ---------------------------------------------------------------------------------
+// The direct kernel is bound by L1 wavefronts: every tap load of a warp touches 5-6 cache lines and each ERP
+// byte is fetched by several warps.  Here a block owns a 16 x 16 patch of the tangent stack; the plan knows the
+// bounding box of its taps (median 21 x 18 ERP pixels at 2K), and that box is brought into shared memory with
+// 16-byte asynchronous copies (cp.async, no register staging), TIF_S1_STAGES - 1 images ahead of the blend.
+// The taps then come from shared memory (LDS, no L1 tag traffic) and the global reads are whole aligned rows.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+#ifndef TIF_ERP2ICO_STAGED_MIN_BLOCKS
+#define TIF_ERP2ICO_STAGED_MIN_BLOCKS 4
+#endif
+#define TIF_S1_THREADS (TIF_S1_TILE * TIF_S1_TILE)
+static_assert(TIF_S1_STAGE_BYTES <= 2 * 16 * TIF_S1_THREADS, "a thread copies at most two 16-byte chunks per image");
+
+__global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
+k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
+                 const uint2* __restrict__ s1_tiles, int tiles_x, const uint8_t* __restrict__ erp,
+                 uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w, int batch,
+                 int batch_per_block_row, int full_face) {
+    __shared__ __align__(128) uint8_t stage[TIF_S1_STAGES][TIF_S1_STAGE_BYTES];
+    const int tid = threadIdx.x;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int trow = ty * TIF_S1_TILE + tid / TIF_S1_TILE, tcol = tx * TIF_S1_TILE + tid % TIF_S1_TILE;
+    const bool valid = trow < (int)(n_pix / tangent_w) && tcol < tangent_w;
+    const int64_t p = (int64_t)trow * tangent_w + tcol;
+    const int b_begin = blockIdx.y * batch_per_block_row;
+    const int n_img = min(batch, b_begin + batch_per_block_row) - b_begin;
+    const uint2 desc = s1_tiles[blockIdx.x];
+    const uint32_t n_rows = desc.y & 0xffffu, pitch = desc.y >> 16;
+    if (n_rows == 0u) {        // footprint too large for a stage: block-uniform fall back to direct gathers
+        if (valid) erp2ico_direct<true>(p, s1_base, s1_frac64, erp, out, n_pix, erp_h, erp_w, b_begin, b_begin + n_img, full_face);
+        return;
+    }
+    const uint32_t row_bytes = (uint32_t)erp_w * 3u;
+    const size_t image_bytes = (size_t)erp_h * row_bytes;
+    const uint32_t stage0 = smem_u32(&stage[0][0]);
+    // the staged box is dense (rows `pitch` apart): chunk c of the box is bytes [16 c, 16 c + 16)
+    const uint32_t cpr = pitch >> 4, n_chunks = n_rows * cpr;
+    const uint32_t c0 = (uint32_t)tid, c1 = (uint32_t)tid + TIF_S1_THREADS;
+    const bool have0 = c0 < n_chunks, have1 = c1 < n_chunks;
+    const uint32_t r0 = c0 / cpr, r1 = c1 / cpr;
+    const uint8_t* img = erp + (size_t)b_begin * image_bytes + desc.x;
+    const uint32_t src0 = r0 * row_bytes + (c0 - r0 * cpr) * 16u, src1 = r1 * row_bytes + (c1 - r1 * cpr) * 16u;
+    auto issue = [&](int i) {       // image b_begin + i -> buffer i % STAGES
+        if (i < n_img) {
+            const uint32_t buf = stage0 + (uint32_t)(i % TIF_S1_STAGES) * TIF_S1_STAGE_BYTES;
+            const uint8_t* g = img + (size_t)i * image_bytes;
+            if (have0) cp_async16(buf + c0 * 16u, g + src0);
+            if (have1) cp_async16(buf + c1 * 16u, g + src1);
+        }
+        cp_async_commit();          // one group per image, empty or not: the wait below counts groups
+    };
+#pragma unroll
+    for (int i = 0; i < TIF_S1_STAGES - 1; ++i) issue(i);
+
+    uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = 0u, sh = 0u;
+    bool blend = false;
+    if (valid) {
+        bs = s1_base[p];
+        blend = !((bs & TIF_S1_OUTSIDE) && !full_face);
+    }
+    if (blend) {
+        const double2 fr = s1_frac64[p];
+        const double wx0 = 1.0 - fr.x, wx1 = 1.0 - wx0, wy0 = 1.0 - fr.y, wy1 = 1.0 - wy0;
+        w00 = (uint32_t)(wy0 * wx0 * TIF_FIX_ONE + 0.5);
+        w01 = (uint32_t)(wy0 * wx1 * TIF_FIX_ONE + 0.5);
+        w10 = (uint32_t)(wy1 * wx0 * TIF_FIX_ONE + 0.5);
+        w11 = (uint32_t)(wy1 * wx1 * TIF_FIX_ONE + 0.5);
+        // byte offset of the first tap inside the staged box: rows are `pitch` apart there, `row_bytes` in the image
+        const uint32_t t = (bs & 0x7fffffffu) * 3u - desc.x;
+        const uint32_t dy = t / row_bytes, dxb = t - dy * row_bytes;
+        const uint32_t o = dy * pitch + dxb;
+        tap = o & ~3u;              // pitch is a multiple of 16: both rows share the byte phase
+        sh = (o & 3u) * 8u;
+    }
+    uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
+    int s = 0;
+    for (int i = 0; i < n_img; ++i, o4 += n_pix) {
+        cp_async_wait<TIF_S1_STAGES - 2>();     // this thread's chunks of image i have landed
+        __syncthreads();                        // ... everyone's have, and everyone is done with image i - 1
+        issue(i + TIF_S1_STAGES - 1);           // refills the buffer of image i - 1
+        const uint32_t buf = stage0 + (uint32_t)s * TIF_S1_STAGE_BYTES;
+        if (++s == TIF_S1_STAGES) s = 0;
+        if (blend) {
+            const uint32_t a0 = buf + tap, a1 = a0 + pitch;
+            const uint32_t r00 = lds_u32(a0), r01 = lds_u32(a0 + 4u), r02 = lds_u32(a0 + 8u);
+            const uint32_t r10 = lds_u32(a1), r11 = lds_u32(a1 + 4u), r12 = lds_u32(a1 + 8u);
+            const uint32_t lo0 = __funnelshift_r(r00, r01, sh), hi0 = __funnelshift_r(r01, r02, sh);
+            const uint32_t lo1 = __funnelshift_r(r10, r11, sh), hi1 = __funnelshift_r(r11, r12, sh);
+            uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
+            uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
+            uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
+            if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
+                const double2 fr = s1_frac64[p];        // rare: re-read instead of keeping four registers live
+                ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
+                ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
+                ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
+            }
+            *o4 = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
+        } else if (valid) {
+            *o4 = 0x00ffffffu;          // RGB 255, alpha 0
+        }
+    }
+    cp_async_wait<0>();
+}
+
 extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch, int full_face_image,
                               uint8_t* tangent_rgba, void* stream) {
     if (!plan || !erp || !tangent_rgba || batch <= 0) {
         tif_set_error("tif_erp2ico_u8: invalid argument");
         return TIF_ERR_INVALID_ARG;
     }
-    const int threads = 256;
+    const int threads = TIF_ERP2ICO_THREADS;
     const int64_t n_threads = tile_threads(plan->tangent_w, (int)(plan->tangent_pixels / plan->tangent_w));
     const unsigned blocks_x = (unsigned)((n_threads + threads - 1) / threads);
     // every thread walks the whole batch so that the plan entry is read once; only tiny problems
@@ -242,7 +379,19 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
     dim3 grid(blocks_x, (unsigned)((batch + per_row - 1) / per_row));
     const size_t image_bytes = (size_t)plan->erp_h * plan->erp_w * 3;
     const bool aligned = (image_bytes % 4 == 0) && (reinterpret_cast<uintptr_t>(erp) % 4 == 0);
-    if (aligned)
+    const bool stageable = aligned && plan->d_s1_tiles && plan->s1_staged_tiles > 0 &&
+                           reinterpret_cast<uintptr_t>(erp) % 16 == 0 && image_bytes % 16 == 0 &&
+                           ((size_t)plan->erp_w * 3) % 16 == 0;
+    if (stageable) {
+        const unsigned tiles = (unsigned)(plan->s1_tiles_x * plan->s1_tiles_y);
+        int srows = 1;
+        while (srows < batch && (int64_t)tiles * srows < 148 * 16) srows *= 2;
+        const int sper = (batch + srows - 1) / srows;
+        dim3 sgrid(tiles, (unsigned)((batch + sper - 1) / sper));
+        k_erp2ico_staged<<<sgrid, TIF_S1_TILE * TIF_S1_TILE, 0, (cudaStream_t)stream>>>(
+            plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, erp, tangent_rgba, plan->tangent_pixels,
+            plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
+    } else if (aligned)
         k_erp2ico<true><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
                                                                     plan->tangent_pixels, plan->tangent_w, plan->erp_h,
                                                                     plan->erp_w, batch, per_row, full_face_image);
@@ -363,18 +512,29 @@ __device__ __forceinline__ float byte_f(uint32_t w, unsigned k) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | k)) - 8388608.0f;
 }
 
-// float64 lift for the rare polar cases: both directions through CUDA's double atan2 / sqrt.
-// (gx0, gy0): gnomonic position of the tangent pixel; returns the longitude / colatitude differences.
-__device__ __noinline__ void lift_precise(double gx0, double gy0, double s0, double c0, double kx, double ky, float u,
-                                          float v, double* dtheta, double* dcolat) {
+// float64 lift for the rare polar cases: both directions through CUDA's double atan2 / sqrt.  Everything it
+// needs is rebuilt from the pixel index, so that the fast path keeps no float64 state live in registers.
+// Returns the displacement in ERP pixels and, for the target sample, the absolute end point (ex + px, ey + py).
+__device__ __noinline__ void lift_precise(const LiftFace* F, int tcol, int trow, float u, float v, int erp_w, int erp_h,
+                                          const double* __restrict__ s1_ex, const double* __restrict__ s1_ey, int p,
+                                          float* disp, double* end) {
+    const double s0 = F->sin_phi0, c0 = F->cos_phi0;
+    const double gx0 = fma((double)tcol, F->kx, F->xmin);
+    const double gy0 = fma(-(double)(trow - F->first_row), F->ky, F->ymax);
     const double b0 = fma(-gy0, s0, c0), z0 = fma(gy0, c0, s0);
-    const double gx = fma((double)u, kx, gx0), gy = fma(-(double)v, ky, gy0);
+    const double gx = fma((double)u, F->kx, gx0), gy = fma(-(double)v, F->ky, gy0);
     const double b1 = fma(-gy, s0, c0), z1 = fma(gy, c0, s0);
     double d = atan2(gx, b1) - atan2(gx0, b0);
     if (d > TIF_PI) d -= TIF_TWO_PI;
     else if (d <= -TIF_PI) d += TIF_TWO_PI;
-    *dtheta = d;
-    *dcolat = atan2(sqrt(fma(gx, gx, b1 * b1)), z1) - atan2(sqrt(fma(gx0, gx0, b0 * b0)), z0);
+    const double dco = atan2(sqrt(fma(gx, gx, b1 * b1)), z1) - atan2(sqrt(fma(gx0, gx0, b0 * b0)), z0);
+    const double px = d * ((double)erp_w / TIF_TWO_PI), py = dco * ((double)erp_h / TIF_PI);
+    disp[0] = (float)px;
+    disp[1] = (float)py;
+    if (s1_ex) {
+        end[0] = s1_ex[p] + px;
+        end[1] = s1_ey[p] + py;
+    }
 }
 
 // Displacement of the flow end point of ONE tangent pixel, projection_icosahedron.py:336-347:
@@ -388,11 +548,14 @@ __device__ __noinline__ void lift_precise(double gx0, double gy0, double s0, dou
 #ifndef TIF_LIFT_MIN_BLOCKS
 #define TIF_LIFT_MIN_BLOCKS 4
 #endif
+#ifndef TIF_LIFT_THREADS
+#define TIF_LIFT_THREADS 256
+#endif
 // SAMPLE 0: displacement only.  SAMPLE 1: + float bilinear sample of the target image (normwarp: the reference
 // converts the images to float64 first).  SAMPLE 2: + the sample rounded half-up to uint8 (cubemap stage: its
 // images stay uint8, so scipy rounds every sample, projection.py:103-104).
 template <int SAMPLE>
-__global__ void __launch_bounds__(256, TIF_LIFT_MIN_BLOCKS)
+__global__ void __launch_bounds__(TIF_LIFT_THREADS, TIF_LIFT_MIN_BLOCKS)
 k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
@@ -429,12 +592,15 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     const LiftFace& F = sh_face[__ldg(row_face + trow)];
 
     // ---- per tangent pixel, once for the chunk of images -------------------------------------------------
-    const double gx0 = fma((double)tcol, F.kx, F.xmin);
-    const double gy0 = fma(-(double)(trow - F.first_row), F.ky, F.ymax);
-    // own direction (east, toward the face meridian, polar axis) before normalisation
-    const float a0 = (float)gx0;
-    const float bz0 = (float)fma(-gy0, F.sin_phi0, F.cos_phi0);
-    const float cy0 = (float)fma(gy0, F.cos_phi0, F.sin_phi0);
+    float a0, bz0, cy0;
+    {
+        const double gx0 = fma((double)tcol, F.kx, F.xmin);
+        const double gy0 = fma(-(double)(trow - F.first_row), F.ky, F.ymax);
+        // own direction (east, toward the face meridian, polar axis) before normalisation
+        a0 = (float)gx0;
+        bz0 = (float)fma(-gy0, F.sin_phi0, F.cos_phi0);
+        cy0 = (float)fma(gy0, F.cos_phi0, F.sin_phi0);
+    }
     const float hp2 = fmaf(a0, a0, bz0 * bz0), n2 = hp2 + cy0 * cy0;
     const bool polar_pixel = hp2 < TIF_POLAR_SIN2 * n2;
     const float inv_hp = rsqrtf(fmaxf(hp2, 1e-30f)), inv_n = rsqrtf(n2);
@@ -450,10 +616,8 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     // own ERP position (plan stage 1), split into integer and fraction for the target sample
     int exi = 0, eyi = 0;
     float exf = 0.0f, eyf = 0.0f;
-    double ex = 0.0, ey = 0.0;
     if (NW) {
-        ex = s1_ex[p];
-        ey = s1_ey[p];
+        const double ex = s1_ex[p], ey = s1_ey[p];
         const double fxi = floor(ex), fyi = floor(ey);
         exi = (int)fxi;
         eyi = (int)fyi;
@@ -481,18 +645,17 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
         float disp_x, disp_y, fx, fy;
         int xi, yi;
         if (polar_pixel || h < 0.1f * fabsf(z)) {       // pixel or end point within ~5.7 degrees of a pole
-            double dth, dco;
-            lift_precise(gx0, gy0, F.sin_phi0, F.cos_phi0, F.kx, F.ky, uv.x, uv.y, &dth, &dco);
-            const double px = dth * ((double)erp_w / TIF_TWO_PI), py = dco * ((double)erp_h / TIF_PI);
-            disp_x = (float)px;
-            disp_y = (float)py;
+            float disp[2];
+            double end[2];
+            lift_precise(&F, tcol, trow, uv.x, uv.y, erp_w, erp_h, NW ? s1_ex : nullptr, s1_ey, p, disp, end);
+            disp_x = disp[0];
+            disp_y = disp[1];
             if (NW) {
-                const double ax = ex + px, ay = ey + py;
-                const double fax = floor(ax), fay = floor(ay);
+                const double fax = floor(end[0]), fay = floor(end[1]);
                 xi = (int)fax;
                 yi = (int)fay;
-                fx = (float)(ax - fax);
-                fy = (float)(ay - fay);
+                fx = (float)(end[0] - fax);
+                fy = (float)(end[1] - fay);
             }
         } else {
             const float dtheta = atan2_fast(E, rm);
@@ -807,7 +970,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     unsigned long long* nw_sums = (unsigned long long*)scratch;
     void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
     const int n_ref = (int)plan->referenced_tangent_pixels;
-    const dim3 lift_grid((unsigned)((n_ref + 255) / 256), by);
+    const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), by);
     const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS), by);
     const size_t lift_smem = sizeof(LiftFace) * n_faces;
     const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * n_faces;
@@ -817,7 +980,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
         if (!skip_lift)
-            k_lift<0><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<0><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                                  n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
                                                                  records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
@@ -829,7 +992,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         }
     } else if (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) {
         if (!skip_lift)
-            k_lift<2><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<2><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
                                                              records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
@@ -838,7 +1001,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if (pass_mask & 1) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (!skip_lift)
-                k_lift<1><<<lift_grid, 256, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
+                k_lift<1><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
                                                                     plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch);

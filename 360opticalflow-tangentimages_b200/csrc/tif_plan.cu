@@ -261,6 +261,7 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_s1_frac64);
     cudaFree(plan->d_s1_ex);
     cudaFree(plan->d_s1_ey);
+    cudaFree(plan->d_s1_tiles);
     cudaFree(plan->d_s2_count);
     cudaFree(plan->d_s2_entries);
     cudaFree(plan->d_s2_snap);
@@ -471,6 +472,58 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
                           (long long)n_list, (long long)plan->referenced_tangent_pixels);
             PLAN_TRY(TIF_ERR_RANGE);
         }
+    }
+    {
+        // stage-1 tile table: the bounding box of the taps of every 16 x 16 tangent patch.  Patches whose box fits a
+        // shared-memory stage are resampled from a staged copy of the box; the rest (polar caps, the seam, patches
+        // spanning two faces) keep the direct gathers.
+        const int tile = TIF_S1_TILE;
+        const int tiles_x = (tangent_w + tile - 1) / tile, tiles_y = (int)((n_rows + tile - 1) / tile);
+        const size_t n_tiles = (size_t)tiles_x * tiles_y;
+        const uint32_t row_bytes = (uint32_t)erp_w * 3u;
+        const bool alignable = row_bytes % 16u == 0 && ((size_t)erp_h * row_bytes) % 16u == 0;
+        uint32_t* h_base = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_tangent);
+        uint2* h_tiles = (uint2*)malloc(sizeof(uint2) * n_tiles);
+        cudaError_t ea = cudaMemcpy(h_base, plan->d_s1_base, sizeof(uint32_t) * (size_t)n_tangent, cudaMemcpyDeviceToHost);
+        int64_t staged = 0;
+        if (ea == cudaSuccess) {
+            for (int ty = 0; ty < tiles_y; ++ty)
+                for (int tx = 0; tx < tiles_x; ++tx) {
+                    uint32_t x_lo = 0xffffffffu, x_hi = 0, y_lo = 0xffffffffu, y_hi = 0;
+                    for (int64_t y = (int64_t)ty * tile; y < (int64_t)(ty + 1) * tile && y < n_rows; ++y)
+                        for (int x = tx * tile; x < (tx + 1) * tile && x < tangent_w; ++x) {
+                            const uint32_t b = h_base[y * tangent_w + x] & 0x7fffffffu;
+                            const uint32_t y0 = b / (uint32_t)erp_w, x0 = b - y0 * (uint32_t)erp_w;
+                            x_lo = x0 < x_lo ? x0 : x_lo;
+                            x_hi = x0 > x_hi ? x0 : x_hi;
+                            y_lo = y0 < y_lo ? y0 : y_lo;
+                            y_hi = y0 > y_hi ? y0 : y_hi;
+                        }
+                    uint2 d = make_uint2(0u, 0u);
+                    if (alignable && x_lo <= x_hi) {
+                        const uint32_t xb0 = (x_lo * 3u) & ~15u;
+                        uint32_t xb1 = ((x_hi + 2u) * 3u + 15u) & ~15u;       // taps x0, x0 + 1: 6 bytes from x0 * 3
+                        if (xb1 > row_bytes) xb1 = row_bytes;
+                        const uint32_t pitch = xb1 - xb0, rows = y_hi + 2u - y_lo;
+                        // 16 bytes of slack: the aligned 12-byte window of the last tap may end past its row
+                        if (rows <= 256u && (size_t)rows * pitch + 16u <= TIF_S1_STAGE_BYTES && y_hi + 1u < (uint32_t)erp_h) {
+                            d = make_uint2(y_lo * row_bytes + xb0, rows | (pitch << 16));
+                            ++staged;
+                        }
+                    }
+                    h_tiles[(size_t)ty * tiles_x + tx] = d;
+                }
+        }
+        int st = dev_alloc(&plan->d_s1_tiles, n_tiles, plan);
+        cudaError_t eb = cudaSuccess;
+        if (st == TIF_OK) eb = cudaMemcpy(plan->d_s1_tiles, h_tiles, sizeof(uint2) * n_tiles, cudaMemcpyHostToDevice);
+        free(h_base);
+        free(h_tiles);
+        PLAN_TRY(st);
+        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "stage-1 tile table"));
+        plan->s1_tiles_x = tiles_x;
+        plan->s1_tiles_y = tiles_y;
+        plan->s1_staged_tiles = staged;
     }
     cudaFree(d_gx);
     cudaFree(d_gy);
