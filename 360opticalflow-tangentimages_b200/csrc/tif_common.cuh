@@ -30,11 +30,20 @@
 // 128 threads x 765 x 7 x 1024 < 2^32: a block's partial sum fits a native 32-bit shared atomic
 #define TIF_NW_FIXED_SCALE 1024.0f
 
-// stage-1 staging: a block owns a TIF_S1_TILE x TIF_S1_TILE patch of the tangent stack; the ERP rows its taps
-// touch are bulk-copied (cp.async.bulk + mbarrier) into one of TIF_S1_STAGES shared-memory buffers per image
+// stage-1 staging: a block owns a TIF_S1_TILE x TIF_S1_TILE patch of the tangent stack; the ERP box its taps touch
+// (at most TIF_S1_STAGE_BYTES per image) is copied asynchronously (cp.async) into shared memory, TIF_S1_IPS images
+// per pipeline stage, TIF_S1_STAGES stages
 #define TIF_S1_TILE 16
-#define TIF_S1_STAGE_BYTES 6144
-#define TIF_S1_STAGES 3
+#ifndef TIF_S1_STAGE_BYTES
+#define TIF_S1_STAGE_BYTES 4096
+#endif
+#ifndef TIF_S1_IPS
+#define TIF_S1_IPS 1
+#endif
+#ifndef TIF_S1_STAGES
+#define TIF_S1_STAGES 4
+#endif
+#define TIF_S1_GROUP_BYTES (TIF_S1_IPS * TIF_S1_STAGE_BYTES)
 
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;

@@ -111,13 +111,17 @@ __device__ __forceinline__ void load_tap_pair_bytes(const uint8_t* __restrict__ 
 #define TIF_FIX_GUARD 0x00000400u
 #endif
 
+// The accumulator carries the rounding half AND the guard: acc = sum + 2^23 + G.  The sample is undecided when the
+// low 24 bits of acc are below 2 G (one AND, 2 G is a power of two); otherwise subtracting G again would not borrow
+// from the top byte, so the top byte of acc itself is the rounded value.
+static_assert((TIF_FIX_GUARD & (TIF_FIX_GUARD - 1u)) == 0u, "TIF_FIX_GUARD must be a power of two");
 __device__ __forceinline__ uint32_t fix_bilinear(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, uint32_t w00,
                                                  uint32_t w01, uint32_t w10, uint32_t w11) {
-    return p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + TIF_FIX_HALF;
+    return p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (TIF_FIX_HALF + TIF_FIX_GUARD);
 }
 
 __device__ __forceinline__ bool fix_undecided(uint32_t acc) {
-    return ((acc + TIF_FIX_GUARD) & 0x00ffffffu) < 2u * TIF_FIX_GUARD;
+    return (acc & (0x01000000u - 2u * TIF_FIX_GUARD)) == 0u;
 }
 
 // one RGBA output pixel from the two aligned tap pairs (R: bytes 0,3 of lo; G: byte 1 of lo, byte 0 of hi;
@@ -275,7 +279,7 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
                  const uint2* __restrict__ s1_tiles, int tiles_x, const uint8_t* __restrict__ erp,
                  uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w, int batch,
                  int batch_per_block_row, int full_face) {
-    __shared__ __align__(128) uint8_t stage[TIF_S1_STAGES][TIF_S1_STAGE_BYTES];
+    __shared__ __align__(128) uint8_t stage[TIF_S1_STAGES][TIF_S1_GROUP_BYTES];
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int trow = ty * TIF_S1_TILE + tid / TIF_S1_TILE, tcol = tx * TIF_S1_TILE + tid % TIF_S1_TILE;
@@ -299,19 +303,28 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
     const uint32_t r0 = c0 / cpr, r1 = c1 / cpr;
     const uint8_t* img = erp + (size_t)b_begin * image_bytes + desc.x;
     const uint32_t src0 = r0 * row_bytes + (c0 - r0 * cpr) * 16u, src1 = r1 * row_bytes + (c1 - r1 * cpr) * 16u;
-    auto issue = [&](int i) {       // image b_begin + i -> buffer i % STAGES
-        if (i < n_img) {
-            const uint32_t buf = stage0 + (uint32_t)(i % TIF_S1_STAGES) * TIF_S1_STAGE_BYTES;
-            const uint8_t* g = img + (size_t)i * image_bytes;
-            if (have0) cp_async16(buf + c0 * 16u, g + src0);
-            if (have1) cp_async16(buf + c1 * 16u, g + src1);
+    const uint32_t d0 = stage0 + c0 * 16u, d1 = stage0 + c1 * 16u;
+    // a stage holds the boxes of TIF_S1_IPS consecutive images: one barrier per group, and the blends of a
+    // group are independent instruction chains
+    const int n_grp = (n_img + TIF_S1_IPS - 1) / TIF_S1_IPS;
+    const uint8_t* gnext = img;     // first image of the next group of copies
+    int inext = 0;                  // its index
+    auto copy_group = [&](uint32_t off) {
+#pragma unroll
+        for (int k = 0; k < TIF_S1_IPS; ++k) {
+            if (inext + k < n_img) {
+                if (have0) cp_async16(d0 + off + (uint32_t)k * TIF_S1_STAGE_BYTES, gnext + (size_t)k * image_bytes + src0);
+                if (have1) cp_async16(d1 + off + (uint32_t)k * TIF_S1_STAGE_BYTES, gnext + (size_t)k * image_bytes + src1);
+            }
         }
-        cp_async_commit();          // one group per image, empty or not: the wait below counts groups
+        cp_async_commit();          // one commit group per image group, empty or not: the waits count groups
+        gnext += (size_t)TIF_S1_IPS * image_bytes;
+        inext += TIF_S1_IPS;
     };
 #pragma unroll
-    for (int i = 0; i < TIF_S1_STAGES - 1; ++i) issue(i);
+    for (int g = 0; g < TIF_S1_STAGES - 1; ++g) copy_group((uint32_t)g * TIF_S1_GROUP_BYTES);
 
-    uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = 0u, sh = 0u;
+    uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = stage0, sh = 0u;
     bool blend = false;
     if (valid) {
         bs = s1_base[p];
@@ -328,35 +341,52 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
         const uint32_t t = (bs & 0x7fffffffu) * 3u - desc.x;
         const uint32_t dy = t / row_bytes, dxb = t - dy * row_bytes;
         const uint32_t o = dy * pitch + dxb;
-        tap = o & ~3u;              // pitch is a multiple of 16: both rows share the byte phase
+        tap = stage0 + (o & ~3u);   // pitch is a multiple of 16: both rows share the byte phase
         sh = (o & 3u) * 8u;
     }
     uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
-    int s = 0;
-    for (int i = 0; i < n_img; ++i, o4 += n_pix) {
-        cp_async_wait<TIF_S1_STAGES - 2>();     // this thread's chunks of image i have landed
-        __syncthreads();                        // ... everyone's have, and everyone is done with image i - 1
-        issue(i + TIF_S1_STAGES - 1);           // refills the buffer of image i - 1
-        const uint32_t buf = stage0 + (uint32_t)s * TIF_S1_STAGE_BYTES;
-        if (++s == TIF_S1_STAGES) s = 0;
-        if (blend) {
-            const uint32_t a0 = buf + tap, a1 = a0 + pitch;
-            const uint32_t r00 = lds_u32(a0), r01 = lds_u32(a0 + 4u), r02 = lds_u32(a0 + 8u);
-            const uint32_t r10 = lds_u32(a1), r11 = lds_u32(a1 + 4u), r12 = lds_u32(a1 + 8u);
-            const uint32_t lo0 = __funnelshift_r(r00, r01, sh), hi0 = __funnelshift_r(r01, r02, sh);
-            const uint32_t lo1 = __funnelshift_r(r10, r11, sh), hi1 = __funnelshift_r(r11, r12, sh);
-            uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
-            uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
-            uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
-            if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
-                const double2 fr = s1_frac64[p];        // rare: re-read instead of keeping four registers live
-                ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
-                ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
-                ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
+    // the group loop is unrolled over the stages: buffer offsets are immediates
+    for (int g0 = 0; g0 < n_grp; g0 += TIF_S1_STAGES) {
+#pragma unroll
+        for (int st = 0; st < TIF_S1_STAGES; ++st) {
+            const int g = g0 + st;
+            if (g >= n_grp) break;
+            cp_async_wait<TIF_S1_STAGES - 2>();     // this thread's chunks of group g have landed
+            __syncthreads();                        // ... everyone's have, and everyone is done with group g - 1
+            copy_group((uint32_t)((st + TIF_S1_STAGES - 1) % TIF_S1_STAGES) * TIF_S1_GROUP_BYTES);   // refills the buffer of group g - 1
+            if (blend) {
+                uint32_t lo0[TIF_S1_IPS], hi0[TIF_S1_IPS], lo1[TIF_S1_IPS], hi1[TIF_S1_IPS];
+#pragma unroll
+                for (int k = 0; k < TIF_S1_IPS; ++k) {
+                    const uint32_t a0 = tap + (uint32_t)st * TIF_S1_GROUP_BYTES + (uint32_t)k * TIF_S1_STAGE_BYTES, a1 = a0 + pitch;
+                    const uint32_t r00 = lds_u32(a0), r01 = lds_u32(a0 + 4u), r02 = lds_u32(a0 + 8u);
+                    const uint32_t r10 = lds_u32(a1), r11 = lds_u32(a1 + 4u), r12 = lds_u32(a1 + 8u);
+                    lo0[k] = __funnelshift_r(r00, r01, sh);
+                    hi0[k] = __funnelshift_r(r01, r02, sh);
+                    lo1[k] = __funnelshift_r(r10, r11, sh);
+                    hi1[k] = __funnelshift_r(r11, r12, sh);
+                }
+#pragma unroll
+                for (int k = 0; k < TIF_S1_IPS; ++k) {
+                    if (g * TIF_S1_IPS + k < n_img) {
+                        uint32_t ar = fix_bilinear(TIF_BYTE(lo0[k], 0), TIF_BYTE(lo0[k], 3), TIF_BYTE(lo1[k], 0), TIF_BYTE(lo1[k], 3), w00, w01, w10, w11);
+                        uint32_t ag = fix_bilinear(TIF_BYTE(lo0[k], 1), TIF_BYTE(hi0[k], 0), TIF_BYTE(lo1[k], 1), TIF_BYTE(hi1[k], 0), w00, w01, w10, w11);
+                        uint32_t ab = fix_bilinear(TIF_BYTE(lo0[k], 2), TIF_BYTE(hi0[k], 1), TIF_BYTE(lo1[k], 2), TIF_BYTE(hi1[k], 1), w00, w01, w10, w11);
+                        if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
+                            const double2 fr = s1_frac64[p];        // rare: re-read instead of keeping four registers live
+                            ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 0), TIF_BYTE(lo0[k], 3), TIF_BYTE(lo1[k], 0), TIF_BYTE(lo1[k], 3), fr.x, fr.y)) << 24;
+                            ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 1), TIF_BYTE(hi0[k], 0), TIF_BYTE(lo1[k], 1), TIF_BYTE(hi1[k], 0), fr.x, fr.y)) << 24;
+                            ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 2), TIF_BYTE(hi0[k], 1), TIF_BYTE(lo1[k], 2), TIF_BYTE(hi1[k], 1), fr.x, fr.y)) << 24;
+                        }
+                        o4[(size_t)k * n_pix] = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
+                    }
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int k = 0; k < TIF_S1_IPS; ++k)
+                    if (g * TIF_S1_IPS + k < n_img) o4[(size_t)k * n_pix] = 0x00ffffffu;          // RGB 255, alpha 0
             }
-            *o4 = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
-        } else if (valid) {
-            *o4 = 0x00ffffffu;          // RGB 255, alpha 0
+            o4 += (size_t)TIF_S1_IPS * n_pix;
         }
     }
     cp_async_wait<0>();
