@@ -575,17 +575,30 @@ __device__ __noinline__ void lift_precise(const LiftFace* F, int tcol, int trow,
 //   delta_theta = atan2(E, rho)     delta_colat = atan2(-N + E^2 cos / (h + rho), ...)
 // see small angles and float32 keeps ~1e-7 relative precision on the displacement itself.
 // The result is (delta_theta W / 2 pi, delta_colat H / pi); k_gather adds the pixel's own ERP position.
+// launch shape per variant, measured on B200: the sampling variants spill at 64 registers, 128 x 7 gives them 72
 #ifndef TIF_LIFT_MIN_BLOCKS
 #define TIF_LIFT_MIN_BLOCKS 4
 #endif
 #ifndef TIF_LIFT_THREADS
 #define TIF_LIFT_THREADS 256
 #endif
+#ifndef TIF_LIFT_NW_MIN_BLOCKS
+#define TIF_LIFT_NW_MIN_BLOCKS 7
+#endif
+#ifndef TIF_LIFT_NW_THREADS
+#define TIF_LIFT_NW_THREADS 128
+#endif
+#define TIF_LIFT_THREADS_OF(SAMPLE) ((SAMPLE) ? TIF_LIFT_NW_THREADS : TIF_LIFT_THREADS)
+#define TIF_LIFT_BLOCKS_OF(SAMPLE) ((SAMPLE) ? TIF_LIFT_NW_MIN_BLOCKS : TIF_LIFT_MIN_BLOCKS)
+#ifndef TIF_LIFT_GROUP
+#define TIF_LIFT_GROUP 2
+#endif
+static_assert(TIF_BATCH_CHUNK % TIF_LIFT_GROUP == 0, "the chunk is split into whole groups");
 // SAMPLE 0: displacement only.  SAMPLE 1: + float bilinear sample of the target image (normwarp: the reference
 // converts the images to float64 first).  SAMPLE 2: + the sample rounded half-up to uint8 (cubemap stage: its
 // images stay uint8, so scipy rounds every sample, projection.py:103-104).
 template <int SAMPLE>
-__global__ void __launch_bounds__(TIF_LIFT_THREADS, TIF_LIFT_MIN_BLOCKS)
+__global__ void __launch_bounds__(TIF_LIFT_THREADS_OF(SAMPLE), TIF_LIFT_BLOCKS_OF(SAMPLE))
 k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
@@ -660,99 +673,131 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     // one or two adjacent sectors instead of one sector per image
     const size_t rec0 = ((size_t)blockIdx.y * n_tangent + p) * TIF_BATCH_CHUNK;
 
+    // The images of the chunk are handled in groups of TIF_LIFT_GROUP: first the end points of the whole group,
+    // then all its target-image tap loads, then the blends -- the tap gathers are L2-latency bound, and issued
+    // back to back they overlap instead of each waiting behind the lift arithmetic of its own image.
+    constexpr int G = NW ? TIF_LIFT_GROUP : 1;
+    constexpr unsigned kNoSample = 0xffffffffu;
 #pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
-        const int b = b0 + bb;
-        if (b >= batch) break;
-        const float2 uv = uvs[bb];
-        const float dx = uv.x * kxf, dy = -uv.y * kyf;
-        const float E = fmaf(dy, e1, dx * e2);
-        const float N = fmaf(dy, n1, dx * n2c);
-        const float U = fmaf(dy, u1, fmaf(dx, u2, u0));
-        const float rm = fmaf(U, cp, -N * sp);          // horizontal part in the pixel's meridian plane
-        const float z = fmaf(U, sp, N * cp);            // part along the polar axis
-        const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
-        float disp_x, disp_y, fx, fy;
-        int xi, yi;
-        if (polar_pixel || h < 0.1f * fabsf(z)) {       // pixel or end point within ~5.7 degrees of a pole
-            float disp[2];
-            double end[2];
-            lift_precise(&F, tcol, trow, uv.x, uv.y, erp_w, erp_h, NW ? s1_ex : nullptr, s1_ey, p, disp, end);
-            disp_x = disp[0];
-            disp_y = disp[1];
-            if (NW) {
-                const double fax = floor(end[0]), fay = floor(end[1]);
-                xi = (int)fax;
-                yi = (int)fay;
-                fx = (float)(end[0] - fax);
-                fy = (float)(end[1] - fay);
-            }
-        } else {
-            const float dtheta = atan2_fast(E, rm);
-            // h sin(lat) - z cos(lat) = -N + (h - rm) sin(lat), and h - rm = E^2 / (h + rm)
-            const float yc = rm > 0.0f ? fmaf(E * E, sp * rcp_newton(h + rm), -N) : fmaf(h, sp, -z * cp);
-            const float xc = fmaf(z, sp, h * cp);
-            const float dcolat = atan2_fast(yc, xc);
-            disp_x = dtheta * u_scale;
-            disp_y = dcolat * v_scale;
-            if (NW) {
-                int di, dj;
-                float df, dg;
-                split_floor(disp_x, di, df);
-                split_floor(disp_y, dj, dg);
-                xi = exi + di;
-                yi = eyi + dj;
-                fx = exf + df;
-                fy = eyf + dg;
-                if (fx >= 1.0f) { fx -= 1.0f; xi += 1; }
-                if (fy >= 1.0f) { fy -= 1.0f; yi += 1; }
-            }
-        }
-        if (!NW) {
-            reinterpret_cast<float2*>(records)[rec0 + bb] = make_float2(disp_x, disp_y);
-            continue;
-        }
-        // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
-        // periodic (the seam conventions only move the end point by whole image widths), the gap (W-1, W) and
-        // anything outside [0, H-1] vertically reads 255 outright
-        // own position in [-0.5, W - 0.5) plus a displacement of at most half a turn: one fold brings x into [0, W)
-        if (xi >= erp_w) xi -= erp_w;
-        else if (xi < 0) xi += erp_w;
-        float t0, t1, t2;
-        const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx == 0.0f));
-        const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy == 0.0f));
-        if (!(x_ok & y_ok)) {
-            t0 = t1 = t2 = 255.0f;
-        } else {
-            if (xi == erp_w - 1) { xi = erp_w - 2; fx = 1.0f; }
-            if (yi == erp_h - 1) { yi = erp_h - 2; fy = 1.0f; }
-            const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
-            const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
-            const uint8_t* r0 = tar_chunk + ((unsigned)bb * image_bytes + (unsigned)((yi * erp_w + xi) * 3));
-            const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
-            uint32_t lo0, hi0, lo1, hi1;
-            if ((b == batch - 1) & (yi == erp_h - 2) & (xi >= erp_w - 6)) {     // wide loads could leave the buffer
-                load_tap_pair_bytes(r0, lo0, hi0);
-                load_tap_pair_bytes(r1, lo1, hi1);
+    for (int g0 = 0; g0 < TIF_BATCH_CHUNK; g0 += G) {
+        float disp_x[G], disp_y[G], fx[G], fy[G];
+        unsigned off[G];             // byte offset of the first tap in the chunk of target images
+        bool tail[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int bb = g0 + j, b = b0 + bb;
+            off[j] = kNoSample;
+            tail[j] = false;
+            disp_x[j] = disp_y[j] = fx[j] = fy[j] = 0.0f;
+            if (b >= batch) continue;
+            const float2 uv = uvs[bb];
+            const float dx = uv.x * kxf, dy = -uv.y * kyf;
+            const float E = fmaf(dy, e1, dx * e2);
+            const float N = fmaf(dy, n1, dx * n2c);
+            const float U = fmaf(dy, u1, fmaf(dx, u2, u0));
+            const float rm = fmaf(U, cp, -N * sp);          // horizontal part in the pixel's meridian plane
+            const float z = fmaf(U, sp, N * cp);            // part along the polar axis
+            const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
+            int xi = 0, yi = 0;
+            if (polar_pixel || h < 0.1f * fabsf(z)) {       // pixel or end point within ~5.7 degrees of a pole
+                float disp[2];
+                double end[2];
+                lift_precise(&F, tcol, trow, uv.x, uv.y, erp_w, erp_h, NW ? s1_ex : nullptr, s1_ey, p, disp, end);
+                disp_x[j] = disp[0];
+                disp_y[j] = disp[1];
+                if (NW) {
+                    const double fax = floor(end[0]), fay = floor(end[1]);
+                    xi = (int)fax;
+                    yi = (int)fay;
+                    fx[j] = (float)(end[0] - fax);
+                    fy[j] = (float)(end[1] - fay);
+                }
             } else {
-                load_tap_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
-                load_tap_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
+                const float dtheta = atan2_fast(E, rm);
+                // h sin(lat) - z cos(lat) = -N + (h - rm) sin(lat), and h - rm = E^2 / (h + rm)
+                const float yc = rm > 0.0f ? fmaf(E * E, sp * rcp_newton(h + rm), -N) : fmaf(h, sp, -z * cp);
+                const float xc = fmaf(z, sp, h * cp);
+                const float dcolat = atan2_fast(yc, xc);
+                disp_x[j] = dtheta * u_scale;
+                disp_y[j] = dcolat * v_scale;
+                if (NW) {
+                    int di, dj;
+                    float df, dg;
+                    split_floor(disp_x[j], di, df);
+                    split_floor(disp_y[j], dj, dg);
+                    xi = exi + di;
+                    yi = eyi + dj;
+                    fx[j] = exf + df;
+                    fy[j] = eyf + dg;
+                    if (fx[j] >= 1.0f) { fx[j] -= 1.0f; xi += 1; }
+                    if (fy[j] >= 1.0f) { fy[j] -= 1.0f; yi += 1; }
+                }
             }
-            t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
-            t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
-            t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
+            if (!NW) {
+                reinterpret_cast<float2*>(records)[rec0 + bb] = make_float2(disp_x[j], disp_y[j]);
+                continue;
+            }
+            // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
+            // periodic (the seam conventions only move the end point by whole image widths), the gap (W-1, W) and
+            // anything outside [0, H-1] vertically reads 255 outright
+            // own position in [-0.5, W - 0.5) plus a displacement of at most half a turn: one fold brings x into [0, W)
+            if (xi >= erp_w) xi -= erp_w;
+            else if (xi < 0) xi += erp_w;
+            const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx[j] == 0.0f));
+            const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy[j] == 0.0f));
+            if (x_ok & y_ok) {
+                if (xi == erp_w - 1) { xi = erp_w - 2; fx[j] = 1.0f; }
+                if (yi == erp_h - 1) { yi = erp_h - 2; fy[j] = 1.0f; }
+                off[j] = (unsigned)bb * image_bytes + (unsigned)((yi * erp_w + xi) * 3);
+                tail[j] = (b == batch - 1) & (yi == erp_h - 2) & (xi >= erp_w - 6);     // wide loads could leave the buffer
+            }
         }
-        if (SAMPLE == 2) {          // scipy uint8 output: trunc(t + 0.5)
-            t0 = floorf(t0 + 0.5f);
-            t1 = floorf(t1 + 0.5f);
-            t2 = floorf(t2 + 0.5f);
+        if (!NW) continue;
+        RawPair raw0[G], raw1[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            raw0[j].w0 = raw0[j].w1 = raw0[j].w2 = raw1[j].w0 = raw1[j].w1 = raw1[j].w2 = 0u;
+            if (off[j] != kNoSample && !tail[j]) {
+                const uint8_t* r0 = tar_chunk + off[j];
+                const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
+                raw0[j] = load_raw_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3));
+                raw1[j] = load_raw_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3));
+            }
         }
-        // 21-bit fixed point (x 8192, round to nearest) through the 2^23 mantissa trick: no XU conversions
-        const uint32_t q0 = __float_as_uint(fmaf(t0, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
-        const uint32_t q1 = __float_as_uint(fmaf(t1, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
-        const uint32_t q2 = __float_as_uint(fmaf(t2, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
-        reinterpret_cast<uint4*>(records)[rec0 + bb] =
-            make_uint4(__float_as_uint(disp_x), __float_as_uint(disp_y), q0 | (q1 << 21), (q1 >> 11) | (q2 << 10));
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int bb = g0 + j;
+            if (b0 + bb >= batch) continue;
+            float t0 = 255.0f, t1 = 255.0f, t2 = 255.0f;
+            if (off[j] != kNoSample) {
+                const uint8_t* r0 = tar_chunk + off[j];
+                const uint8_t* r1 = r0 + (unsigned)(erp_w * 3);
+                uint32_t lo0, hi0, lo1, hi1;
+                if (tail[j]) {
+                    load_tap_pair_bytes(r0, lo0, hi0);
+                    load_tap_pair_bytes(r1, lo1, hi1);
+                } else {
+                    align_pair(raw0[j], (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
+                    align_pair(raw1[j], (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
+                }
+                const float wx0 = 1.0f - fx[j], wy0 = 1.0f - fy[j];
+                const float w00 = wy0 * wx0, w01 = wy0 * fx[j], w10 = fy[j] * wx0, w11 = fy[j] * fx[j];
+                t0 = byte_f(lo0, 0) * w00 + byte_f(lo0, 3) * w01 + byte_f(lo1, 0) * w10 + byte_f(lo1, 3) * w11;
+                t1 = byte_f(lo0, 1) * w00 + byte_f(hi0, 0) * w01 + byte_f(lo1, 1) * w10 + byte_f(hi1, 0) * w11;
+                t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
+            }
+            if (SAMPLE == 2) {          // scipy uint8 output: trunc(t + 0.5)
+                t0 = floorf(t0 + 0.5f);
+                t1 = floorf(t1 + 0.5f);
+                t2 = floorf(t2 + 0.5f);
+            }
+            // 21-bit fixed point (x 8192, round to nearest) through the 2^23 mantissa trick: no XU conversions
+            const uint32_t q0 = __float_as_uint(fmaf(t0, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
+            const uint32_t q1 = __float_as_uint(fmaf(t1, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
+            const uint32_t q2 = __float_as_uint(fmaf(t2, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;
+            reinterpret_cast<uint4*>(records)[rec0 + bb] =
+                make_uint4(__float_as_uint(disp_x[j]), __float_as_uint(disp_y[j]), q0 | (q1 << 21), (q1 >> 11) | (q2 << 10));
+        }
     }
 }
 
@@ -1001,6 +1046,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
     const int n_ref = (int)plan->referenced_tangent_pixels;
     const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), by);
+    const dim3 lift_nw_grid((unsigned)((n_ref + TIF_LIFT_NW_THREADS - 1) / TIF_LIFT_NW_THREADS), by);
     const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS), by);
     const size_t lift_smem = sizeof(LiftFace) * n_faces;
     const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * n_faces;
@@ -1022,21 +1068,21 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         }
     } else if (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) {
         if (!skip_lift)
-            k_lift<2><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<2><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
                                                              records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) k_gather<4><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
-        if (pass_mask & 1) {
-            TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
+        if (pass_mask & (1 | 8)) {
+            if (pass_mask & 1) TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (!skip_lift)
-                k_lift<1><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
+                k_lift<1><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
                                                                     plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch);
             TIF_CUDA_CHECK(cudaGetLastError());
-            k_gather<1><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+            if (pass_mask & 1) k_gather<1><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
         if (pass_mask & 2) k_gather<2><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);

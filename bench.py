@@ -281,15 +281,15 @@ def run_ours(args):
     hw = plan.erp_h * plan.erp_w
     P, Pref = plan.tangent_pixels, plan.referenced_tangent_pixels
     sf, nw = lib.BLEND_STRAIGHTFORWARD, lib.BLEND_NORMWARP
-    # pass_mask: 1 = lift (+ normwarp face sums), 2 = blend, 4 = skip the lift kernel (reuse the records)
+    # pass_mask: 1 = lift + normwarp face sums, 2 = blend, 4 = skip the lift kernel (reuse the records), 8 = lift only
     kernels = {
         "k_erp2ico": (lambda: ops.erp2ico_out(plan, src, True, tan_src), B * (hw * 3 + P * 4)),
         "k_lift<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 8),
                                     B * (8 * Pref)),
         "k_gather<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 4 | 3),
                                       B * (8 * hw)),
-        "k_lift<normwarp> + k_gather<sums>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 1),
-                                              B * (8 * Pref + 6 * hw)),
+        "k_lift<normwarp>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 8),
+                             B * (8 * Pref + 3 * hw)),
         "k_gather<sums>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 1 | 4), B * (3 * hw)),
         "k_gather<blend>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 2), B * (8 * hw)),
     }
@@ -308,7 +308,7 @@ def run_ours(args):
         ktimes[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
                         "frac": nbytes / (ms * 1e-3) / 1e9 / peak_gbs}
     used = ["k_erp2ico"] + (["k_lift<straightforward>", "k_gather<straightforward>"] if blend == sf
-                            else ["k_lift<normwarp> + k_gather<sums>", "k_gather<blend>"])
+                            else ["k_lift<normwarp>", "k_gather<sums>", "k_gather<blend>"])
     weight = {k: ktimes[k]["ms"] * (2 if k == "k_erp2ico" else 1) for k in used}
     dominant = max(weight, key=weight.get)
     traffic = None

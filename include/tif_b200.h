@@ -172,7 +172,8 @@ int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_flow /*[B,P,2
 
 /* Profiling aid: the same call restricted to some of its kernels.  pass_mask bit 0: lift the tangent pixels and
  * (normwarp) accumulate the face-global warp-error sums; bit 1: blend using what is already in `scratch`;
- * bit 2: skip the lift kernel and reuse the records of an earlier call.  3 = the call above. */
+ * bit 2: skip the lift kernel and reuse the records of an earlier call; bit 3 alone: the lift kernel only.
+ * 3 = the call above. */
 int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
                             const uint8_t* erp_tar, int batch, int blend, int wrap_around, float* erp_flow,
                             void* scratch, int pass_mask, void* stream);
