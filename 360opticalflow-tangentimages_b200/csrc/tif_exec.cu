@@ -461,6 +461,11 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 #ifndef TIF_GATHER2_MIN_BLOCKS
 #define TIF_GATHER2_MIN_BLOCKS 4
 #endif
+// images per k_gather thread: a divisor of the lift chunk (the records stay interleaved per lift chunk)
+#ifndef TIF_GATHER_IMGS
+#define TIF_GATHER_IMGS 4
+#endif
+static_assert(TIF_BATCH_CHUNK % TIF_GATHER_IMGS == 0, "k_gather groups must not straddle lift chunks");
 #define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
 #define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
 
@@ -593,7 +598,12 @@ __device__ __noinline__ void lift_precise(const LiftFace* F, int tcol, int trow,
 #ifndef TIF_LIFT_GROUP
 #define TIF_LIFT_GROUP 2
 #endif
-static_assert(TIF_BATCH_CHUNK % TIF_LIFT_GROUP == 0, "the chunk is split into whole groups");
+// images per k_lift thread: a divisor of the record chunk TIF_BATCH_CHUNK
+#ifndef TIF_LIFT_IMGS
+#define TIF_LIFT_IMGS 4
+#endif
+static_assert(TIF_BATCH_CHUNK % TIF_LIFT_IMGS == 0, "k_lift groups must not straddle record chunks");
+static_assert(TIF_LIFT_IMGS % TIF_LIFT_GROUP == 0, "the images of a thread are split into whole groups");
 // SAMPLE 0: displacement only.  SAMPLE 1: + float bilinear sample of the target image (normwarp: the reference
 // converts the images to float64 first).  SAMPLE 2: + the sample rounded half-up to uint8 (cubemap stage: its
 // images stay uint8, so scipy rounds every sample, projection.py:103-104).
@@ -625,12 +635,12 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     if (idx >= n_ref) return;
     const int p = __ldg(ref_list + idx);
     const int trow = p / tangent_w, tcol = p - trow * tangent_w;
-    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+    const int b0 = blockIdx.y * TIF_LIFT_IMGS;
     const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
     // all flows of the chunk are requested before anything depends on them (the kernel is latency bound)
-    float2 uvs[TIF_BATCH_CHUNK];
+    float2 uvs[TIF_LIFT_IMGS];
 #pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb)
+    for (int bb = 0; bb < TIF_LIFT_IMGS; ++bb)
         uvs[bb] = (b0 + bb < batch) ? __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p)) : make_float2(0.0f, 0.0f);
     const LiftFace& F = sh_face[__ldg(row_face + trow)];
 
@@ -671,7 +681,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     const uint8_t* __restrict__ tar_chunk = NW ? erp_tar + (size_t)b0 * image_bytes : nullptr;
     // records of one tangent pixel are interleaved over the images of the chunk: k_gather fetches them from
     // one or two adjacent sectors instead of one sector per image
-    const size_t rec0 = ((size_t)blockIdx.y * n_tangent + p) * TIF_BATCH_CHUNK;
+    const size_t rec0 = ((size_t)(b0 / TIF_BATCH_CHUNK) * n_tangent + p) * TIF_BATCH_CHUNK + (size_t)(b0 % TIF_BATCH_CHUNK);
 
     // The images of the chunk are handled in groups of TIF_LIFT_GROUP: first the end points of the whole group,
     // then all its target-image tap loads, then the blends -- the tap gathers are L2-latency bound, and issued
@@ -679,7 +689,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     constexpr int G = NW ? TIF_LIFT_GROUP : 1;
     constexpr unsigned kNoSample = 0xffffffffu;
 #pragma unroll
-    for (int g0 = 0; g0 < TIF_BATCH_CHUNK; g0 += G) {
+    for (int g0 = 0; g0 < TIF_LIFT_IMGS; g0 += G) {
         float disp_x[G], disp_y[G], fx[G], fy[G];
         unsigned off[G];             // byte offset of the first tap in the chunk of target images
         bool tail[G];
@@ -822,12 +832,13 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     int* sh_offset = reinterpret_cast<int*>(smem_raw);                       // [F] first pixel of each face
     unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_offset + n_faces);      // MODE 1: [CHUNK][F] partial sums
     float* sh_inv_mean = reinterpret_cast<float*>(sh_offset + n_faces);      // MODE 2: [CHUNK][F] 1 / (3 mean)
-    const int b0 = blockIdx.y * TIF_BATCH_CHUNK;
+    const int b0 = blockIdx.y * TIF_GATHER_IMGS;         // first image of this thread's group
+    const unsigned bsub = (unsigned)(b0 % TIF_BATCH_CHUNK);   // its position inside the lift chunk
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) sh_offset[f] = faces[f].pix_offset;
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) sh_sum[i] = 0u;
+        for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x) sh_sum[i] = 0u;
     } else if (MODE == 2) {
-        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
+        for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x) {
             const int bb = i / n_faces, f = i - bb * n_faces;
             float inv = 0.0f;
             if (b0 + bb < batch) {
@@ -847,10 +858,10 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     const int pix = live ? r * erp_w + c : 0;
     const int cnt = live ? (int)s2_count[pix] : 0;
     const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
-    float acc_u[TIF_BATCH_CHUNK], acc_v[TIF_BATCH_CHUNK], acc_w[TIF_BATCH_CHUNK];
-    float sp[TIF_BATCH_CHUNK][3];
+    float acc_u[TIF_GATHER_IMGS], acc_v[TIF_GATHER_IMGS], acc_w[TIF_GATHER_IMGS];
+    float sp[TIF_GATHER_IMGS][3];
 #pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+    for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
         acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
         sp[bb][0] = sp[bb][1] = sp[bb][2] = 0.0f;
     }
@@ -858,7 +869,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     constexpr bool USES_IMAGES = (MODE == 1 || MODE == 2 || MODE == 4);
     if (USES_IMAGES && live) {
 #pragma unroll
-        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
             if (b0 + bb < batch) {
                 const uint8_t* q = erp_src + (size_t)b0 * image_bytes + ((unsigned)bb * image_bytes + (unsigned)pix * 3u);
                 sp[bb][0] = (float)__ldg(q);
@@ -867,8 +878,8 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             }
         }
     }
-    const float2* __restrict__ disp_chunk = reinterpret_cast<const float2*>(records) + (size_t)b0 * n_tangent;
-    const uint4* __restrict__ rec_chunk = reinterpret_cast<const uint4*>(records) + (size_t)b0 * n_tangent;   // b0 = chunk * CHUNK
+    const float2* __restrict__ disp_chunk = reinterpret_cast<const float2*>(records) + (size_t)(b0 - (int)bsub) * n_tangent;
+    const uint4* __restrict__ rec_chunk = reinterpret_cast<const uint4*>(records) + (size_t)(b0 - (int)bsub) * n_tangent;   // b0 = chunk * CHUNK
 
     const int max_cnt = (MODE == 1) ? __reduce_max_sync(0xffffffffu, cnt) : cnt;
     uint32_t e_next = 0u;
@@ -889,17 +900,17 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
         const float mult = (float)TIF_E_MULT(e);
         // all records of the chunk are requested before any is used (one or two adjacent sectors)
-        float2 disp[TIF_BATCH_CHUNK];
-        uint2 rgb[TIF_BATCH_CHUNK];
+        float2 disp[TIF_GATHER_IMGS];
+        uint2 rgb[TIF_GATHER_IMGS];
 #pragma unroll
-        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
             disp[bb] = make_float2(0.0f, 0.0f);
             rgb[bb] = make_uint2(0u, 0u);
             if (has && b0 + bb < batch) {
                 if (!USES_IMAGES) {
-                    disp[bb] = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
+                    disp[bb] = __ldg(disp_chunk + (tpix * TIF_BATCH_CHUNK + bsub + (unsigned)bb));
                 } else {
-                    const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + (unsigned)bb));
+                    const uint4 rec = __ldg(rec_chunk + (tpix * TIF_BATCH_CHUNK + bsub + (unsigned)bb));
                     disp[bb] = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
                     rgb[bb] = make_uint2(rec.z, rec.w);
                 }
@@ -914,7 +925,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             uniform = __all_sync(0xffffffffu, (!has) || f == f0) && __shfl_sync(0xffffffffu, (int)has, 0);
         }
 #pragma unroll
-        for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+        for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
             const int b = b0 + bb;
             if (b >= batch) break;
             float fu = disp[bb].x + sn.x;        // end point minus this ERP pixel, the short way round
@@ -979,7 +990,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 
     if (MODE == 1) {
         __syncthreads();
-        for (int i = threadIdx.x; i < TIF_BATCH_CHUNK * n_faces; i += blockDim.x) {
+        for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x) {
             const int bb = i / n_faces, f = i - bb * n_faces;
             if (b0 + bb < batch && sh_sum[i]) atomicAdd(&nw_sums[(size_t)(b0 + bb) * n_faces + f], (unsigned long long)sh_sum[i]);
         }
@@ -988,7 +999,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     if (!live) return;
     const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
 #pragma unroll
-    for (int bb = 0; bb < TIF_BATCH_CHUNK; ++bb) {
+    for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
         const int b = b0 + bb;
         if (b >= batch) break;
         float u = acc_u[bb], v = acc_v[bb];
@@ -1045,11 +1056,13 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     unsigned long long* nw_sums = (unsigned long long*)scratch;
     void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
     const int n_ref = (int)plan->referenced_tangent_pixels;
-    const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), by);
-    const dim3 lift_nw_grid((unsigned)((n_ref + TIF_LIFT_NW_THREADS - 1) / TIF_LIFT_NW_THREADS), by);
-    const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS), by);
+    const unsigned lift_by = (unsigned)((batch + TIF_LIFT_IMGS - 1) / TIF_LIFT_IMGS);
+    const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), lift_by);
+    const dim3 lift_nw_grid((unsigned)((n_ref + TIF_LIFT_NW_THREADS - 1) / TIF_LIFT_NW_THREADS), lift_by);
+    const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS),
+                           (unsigned)((batch + TIF_GATHER_IMGS - 1) / TIF_GATHER_IMGS));
     const size_t lift_smem = sizeof(LiftFace) * n_faces;
-    const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_BATCH_CHUNK * n_faces;
+    const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_GATHER_IMGS * n_faces;
 #define GATHER_ARGS                                                                                                  \
     plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
         erp_src, nw_sums, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
