@@ -811,6 +811,12 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     }
 }
 
+__device__ __forceinline__ float exp2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // shared-memory reduction without a return value (and without the compiler's warp-aggregation wrapper)
 __device__ __forceinline__ void red_shared_add(unsigned* addr, unsigned val) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)), "r"(val) : "memory");
@@ -831,7 +837,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* sh_offset = reinterpret_cast<int*>(smem_raw);                       // [F] first pixel of each face
     unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_offset + n_faces);      // MODE 1: [CHUNK][F] partial sums
-    float* sh_inv_mean = reinterpret_cast<float*>(sh_offset + n_faces);      // MODE 2: [CHUNK][F] 1 / (3 mean)
+    float* sh_inv_mean = reinterpret_cast<float*>(sh_offset + n_faces);      // MODE 2: [CHUNK][F] -log2(e) / (3 mean)
     const int b0 = blockIdx.y * TIF_GATHER_IMGS;         // first image of this thread's group
     const unsigned bsub = (unsigned)(b0 % TIF_BATCH_CHUNK);   // its position inside the lift chunk
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) sh_offset[f] = faces[f].pix_offset;
@@ -845,7 +851,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
                 // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
                 const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
                 const double mean = total / (3.0 * face_mult_sum[f]);
-                inv = (float)(1.0 / (3.0 * mean));
+                inv = (float)(-1.4426950408889634 / (3.0 * mean));       // exp(-x / (3 mean)) = 2^(x inv)
             }
             sh_inv_mean[i] = inv;
         }
@@ -859,7 +865,14 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     const int cnt = live ? (int)s2_count[pix] : 0;
     const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
     float acc_u[TIF_GATHER_IMGS], acc_v[TIF_GATHER_IMGS], acc_w[TIF_GATHER_IMGS];
-    float sp[TIF_GATHER_IMGS][3];
+    // A float with the bits of 1024.0 and a 21-bit fixed-point sample q (x 8192) in its mantissa is 1024 + q / 8192:
+    // the packed target samples become floats with one OR, and the source pixels are kept as 1024 + value, so that
+    // the per-channel difference is a single exact FADD (no I2F, no rescaling multiply)
+    static_assert(TIF_RGB_FIX == 8192.0f, "the exponent trick below assumes 13 fraction bits");
+    constexpr uint32_t kFixExp = 0x44800000u;
+    constexpr uint32_t kQ255 = 255u << 13;                                   // the hard 255 outside the image
+    constexpr uint32_t kLo255 = kQ255 | (kQ255 << 21), kHi255 = (kQ255 >> 11) | (kQ255 << 10);
+    float sp[TIF_GATHER_IMGS][3];          // 1024 + source pixel
 #pragma unroll
     for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
         acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
@@ -872,9 +885,9 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
         for (int bb = 0; bb < TIF_GATHER_IMGS; ++bb) {
             if (b0 + bb < batch) {
                 const uint8_t* q = erp_src + (size_t)b0 * image_bytes + ((unsigned)bb * image_bytes + (unsigned)pix * 3u);
-                sp[bb][0] = (float)__ldg(q);
-                sp[bb][1] = (float)__ldg(q + 1);
-                sp[bb][2] = (float)__ldg(q + 2);
+                sp[bb][0] = __uint_as_float(kFixExp + ((uint32_t)__ldg(q) << 13));
+                sp[bb][1] = __uint_as_float(kFixExp + ((uint32_t)__ldg(q + 1) << 13));
+                sp[bb][2] = __uint_as_float(kFixExp + ((uint32_t)__ldg(q + 2) << 13));
             }
         }
     }
@@ -943,13 +956,11 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             }
             float dsum = 0.0f, dnorm2 = 0.0f;
             if (USES_IMAGES) {
-                const uint32_t plo = rgb[bb].x, phi = rgb[bb].y;
-                const uint32_t q0 = plo & 0x1fffffu, q1 = (plo >> 21) | ((phi & 0x3ffu) << 11), q2 = phi >> 10;
-                float t0 = (__uint_as_float(0x4B000000u | q0) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                float t1 = (__uint_as_float(0x4B000000u | q1) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                float t2 = (__uint_as_float(0x4B000000u | q2) - 8388608.0f) * (1.0f / TIF_RGB_FIX);
-                if (!x_ok) t0 = t1 = t2 = 255.0f;
-                const float d0 = t0 - sp[bb][0], d1 = t1 - sp[bb][1], d2 = t2 - sp[bb][2];
+                const uint32_t plo = x_ok ? rgb[bb].x : kLo255, phi = x_ok ? rgb[bb].y : kHi255;
+                const uint32_t q0 = plo & 0x1fffffu, q1 = __funnelshift_r(plo, phi, 21) & 0x1fffffu, q2 = phi >> 10;
+                const float d0 = __uint_as_float(kFixExp | q0) - sp[bb][0];
+                const float d1 = __uint_as_float(kFixExp | q1) - sp[bb][1];
+                const float d2 = __uint_as_float(kFixExp | q2) - sp[bb][2];
                 dsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
                 dnorm2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
             }
@@ -971,7 +982,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
             } else if (MODE == 2) {
                 if (has) {
                     // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
-                    const float w = __expf(-dsum * sh_inv_mean[bb * n_faces + f]);
+                    const float w = exp2_approx(dsum * sh_inv_mean[bb * n_faces + f]);
                     acc_u[bb] = fmaf(fu, w, acc_u[bb]);
                     acc_v[bb] = fmaf(fv, w, acc_v[bb]);
                     acc_w[bb] += w;
