@@ -50,8 +50,9 @@ def main():
         per.setdefault(name, []).append(val)
     total = sum(sum(v) for v in per.values())
     with open(os.path.join(out, "launches_%s.md" % tag), "w") as f:
-        f.write("# ncu launch list (%s)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 2 "
-                "--warmup 3 --no-e2e --no-cpu-baseline --kernel-reps 1 --batch %d`.\nPer-launch times are cold-cache and "
+        f.write("# ncu launch list (%s)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` over `bench.py --steps 2 "
+                "--warmup 1 --batch %d --no-e2e --no-cpu-baseline` (scripts/gpu_record.sh; the plan build and bench.py's "
+                "per-kernel timing loops are part of the list).\nPer-launch times are cold-cache and "
                 "serialised: compare shares, not absolutes.  Raw list: `launches_%s.csv`.\n\n" % (tag, batch, tag))
         f.write("| kernel | launches | total us | mean us | share |\n|---|---|---|---|---|\n")
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):

@@ -13,8 +13,13 @@ def main(path):
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
     pipes = [h for h in hdr if h.startswith("sm__inst_executed_pipe_") and h.endswith(".avg.pct_of_peak_sustained_active")]
+    seen = set()
     for r in rows[2:]:
-        print("## " + r[idx["Kernel Name"]].split("(")[0])
+        name = r[idx["Kernel Name"]].split("(")[0]
+        if name in seen:            # one launch per kernel: repeats of the same launch differ by < 1 %
+            continue
+        seen.add(name)
+        print("## " + name)
         for w in want:
             if w in idx:
                 print("  %-62s %s %s" % (w, r[idx[w]], units[idx[w]]))

@@ -15,7 +15,11 @@ def main(path, top=12):
             cur["hdr"] = r
         elif cur is not None and len(r) == len(cur["hdr"]):
             cur["data"].append(r)
+    seen = set()
     for k in kernels:
+        if k["name"] in seen:       # one launch per kernel
+            continue
+        seen.add(k["name"])
         hdr, data = k["hdr"], k["data"]
         idx = {h: i for i, h in enumerate(hdr)}
         ie = idx["Instructions Executed"]
