@@ -155,6 +155,26 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs NVML reports as local to the GPU, so that the pinned staging buffers of
+    the end-to-end pipeline are first-touched on that NUMA node (the host<->device copies of the ranks otherwise
+    share one node's memory controllers).  Returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def synth_device(torch, plan, batch, seed, device):
     """Synthetic pairs on the device: IID uint8 images, analytic tangent flows."""
     import math
@@ -187,6 +207,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpu_binding = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         # NCCL announces its version on stdout when the communicator is created; stdout carries exactly one
         # JSON line, so route fd 1 to stderr until the first collective has run
@@ -385,7 +406,7 @@ def run_ours(args):
                 "clocks": clocks, "plan": {"build_ms_outside_timed_region": plan_build_ms, "device_bytes": plan.device_bytes,
                                            "max_faces_per_pixel": plan.max_faces_per_pixel, "accepted": plan.accepted_unique,
                                            "referenced_tangent_pixels": Pref},
-                "gather": gather}
+                "gather": gather, "cpus_bound_per_rank": cpu_binding}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
