@@ -355,6 +355,8 @@ class Plan:
         self.accepted_unique = info.accepted_unique
         self.referenced_tangent_pixels = info.referenced_tangent_pixels
         self.device_bytes = info.device_bytes
+        self.stage1_patches = info.stage1_patches
+        self.stage1_staged_patches = info.stage1_staged_patches
 
     def __del__(self):
         try:

@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
 
 TIF_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 BLEND_STRAIGHTFORWARD = 0
 BLEND_NORMWARP = 1
 BLEND_CUBEMAP_INSIDE = 2
@@ -53,6 +53,7 @@ class TifPlanInfo(C.Structure):
         ("n_faces", C.c_int32), ("erp_h", C.c_int32), ("erp_w", C.c_int32), ("tangent_w", C.c_int32),
         ("tangent_pixels", C.c_int64), ("max_faces_per_pixel", C.c_int32),
         ("accepted_unique", C.c_int64), ("referenced_tangent_pixels", C.c_int64), ("device_bytes", C.c_int64),
+        ("stage1_patches", C.c_int64), ("stage1_staged_patches", C.c_int64),
     ]
 
 

@@ -31,19 +31,23 @@
 #define TIF_NW_FIXED_SCALE 1024.0f
 
 // stage-1 staging: a block owns a TIF_S1_TILE x TIF_S1_TILE patch of the tangent stack; the ERP box its taps touch
-// (at most TIF_S1_STAGE_BYTES per image) is copied asynchronously (cp.async) into shared memory, TIF_S1_IPS images
-// per pipeline stage, TIF_S1_STAGES stages
+// is copied asynchronously (cp.async) into a ring of TIF_S1_STAGES shared-memory stages, one image per stage.  The
+// plan picks the stage size (a power of two between the bounds below) from the boxes it finds.  16 KB stages (four
+// chunks per thread) measured slower at every ERP size than 8 KB ones with more patches on the direct path.
 #define TIF_S1_TILE 16
-#ifndef TIF_S1_STAGE_BYTES
-#define TIF_S1_STAGE_BYTES 4096
-#endif
-#ifndef TIF_S1_IPS
-#define TIF_S1_IPS 1
-#endif
 #ifndef TIF_S1_STAGES
 #define TIF_S1_STAGES 4
 #endif
-#define TIF_S1_GROUP_BYTES (TIF_S1_IPS * TIF_S1_STAGE_BYTES)
+#ifndef TIF_S1_MIN_STAGE_BYTES
+#define TIF_S1_MIN_STAGE_BYTES 4096
+#endif
+#ifndef TIF_S1_MAX_STAGE_BYTES
+#define TIF_S1_MAX_STAGE_BYTES 8192
+#endif
+// a stage size is taken when this share of the patches fits it (else the next larger one is tried)
+#ifndef TIF_S1_STAGED_SHARE
+#define TIF_S1_STAGED_SHARE 0.93
+#endif
 
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;
@@ -65,6 +69,7 @@ struct TifPlan {
                                    //  aligned), rows | row bytes << 16}; rows == 0: footprint too large, direct gathers
     int s1_tiles_x, s1_tiles_y;
     int64_t s1_staged_tiles;
+    int s1_stage_bytes;            // stage size of k_erp2ico_staged's shared-memory ring
     // stage 2: per ERP pixel
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order

@@ -272,14 +272,38 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 #define TIF_ERP2ICO_STAGED_MIN_BLOCKS 4
 #endif
 #define TIF_S1_THREADS (TIF_S1_TILE * TIF_S1_TILE)
-static_assert(TIF_S1_STAGE_BYTES <= 2 * 16 * TIF_S1_THREADS, "a thread copies at most two 16-byte chunks per image");
+#define TIF_S1_MAX_CHUNKS (TIF_S1_MAX_STAGE_BYTES / (16 * TIF_S1_THREADS))      // 16-byte chunks a thread copies per image
 
+// one RGBA output pixel from a staged box: a0 = shared address of the aligned word holding the first tap, the
+// second tap row is `pitch` bytes on, `sh` = 8 x byte phase (the same for both rows: pitch is a multiple of 16)
+__device__ __forceinline__ uint32_t erp2ico_staged_pixel(uint32_t a0, uint32_t pitch, uint32_t sh, uint32_t w00,
+                                                         uint32_t w01, uint32_t w10, uint32_t w11,
+                                                         const double2* __restrict__ frac) {
+    const uint32_t a1 = a0 + pitch;
+    const uint32_t r00 = lds_u32(a0), r01 = lds_u32(a0 + 4u), r02 = lds_u32(a0 + 8u);
+    const uint32_t r10 = lds_u32(a1), r11 = lds_u32(a1 + 4u), r12 = lds_u32(a1 + 8u);
+    const uint32_t lo0 = __funnelshift_r(r00, r01, sh), hi0 = __funnelshift_r(r01, r02, sh);
+    const uint32_t lo1 = __funnelshift_r(r10, r11, sh), hi1 = __funnelshift_r(r11, r12, sh);
+    uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
+    uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
+    uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
+    if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
+        const double2 fr = *frac;       // rare: re-read instead of keeping four registers live
+        ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
+        ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
+        ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
+    }
+    return __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
+}
+
+// TIF_S1_STAGES buffers of `stage_bytes` each in dynamic shared memory; the plan picks the stage size from the boxes
+// it found (4 KB at 1280x640, 8 KB at 2K and 4K with the default 480-pixel tangent images)
 __global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
 k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
-                 const uint2* __restrict__ s1_tiles, int tiles_x, const uint8_t* __restrict__ erp,
+                 const uint2* __restrict__ s1_tiles, int tiles_x, uint32_t stage_bytes, const uint8_t* __restrict__ erp,
                  uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w, int batch,
                  int batch_per_block_row, int full_face) {
-    __shared__ __align__(128) uint8_t stage[TIF_S1_STAGES][TIF_S1_GROUP_BYTES];
+    extern __shared__ __align__(128) uint8_t stage[];
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int trow = ty * TIF_S1_TILE + tid / TIF_S1_TILE, tcol = tx * TIF_S1_TILE + tid % TIF_S1_TILE;
@@ -295,34 +319,32 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
     }
     const uint32_t row_bytes = (uint32_t)erp_w * 3u;
     const size_t image_bytes = (size_t)erp_h * row_bytes;
-    const uint32_t stage0 = smem_u32(&stage[0][0]);
-    // the staged box is dense (rows `pitch` apart): chunk c of the box is bytes [16 c, 16 c + 16)
+    const uint32_t stage0 = smem_u32(stage);
+    // the staged box is dense (rows `pitch` apart): chunk c of the box is bytes [16 c, 16 c + 16); thread t copies
+    // the chunks t, t + 256, ...
     const uint32_t cpr = pitch >> 4, n_chunks = n_rows * cpr;
-    const uint32_t c0 = (uint32_t)tid, c1 = (uint32_t)tid + TIF_S1_THREADS;
-    const bool have0 = c0 < n_chunks, have1 = c1 < n_chunks;
-    const uint32_t r0 = c0 / cpr, r1 = c1 / cpr;
-    const uint8_t* img = erp + (size_t)b_begin * image_bytes + desc.x;
-    const uint32_t src0 = r0 * row_bytes + (c0 - r0 * cpr) * 16u, src1 = r1 * row_bytes + (c1 - r1 * cpr) * 16u;
-    const uint32_t d0 = stage0 + c0 * 16u, d1 = stage0 + c1 * 16u;
-    // a stage holds the boxes of TIF_S1_IPS consecutive images: one barrier per group, and the blends of a
-    // group are independent instruction chains
-    const int n_grp = (n_img + TIF_S1_IPS - 1) / TIF_S1_IPS;
-    const uint8_t* gnext = img;     // first image of the next group of copies
-    int inext = 0;                  // its index
-    auto copy_group = [&](uint32_t off) {
+    uint32_t src[TIF_S1_MAX_CHUNKS];
 #pragma unroll
-        for (int k = 0; k < TIF_S1_IPS; ++k) {
-            if (inext + k < n_img) {
-                if (have0) cp_async16(d0 + off + (uint32_t)k * TIF_S1_STAGE_BYTES, gnext + (size_t)k * image_bytes + src0);
-                if (have1) cp_async16(d1 + off + (uint32_t)k * TIF_S1_STAGE_BYTES, gnext + (size_t)k * image_bytes + src1);
-            }
+    for (int j = 0; j < TIF_S1_MAX_CHUNKS; ++j) {
+        const uint32_t c = (uint32_t)tid + (uint32_t)j * TIF_S1_THREADS, r = c / cpr;
+        src[j] = c < n_chunks ? r * row_bytes + (c - r * cpr) * 16u : 0xffffffffu;
+    }
+    const uint32_t d0 = stage0 + (uint32_t)tid * 16u;
+    const uint8_t* gnext = erp + (size_t)b_begin * image_bytes + desc.x;     // box of the next image to copy
+    int inext = 0;                                                           // its index
+    auto copy_image = [&](uint32_t off) {
+        if (inext < n_img) {
+#pragma unroll
+            for (int j = 0; j < TIF_S1_MAX_CHUNKS; ++j)
+                if (src[j] != 0xffffffffu) cp_async16(d0 + off + (uint32_t)j * (16u * TIF_S1_THREADS), gnext + src[j]);
         }
-        cp_async_commit();          // one commit group per image group, empty or not: the waits count groups
-        gnext += (size_t)TIF_S1_IPS * image_bytes;
-        inext += TIF_S1_IPS;
+        cp_async_commit();          // one commit group per image, empty or not: the waits count groups
+        gnext += image_bytes;
+        ++inext;
     };
+    constexpr int STAGES = TIF_S1_STAGES;
 #pragma unroll
-    for (int g = 0; g < TIF_S1_STAGES - 1; ++g) copy_group((uint32_t)g * TIF_S1_GROUP_BYTES);
+    for (int g = 0; g < STAGES - 1; ++g) copy_image((uint32_t)g * stage_bytes);
 
     uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = stage0, sh = 0u;
     bool blend = false;
@@ -341,52 +363,21 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
         const uint32_t t = (bs & 0x7fffffffu) * 3u - desc.x;
         const uint32_t dy = t / row_bytes, dxb = t - dy * row_bytes;
         const uint32_t o = dy * pitch + dxb;
-        tap = stage0 + (o & ~3u);   // pitch is a multiple of 16: both rows share the byte phase
+        tap = stage0 + (o & ~3u);
         sh = (o & 3u) * 8u;
     }
     uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
-    // the group loop is unrolled over the stages: buffer offsets are immediates
-    for (int g0 = 0; g0 < n_grp; g0 += TIF_S1_STAGES) {
+    // the image loop is unrolled over the stages
+    for (int i0 = 0; i0 < n_img; i0 += STAGES) {
 #pragma unroll
-        for (int st = 0; st < TIF_S1_STAGES; ++st) {
-            const int g = g0 + st;
-            if (g >= n_grp) break;
-            cp_async_wait<TIF_S1_STAGES - 2>();     // this thread's chunks of group g have landed
-            __syncthreads();                        // ... everyone's have, and everyone is done with group g - 1
-            copy_group((uint32_t)((st + TIF_S1_STAGES - 1) % TIF_S1_STAGES) * TIF_S1_GROUP_BYTES);   // refills the buffer of group g - 1
-            if (blend) {
-                uint32_t lo0[TIF_S1_IPS], hi0[TIF_S1_IPS], lo1[TIF_S1_IPS], hi1[TIF_S1_IPS];
-#pragma unroll
-                for (int k = 0; k < TIF_S1_IPS; ++k) {
-                    const uint32_t a0 = tap + (uint32_t)st * TIF_S1_GROUP_BYTES + (uint32_t)k * TIF_S1_STAGE_BYTES, a1 = a0 + pitch;
-                    const uint32_t r00 = lds_u32(a0), r01 = lds_u32(a0 + 4u), r02 = lds_u32(a0 + 8u);
-                    const uint32_t r10 = lds_u32(a1), r11 = lds_u32(a1 + 4u), r12 = lds_u32(a1 + 8u);
-                    lo0[k] = __funnelshift_r(r00, r01, sh);
-                    hi0[k] = __funnelshift_r(r01, r02, sh);
-                    lo1[k] = __funnelshift_r(r10, r11, sh);
-                    hi1[k] = __funnelshift_r(r11, r12, sh);
-                }
-#pragma unroll
-                for (int k = 0; k < TIF_S1_IPS; ++k) {
-                    if (g * TIF_S1_IPS + k < n_img) {
-                        uint32_t ar = fix_bilinear(TIF_BYTE(lo0[k], 0), TIF_BYTE(lo0[k], 3), TIF_BYTE(lo1[k], 0), TIF_BYTE(lo1[k], 3), w00, w01, w10, w11);
-                        uint32_t ag = fix_bilinear(TIF_BYTE(lo0[k], 1), TIF_BYTE(hi0[k], 0), TIF_BYTE(lo1[k], 1), TIF_BYTE(hi1[k], 0), w00, w01, w10, w11);
-                        uint32_t ab = fix_bilinear(TIF_BYTE(lo0[k], 2), TIF_BYTE(hi0[k], 1), TIF_BYTE(lo1[k], 2), TIF_BYTE(hi1[k], 1), w00, w01, w10, w11);
-                        if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
-                            const double2 fr = s1_frac64[p];        // rare: re-read instead of keeping four registers live
-                            ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 0), TIF_BYTE(lo0[k], 3), TIF_BYTE(lo1[k], 0), TIF_BYTE(lo1[k], 3), fr.x, fr.y)) << 24;
-                            ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 1), TIF_BYTE(hi0[k], 0), TIF_BYTE(lo1[k], 1), TIF_BYTE(hi1[k], 0), fr.x, fr.y)) << 24;
-                            ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0[k], 2), TIF_BYTE(hi0[k], 1), TIF_BYTE(lo1[k], 2), TIF_BYTE(hi1[k], 1), fr.x, fr.y)) << 24;
-                        }
-                        o4[(size_t)k * n_pix] = __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
-                    }
-                }
-            } else if (valid) {
-#pragma unroll
-                for (int k = 0; k < TIF_S1_IPS; ++k)
-                    if (g * TIF_S1_IPS + k < n_img) o4[(size_t)k * n_pix] = 0x00ffffffu;          // RGB 255, alpha 0
-            }
-            o4 += (size_t)TIF_S1_IPS * n_pix;
+        for (int st = 0; st < STAGES; ++st) {
+            if (i0 + st >= n_img) break;
+            cp_async_wait<STAGES - 2>();            // this thread's chunks of image i have landed
+            __syncthreads();                        // ... everyone's have, and everyone is done with image i - 1
+            copy_image((uint32_t)((st + STAGES - 1) % STAGES) * stage_bytes);      // refills the buffer of image i - 1
+            if (blend) *o4 = erp2ico_staged_pixel(tap + (uint32_t)st * stage_bytes, pitch, sh, w00, w01, w10, w11, s1_frac64 + p);
+            else if (valid) *o4 = 0x00ffffffu;      // RGB 255, alpha 0
+            o4 += n_pix;
         }
     }
     cp_async_wait<0>();
@@ -418,9 +409,10 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         while (srows < batch && (int64_t)tiles * srows < 148 * 16) srows *= 2;
         const int sper = (batch + srows - 1) / srows;
         dim3 sgrid(tiles, (unsigned)((batch + sper - 1) / sper));
-        k_erp2ico_staged<<<sgrid, TIF_S1_TILE * TIF_S1_TILE, 0, (cudaStream_t)stream>>>(
-            plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, erp, tangent_rgba, plan->tangent_pixels,
-            plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
+        const size_t smem = (size_t)TIF_S1_STAGES * plan->s1_stage_bytes;
+        k_erp2ico_staged<<<sgrid, TIF_S1_THREADS, smem, (cudaStream_t)stream>>>(
+            plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, (uint32_t)plan->s1_stage_bytes, erp,
+            tangent_rgba, plan->tangent_pixels, plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
     } else if (aligned)
         k_erp2ico<true><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
                                                                     plan->tangent_pixels, plan->tangent_w, plan->erp_h,

@@ -484,8 +484,10 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         const bool alignable = row_bytes % 16u == 0 && ((size_t)erp_h * row_bytes) % 16u == 0;
         uint32_t* h_base = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_tangent);
         uint2* h_tiles = (uint2*)malloc(sizeof(uint2) * n_tiles);
+        uint32_t* h_need = (uint32_t*)malloc(sizeof(uint32_t) * n_tiles);     // bytes of a stage the box needs, 0 = unusable
         cudaError_t ea = cudaMemcpy(h_base, plan->d_s1_base, sizeof(uint32_t) * (size_t)n_tangent, cudaMemcpyDeviceToHost);
         int64_t staged = 0;
+        int stage_bytes = TIF_S1_MIN_STAGE_BYTES;
         if (ea == cudaSuccess) {
             for (int ty = 0; ty < tiles_y; ++ty)
                 for (int tx = 0; tx < tiles_x; ++tx) {
@@ -500,20 +502,35 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
                             y_hi = y0 > y_hi ? y0 : y_hi;
                         }
                     uint2 d = make_uint2(0u, 0u);
+                    uint32_t need = 0u;
                     if (alignable && x_lo <= x_hi) {
                         const uint32_t xb0 = (x_lo * 3u) & ~15u;
                         uint32_t xb1 = ((x_hi + 2u) * 3u + 15u) & ~15u;       // taps x0, x0 + 1: 6 bytes from x0 * 3
                         if (xb1 > row_bytes) xb1 = row_bytes;
                         const uint32_t pitch = xb1 - xb0, rows = y_hi + 2u - y_lo;
                         // 16 bytes of slack: the aligned 12-byte window of the last tap may end past its row
-                        if (rows <= 256u && (size_t)rows * pitch + 16u <= TIF_S1_STAGE_BYTES && y_hi + 1u < (uint32_t)erp_h) {
+                        const size_t bytes = (size_t)rows * pitch + 16u;
+                        if (bytes <= TIF_S1_MAX_STAGE_BYTES && y_hi + 1u < (uint32_t)erp_h) {
                             d = make_uint2(y_lo * row_bytes + xb0, rows | (pitch << 16));
-                            ++staged;
+                            need = (uint32_t)bytes;
                         }
                     }
                     h_tiles[(size_t)ty * tiles_x + tx] = d;
+                    h_need[(size_t)ty * tiles_x + tx] = need;
                 }
+            // the smallest stage that holds most boxes (small stages leave more shared memory to the L1 and more
+            // stages in the ring); what does not fit is resampled by direct gathers
+            for (;;) {
+                staged = 0;
+                for (size_t i = 0; i < n_tiles; ++i) staged += h_need[i] != 0u && h_need[i] <= (uint32_t)stage_bytes;
+                if ((double)staged >= TIF_S1_STAGED_SHARE * (double)n_tiles || stage_bytes >= TIF_S1_MAX_STAGE_BYTES) break;
+                stage_bytes *= 2;
+            }
+            for (size_t i = 0; i < n_tiles; ++i)
+                if (h_need[i] == 0u || h_need[i] > (uint32_t)stage_bytes) h_tiles[i] = make_uint2(0u, 0u);
         }
+        free(h_need);
+        plan->s1_stage_bytes = stage_bytes;
         int st = dev_alloc(&plan->d_s1_tiles, n_tiles, plan);
         cudaError_t eb = cudaSuccess;
         if (st == TIF_OK) eb = cudaMemcpy(plan->d_s1_tiles, h_tiles, sizeof(uint2) * n_tiles, cudaMemcpyHostToDevice);
@@ -546,6 +563,8 @@ extern "C" int tif_plan_info(const TifPlan* plan, TifPlanInfo* info) {
     info->accepted_unique = plan->accepted_unique;
     info->referenced_tangent_pixels = plan->referenced_tangent_pixels;
     info->device_bytes = plan->device_bytes;
+    info->stage1_patches = (int64_t)plan->s1_tiles_x * plan->s1_tiles_y;
+    info->stage1_staged_patches = plan->s1_staged_tiles;
     return TIF_OK;
 }
 

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TIF_ABI_VERSION 3
+#define TIF_ABI_VERSION 4
 #define TIF_MAX_FACES 128      /* 7-bit face id in a membership entry */
 #define TIF_MAX_TANGENT_DIM 2048 /* 11-bit tangent row / column in a membership entry */
 
@@ -116,6 +116,9 @@ typedef struct TifPlanInfo {
     int64_t accepted_unique;        /* sum over ERP pixels of accepting faces */
     int64_t referenced_tangent_pixels; /* unique tangent pixels the stitch reads (P_ref) */
     int64_t device_bytes;           /* plan footprint in HBM */
+    int64_t stage1_patches;         /* 16 x 16 tangent patches of tif_erp2ico_u8 ... */
+    int64_t stage1_staged_patches;  /* ... and how many of them are resampled through shared memory (0: ERP rows are
+                                       not 16-byte multiples, every patch takes the direct gathers) */
 } TifPlanInfo;
 
 int tif_abi_version(void);

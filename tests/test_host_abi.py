@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layout_and_status_strings(pkg):
     lib = pkg._lib.load()
-    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 3
+    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 4
     sizes = [ctypes.c_int32() for _ in range(3)]
     assert lib.tif_struct_sizes(*[ctypes.byref(s) for s in sizes]) == 0
     assert [s.value for s in sizes] == [ctypes.sizeof(pkg._lib.TifFace), ctypes.sizeof(pkg._lib.TifPlanTables),
