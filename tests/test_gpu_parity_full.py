@@ -188,6 +188,15 @@ def test_direct_c_abi_calls(pkg):
     torch.cuda.synchronize()
     want = np.stack(tif_oracle.erp2ico_image(src, wt, PAD, True)).astype(np.uint8)
     assert np.array_equal(out.cpu().numpy().reshape(want.shape), want)
+    # a caller's buffer need not be aligned: at byte offsets 1, 2, 4 and 8 the library leaves the staged resampler
+    # (16-byte row copies) for the direct gathers, at odd offsets also the aligned word loads -- same bytes out
+    for shift in (1, 2, 4, 8):
+        raw = torch.zeros(erp.numel() + 64, dtype=torch.uint8, device="cuda")
+        raw[shift:shift + erp.numel()] = erp.reshape(-1)
+        out2 = torch.zeros_like(out)
+        assert lib.tif_erp2ico_u8(plan.handle, raw.data_ptr() + shift, 1, 1, out2.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(out2, out), shift
     # invalid arguments are rejected with a status, not a crash
     assert lib.tif_erp2ico_u8(None, erp.data_ptr(), 1, 1, out.data_ptr(), stream) == -1
     assert lib.tif_erp2ico_u8(plan.handle, erp.data_ptr(), 0, 1, out.data_ptr(), stream) == -1
