@@ -155,6 +155,8 @@ int tif_plan_export_stage2(const TifPlan* plan, uint8_t* count /*[H*W]*/, uint32
  * erp2ico_image (projection_icosahedron.py:163-248): ERP -> padded tangent images, bilinear with
  * scipy's mode='wrap' (period n-1) and uint8 round-half-up; RGB = samples, A = 255 (0 and RGB 255
  * outside the padded triangle when full_face_image == 0).
+ * Any byte alignment of `erp` and any H are accepted; the fast (shared-memory staged) form needs a 16-byte aligned
+ * `erp` and ERP rows of 6 H bytes that are 16-byte multiples (H % 8 == 0), see TifPlanInfo.stage1_staged_patches.
  */
 int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp /*[B,H,W,3]*/, int batch, int full_face_image,
                    uint8_t* tangent_rgba /*[B,P,4]*/, void* stream);
