@@ -182,6 +182,22 @@ def flow_cross_covariance(flow):
     return out
 
 
+def flow_rotation2d_stats(flow, col_start, col_stop):
+    """tif_flow_rotation2d_stats: [B,6] float64 CUDA tensor (sum u; sign / positive / negative sums of v in the band)."""
+    _need_cuda(flow)
+    if flow.dim() != 4 or flow.shape[-1] != 2:
+        raise ValueError("flow_rotation2d_stats expects [B,H,W,2]")
+    flow = flow.contiguous()
+    b, h, w, _ = flow.shape
+    lib = _lib.load()
+    out = torch.empty((b, 6), dtype=torch.float64, device=flow.device)
+    scratch = torch.empty(max(int(lib.tif_flow_rotation2d_stats_scratch_bytes(b, h, w)), 8), dtype=torch.uint8, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(lib.tif_flow_rotation2d_stats(flow.data_ptr(), _flow_dtype(flow), b, h, w, int(col_start), int(col_stop),
+                                                 out.data_ptr(), scratch.data_ptr(), _stream()), "tif_flow_rotation2d_stats")
+    return out
+
+
 def flow_rotate_endpoint(flow, rotation_field, wraparound):
     """tif_flow_rotate_endpoint: flow [B,H,W,2] (float32/64), rotation_field [H,W,2] float64 -> like flow."""
     _need_cuda(flow, rotation_field)

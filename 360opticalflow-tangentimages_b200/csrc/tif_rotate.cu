@@ -162,6 +162,90 @@ extern "C" int tif_flow_cross_covariance(const void* flow, int dtype, int batch,
 }
 
 // ------------------------------------------------------------------------------------------------
+// flow2rotation_2d statistics -- flow_warp.py:136-187 (use_weight=False, the only form that runs in the reference)
+// ------------------------------------------------------------------------------------------------
+// Six sums per image in one pass: [0] sum of u over the whole image (theta_delta = mean(2 pi u / W), :152-153), and
+// over the columns [col0, col1) of the centre band (:157-170): [1] sum of sign(v), [2] sum and [3] count of v > 0,
+// [4] sum and [5] count of v < 0.  The band depends on [0], so the caller runs the pass twice.  Fixed-order
+// two-level float64 reduction: bitwise reproducible.
+template <typename T>
+__global__ void __launch_bounds__(256) k_rot2d_stats(const T* __restrict__ flow, int h, int w, int col0, int col1,
+                                                     double* __restrict__ partial) {
+    const int b = blockIdx.y;
+    const int64_t n = (int64_t)h * w;
+    const T* f = flow + (size_t)b * n * 2;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % w);
+        const double u = (double)f[2 * i], v = (double)f[2 * i + 1];
+        acc[0] += u;
+        if (c >= col0 && c < col1) {
+            if (v > 0.0) {
+                acc[1] += 1.0;
+                acc[2] += v;
+                acc[3] += 1.0;
+            } else if (v < 0.0) {
+                acc[1] -= 1.0;
+                acc[4] += v;
+                acc[5] += 1.0;
+            }
+        }
+    }
+    __shared__ double sh[8][6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+        for (int wp = 0; wp < 8; ++wp) v += sh[wp][threadIdx.x];
+        partial[((size_t)b * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_rot2d_reduce(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
+    const int b = blockIdx.x, k = threadIdx.x / 32, lane = threadIdx.x & 31;
+    double v = 0.0;
+    for (int i = lane; i < n_blocks; i += 32) v += partial[((size_t)b * n_blocks + i) * 6 + k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) out[b * 6 + k] = v;
+}
+
+static int rot2d_blocks(int h, int w) {
+    const int64_t want = ((int64_t)h * w + 255) / 256;
+    return (int)(want < 148 * 8 ? want : 148 * 8);
+}
+
+extern "C" int64_t tif_flow_rotation2d_stats_scratch_bytes(int batch, int h, int w) {
+    if (batch <= 0 || h <= 0 || w <= 0) return 0;
+    return (int64_t)batch * rot2d_blocks(h, w) * 6 * (int64_t)sizeof(double);
+}
+
+extern "C" int tif_flow_rotation2d_stats(const void* flow, int dtype, int batch, int h, int w, int col_start, int col_stop,
+                                         double* out, void* scratch, void* stream_v) {
+    if (!flow || !out || !scratch || batch <= 0 || h <= 0 || w <= 0) {
+        tif_set_error("tif_flow_rotation2d_stats: invalid argument");
+        return TIF_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int n_blocks = rot2d_blocks(h, w);
+    dim3 grid((unsigned)n_blocks, (unsigned)batch);
+    if (dtype == TIF_DTYPE_F32)
+        k_rot2d_stats<float><<<grid, 256, 0, stream>>>((const float*)flow, h, w, col_start, col_stop, (double*)scratch);
+    else if (dtype == TIF_DTYPE_F64)
+        k_rot2d_stats<double><<<grid, 256, 0, stream>>>((const double*)flow, h, w, col_start, col_stop, (double*)scratch);
+    else
+        return TIF_ERR_INVALID_ARG;
+    TIF_CUDA_CHECK(cudaGetLastError());
+    k_rot2d_reduce<<<batch, 6 * 32, 0, stream>>>((const double*)scratch, n_blocks, out);
+    TIF_CUDA_CHECK(cudaGetLastError());
+    return TIF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // flow_rotate_endpoint
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bilinear_wrap_f64(const double* __restrict__ field, int ch, double y, double x, int h,

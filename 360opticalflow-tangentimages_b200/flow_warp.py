@@ -86,15 +86,48 @@ def flow2rotation_3d(erp_flow, mask_method="center"):
     return rotation_from_covariance(h[0].cpu().numpy())
 
 
+def flow2rotation_2d(erp_flow, use_weight=True):
+    """(theta shift, phi shift) in radians between two ERP images from their flow (src/flow_warp.py:136-187): the
+    mean longitude shift, then the mean latitude shift of the majority sign inside the centre band of columns the
+    longitude shift spans.  Like the reference it first folds the flow with erp_of_wraparound (which rewrites the
+    caller's u plane).  `use_weight=True` fails in the reference (numpy AxisError at :183: a 1-D array averaged
+    over axis 1), so it raises here too; `global_rotation_warping` passes False."""
+    from . import flow_postproc
+    if use_weight:
+        raise np.exceptions.AxisError(1, 1) if hasattr(np, "exceptions") else ValueError("axis 1 is out of bounds for array of dimension 1")
+    flow = flow_postproc.erp_of_wraparound(erp_flow)
+    h, w = flow.shape[0], flow.shape[1]
+    if flow.dtype not in (np.float32, np.float64):
+        flow = flow.astype(np.float64)
+    dev_flow = torch.from_numpy(np.ascontiguousarray(flow)).to(_device())[None]
+    sum_u = float(_ops.flow_rotation2d_stats(dev_flow, 0, 0)[0, 0].item())
+    theta_delta = 2.0 * np.pi * (sum_u / (h * w) / w)
+    delta = theta_delta / (2.0 * np.pi)
+    col_start, col_end = int(w * (0.5 - delta)), int(w * (0.5 + delta))
+    if delta < 0:
+        col_start, col_end = col_end, col_start
+    st = _ops.flow_rotation2d_stats(dev_flow, col_start, col_end)[0].cpu().numpy()
+    total, count = (st[4], st[5]) if st[1] < 0 else (st[2], st[3])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        phi_delta = -np.pi * (np.float64(total) / np.float64(count)) / h      # nan on an empty band, like np.mean([])
+    return np.float64(theta_delta), np.float64(phi_delta)
+
+
 def global_rotation_warping(erp_image, erp_flow, forward_warp=True, rotation_type="3D"):
     """Rotate the ERP image by the global rotation of the flow (src/flow_warp.py:190-229).  Returns the rotated
     image and the rotation matrix."""
-    if rotation_type != "3D":
-        raise NotImplementedError("global_rotation_warping: rotation_type %r is not on the accelerated path" % (rotation_type,))
-    rotation_mat = flow2rotation_3d(erp_flow)
-    if not forward_warp:
-        rotation_mat = rotation_mat.T
     from . import spherical_coordinates as sc
+    if rotation_type == "2D":
+        theta_delta, phi_delta = flow2rotation_2d(erp_flow, False)
+        if not forward_warp:
+            theta_delta, phi_delta = -theta_delta, -phi_delta
+        rotation_mat = sc.rot_sph2mat(theta_delta, phi_delta, False)
+    elif rotation_type == "3D":
+        rotation_mat = flow2rotation_3d(erp_flow)
+        if not forward_warp:
+            rotation_mat = rotation_mat.T
+    else:
+        raise UnboundLocalError("rotation_mat: the reference logs 'Do not suport rotation type %s' and then fails" % (rotation_type,))
     erp_image_rot = sc.rotate_erp_array(erp_image, rotation_mat=rotation_mat)
     if erp_image.dtype == np.uint8:
         erp_image_rot = erp_image_rot.astype(np.uint8)

@@ -213,6 +213,12 @@ int tif_flow_warp_meshgrid(const void* flow_u /*[B,H,W]*/, const void* flow_v /*
 int tif_rotation_motion_vector_f64(const double* rotation /*host, 9*/, int h, int w, int wraparound,
                                    double* out /*[H,W,2]*/, void* stream);
 int64_t tif_flow_cross_covariance_scratch_bytes(int batch, int h, int w);
+/* flow2rotation_2d (flow_warp.py:136-187, use_weight=False): six float64 sums per image -- sum of u over the image;
+ * over the columns [col_start, col_stop): sum of sign(v), sum and count of v > 0, sum and count of v < 0.  The
+ * centre band depends on the first sum, so the caller runs it twice; fixed-order reduction, reproducible. */
+int64_t tif_flow_rotation2d_stats_scratch_bytes(int batch, int h, int w);
+int tif_flow_rotation2d_stats(const void* flow /*[B,H,W,2]*/, int dtype, int batch, int h, int w, int col_start,
+                              int col_stop, double* out /*[B,6]*/, void* scratch, void* stream);
 int tif_flow_cross_covariance(const void* flow /*[B,H,W,2]*/, int dtype, int batch, int h, int w, double* out /*[B,9]*/,
                               void* scratch, void* stream);
 int tif_flow_rotate_endpoint(const void* flow /*[B,H,W,2]*/, int dtype, const double* rotation_field /*[H,W,2]*/,

@@ -860,11 +860,49 @@ def flow2rotation_3d(erp_flow):
     return rotation_from_covariance(flow_cross_covariance(erp_flow))
 
 
-def global_rotation_warping(erp_image, erp_flow, forward_warp=True):
-    """flow_warp.py:190-229 with rotation_type='3D'."""
-    rotation_mat = flow2rotation_3d(erp_flow)
-    if not forward_warp:
-        rotation_mat = rotation_mat.T
+def flow2rotation_2d(erp_flow):
+    """flow_warp.py:136-187 with use_weight=False (use_weight=True raises numpy's AxisError at :183 in the
+    reference: a 1-D array averaged over axis 1).  Rewrites the caller's u plane like the reference (:151)."""
+    h, w = erp_flow.shape[0], erp_flow.shape[1]
+    erp_flow = erp_of_wraparound(erp_flow)
+    theta_delta_array = 2.0 * np.pi * (erp_flow[:, :, 0] / w)
+    theta_delta = np.mean(theta_delta_array)
+    delta = theta_delta / (2.0 * np.pi)
+    col_start, col_end = int(w * (0.5 - delta)), int(w * (0.5 + delta))
+    if delta < 0:
+        col_start, col_end = col_end, col_start
+    centre = np.zeros((h, w), dtype=bool)
+    centre[:, col_start:col_end] = True
+    flow_sign = np.sign(np.sum(np.sign(erp_flow[centre, 1])))
+    if flow_sign < 0:
+        chosen = np.logical_and(erp_flow[:, :, 1] < 0, centre)
+    else:
+        chosen = np.logical_and(erp_flow[:, :, 1] > 0, centre)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            phi_delta = np.mean(-np.pi * (erp_flow[chosen, 1] / h))
+    return theta_delta, phi_delta
+
+
+def rot_sph2mat(theta, phi, degrees_=True):
+    """spherical_coordinates.py:221-224."""
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_euler("xyz", [phi, theta, 0], degrees=degrees_).as_matrix()
+
+
+def global_rotation_warping(erp_image, erp_flow, forward_warp=True, rotation_type="3D"):
+    """flow_warp.py:190-229."""
+    if rotation_type == "2D":
+        theta_delta, phi_delta = flow2rotation_2d(erp_flow)
+        if not forward_warp:
+            theta_delta, phi_delta = -theta_delta, -phi_delta
+        rotation_mat = rot_sph2mat(theta_delta, phi_delta, False)
+    else:
+        rotation_mat = flow2rotation_3d(erp_flow)
+        if not forward_warp:
+            rotation_mat = rotation_mat.T
     out = rotate_erp_array(erp_image, rotation_mat)
     if erp_image.dtype == np.uint8:
         out = out.astype(np.uint8)

@@ -26,6 +26,25 @@ def test_oracle_against_live_reference():
     assert np.array_equal(ia, ib) and np.array_equal(ra, rb)
     for wrap in (False, True):
         assert np.array_equal(pr.flow_rotate_endpoint(flow, R_TEST.T, wrap), tif_oracle.flow_rotate_endpoint(flow, R_TEST.T, wrap))
+    # the "2D" rotation type: mean longitude shift + majority-sign latitude shift of the centre band
+    for shift in ((5.0, -2.0), (-7.5, 1.25), (0.0, 0.5), (2 * h - 3.0, -0.75)):      # the last one folds across the seam
+        f2 = _flow_2d(h, shift)
+        fa, fb = f2.copy(), f2.copy()
+        ta, pa = fw.flow2rotation_2d(fa, False)
+        tb, pb = tif_oracle.flow2rotation_2d(fb)
+        assert (ta, pa) == (tb, pb) or (np.isnan(pa) and np.isnan(pb) and ta == tb)
+        assert np.array_equal(fa, fb)                                             # the same in-place fold of u
+        ia, ra = fw.global_rotation_warping(tar, f2.copy(), False, "2D")
+        ib, rb = tif_oracle.global_rotation_warping(tar, f2.copy(), False, "2D")
+        assert np.array_equal(ia, ib) and np.array_equal(ra, rb)
+    with pytest.raises(Exception) as info:                                         # use_weight=True never worked
+        fw.flow2rotation_2d(_flow_2d(h, (5.0, -2.0)), True)
+    assert "axis 1 is out of bounds" in str(info.value)
+
+
+def _flow_2d(h, shift, seed=3):
+    rng = np.random.default_rng(seed)
+    return rng.normal(0.0, 0.6, (h, 2 * h, 2)) + np.asarray(shift, dtype=np.float64)
 
 
 def test_oracle_recovers_a_known_rotation():
@@ -52,6 +71,20 @@ def test_gpu_rotation_helpers(pkg, h):
     img_w, rot_w = tif_oracle.global_rotation_warping(tar, flow, False)
     assert img.dtype == np.uint8 and np.abs(rot - rot_w).max() < 1e-12
     assert (img != img_w).mean() < 1e-5            # the rotation differs in the last bits: at most a stray rounding
+    for shift in ((5.0, -2.0), (-7.5, 1.25), (2 * h - 3.0, -0.75)):
+        f2 = _flow_2d(h, shift)
+        fa, fb = f2.copy(), f2.copy()
+        (ta, pa), (tb, pb) = fw.flow2rotation_2d(fa, False), tif_oracle.flow2rotation_2d(fb)
+        assert abs(ta - tb) < 1e-12 and abs(pa - pb) < 1e-12 and np.array_equal(fa, fb)
+        assert fw.flow2rotation_2d(f2.copy(), False) == (ta, pa)                                        # deterministic
+        t32, p32 = fw.flow2rotation_2d(f2.astype(np.float32), False)
+        assert abs(t32 - tb) < 1e-6 and abs(p32 - pb) < 1e-6
+        img2, rot2 = fw.global_rotation_warping(tar, f2.copy(), forward_warp=False, rotation_type="2D")
+        img2_w, rot2_w = tif_oracle.global_rotation_warping(tar, f2.copy(), False, "2D")
+        assert np.abs(rot2 - rot2_w).max() < 1e-12 and (img2 != img2_w).mean() < 1e-5
+    with pytest.raises(Exception) as info:
+        fw.flow2rotation_2d(_flow_2d(h, (5.0, -2.0)), True)
+    assert "axis 1 is out of bounds" in str(info.value)
     for wrap in (False, True):
         got = pr.flow_rotate_endpoint(flow, R_TEST.T, wrap)
         want = tif_oracle.flow_rotate_endpoint(flow, R_TEST.T, wrap)
