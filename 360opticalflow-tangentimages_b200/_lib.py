@@ -80,6 +80,9 @@ SYMBOLS = {
     "tif_rotation_motion_vector_f64": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_flow_cross_covariance_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "tif_flow_cross_covariance": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "tif_blend_weight_points_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "tif_blend_weight_points": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_int64, C.c_int,
+                                          _VP, _VP, _VP]),
     "tif_flow_rotation2d_stats_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "tif_flow_rotation2d_stats": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
     "tif_flow_rotate_endpoint": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),

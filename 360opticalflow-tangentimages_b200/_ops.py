@@ -182,6 +182,34 @@ def flow_cross_covariance(flow):
     return out
 
 
+_IMAGE_DTYPES = {torch.float32: 0, torch.float64: 1, torch.uint8: 2}
+
+
+def blend_weight_points(image_src, image_tar, x_src, y_src, x_tar, y_tar, weight_kind):
+    """tif_blend_weight_points: [N] float64 weights for N source / target positions (float64 CUDA tensors) and two
+    [H,W,C] images of one dtype (uint8, float32 or float64)."""
+    _need_cuda(image_src, image_tar, x_src, y_src, x_tar, y_tar)
+    if image_src.dtype != image_tar.dtype or image_src.dtype not in _IMAGE_DTYPES or image_src.shape != image_tar.shape:
+        raise ValueError("blend_weight_points: the two images must share shape and dtype (uint8, float32 or float64)")
+    image_src, image_tar = image_src.contiguous(), image_tar.contiguous()
+    h, w, c = image_src.shape
+    coords = [t.to(torch.float64).contiguous().reshape(-1) for t in (x_src, y_src, x_tar, y_tar)]
+    n = coords[0].numel()
+    if any(t.numel() != n for t in coords):
+        raise ValueError("blend_weight_points: coordinate arrays differ in length")
+    lib = _lib.load()
+    out = torch.empty((n,), dtype=torch.float64, device=image_src.device)
+    if n == 0:
+        return out
+    scratch = torch.empty(max(int(lib.tif_blend_weight_points_scratch_bytes(n)), 8), dtype=torch.uint8, device=image_src.device)
+    with torch.cuda.device(image_src.device):
+        _lib.check(lib.tif_blend_weight_points(image_src.data_ptr(), image_tar.data_ptr(), _IMAGE_DTYPES[image_src.dtype], h, w, c,
+                                               coords[0].data_ptr(), coords[1].data_ptr(), coords[2].data_ptr(),
+                                               coords[3].data_ptr(), n, int(weight_kind), out.data_ptr(), scratch.data_ptr(),
+                                               _stream()), "tif_blend_weight_points")
+    return out
+
+
 def flow_rotation2d_stats(flow, col_start, col_stop):
     """tif_flow_rotation2d_stats: [B,6] float64 CUDA tensor (sum u; sign / positive / negative sums of v in the band)."""
     _need_cuda(flow)

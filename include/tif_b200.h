@@ -68,6 +68,7 @@ typedef enum TifStatus {
 
 #define TIF_DTYPE_F32 0
 #define TIF_DTYPE_F64 1
+#define TIF_DTYPE_U8 2           /* images of tif_blend_weight_points only */
 
 /*
  * One tangent face.  Replaces the dict returned by get_icosahedron_parameters
@@ -239,6 +240,18 @@ int tif_flow_error_mats(const void* gt, const void* eva, int dtype, const uint8_
 int64_t tif_reduce_f64_scratch_bytes(int batch);
 int tif_reduce_f64(const double* x /*[B,n]*/, int batch, int64_t n, int power, double* out /*[B]*/, void* scratch,
                    void* stream);
+
+/*
+ * projection.get_blend_weight_ico / get_blend_weight_cubemap, weight_type "image_warp_error" (projection.py:15-117),
+ * as a stand-alone call (tif_ico2erp_flow_f32 fuses the same weights): n source positions and n target positions in
+ * ERP pixels, two [H,W,C] images (TIF_DTYPE_U8 / F32 / F64), scipy map_coordinates(order=1, mode='constant',
+ * cval=255) per channel.  weight_kind 0: exp(-mean_c|tar - src| / mean over all points and channels);
+ * weight_kind 1: 0.95 / ||tar - src||_2, 1 where that is 0.  Deterministic.
+ */
+int64_t tif_blend_weight_points_scratch_bytes(int64_t n);
+int tif_blend_weight_points(const void* image_src, const void* image_tar, int image_dtype, int h, int w, int channels,
+                            const double* x_src, const double* y_src, const double* x_tar, const double* y_tar,
+                            int64_t n, int weight_kind, double* weights /*[n]*/, void* scratch, void* stream);
 
 /* flow_postproc.erp_of_wraparound (flow_postproc.py:17-44), in place on [B,H,W,2]. */
 int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold, void* stream);

@@ -925,6 +925,35 @@ def flow_rotate_endpoint(optical_flow, rotation_matrix, wraparound=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# stand-alone face weights -- projection.py:15-117 (the stitch functions above restate them in fused form)
+# ------------------------------------------------------------------------------------------------
+
+def _warp_error(face_x, face_y, flow_uv, image_src, image_tar):
+    n, channels = np.shape(face_x)[0], image_src.shape[2]
+    diff = np.zeros((n, channels), dtype=np.float64)
+    for ch in range(channels):
+        t = map_coordinates_order1(image_tar[:, :, ch], flow_uv[:, 1], flow_uv[:, 0], "constant", 255)
+        s = map_coordinates_order1(image_src[:, :, ch], face_y, face_x, "constant", 255)
+        diff[:, ch] = np.absolute(np.asarray(t, dtype=np.float64) - np.asarray(s, dtype=np.float64))
+    return diff
+
+
+def get_blend_weight_ico(face_x, face_y, flow_uv, image_src, image_tar):
+    """projection.py:15-61, weight_type 'image_warp_error'."""
+    diff = _warp_error(face_x, face_y, flow_uv, image_src, image_tar)
+    return np.exp(-(np.mean(diff, axis=1) / np.mean(diff)))
+
+
+def get_blend_weight_cubemap(face_x, face_y, flow_uv, image_src, image_tar):
+    """projection.py:64-117, weight_type 'image_warp_error'."""
+    rgb_diff = np.linalg.norm(_warp_error(face_x, face_y, flow_uv, image_src, image_tar), axis=1)
+    weights = np.ones(np.shape(face_x)[0], dtype=np.float64)
+    nz = rgb_diff != 0.0
+    weights[nz] = 0.95 / rgb_diff[nz]
+    return weights
+
+
+# ------------------------------------------------------------------------------------------------
 # metrics (SURVEY.md section 8f, row f3) -- flow_evaluate.py:23-217
 # ------------------------------------------------------------------------------------------------
 
