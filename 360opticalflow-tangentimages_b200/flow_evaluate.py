@@ -106,3 +106,59 @@ def AAE(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
     """src/flow_evaluate.py:156-164: always planar and unmasked, whatever is passed."""
     _, aae, _, ok = _error_mats(of_ground_truth, of_evaluation, False, None, True)
     return _sum(aae) / float(ok.sum())
+
+
+def opticalflow_metric(flo_gt, flo_eva, erp_flo_error_filename_prefix=None, flo_mask=None, min_ratio=0.1, max_ratio=0.9,
+                       verbose=True):
+    """AAE, EPE, RMS and their "spherical" variants in the reference's order (src/flow_evaluate.py:220-280); like the
+    reference every metric zeroes the unusable pixels of both flows in place, so the later ones see what the earlier
+    ones left.  With a file name prefix the reference also writes colour-mapped error images through its own
+    `image_io` module (used as it is when it is importable) -- and then fails in `AAE_mat(spherical=True)`, which
+    calls a function that does not exist; so does this."""
+    aae = AAE(flo_gt, flo_eva, spherical=False, of_mask=flo_mask)
+    epe = EPE(flo_gt, flo_eva, spherical=False, of_mask=flo_mask)
+    rms = RMSE(flo_gt, flo_eva, spherical=False, of_mask=flo_mask)
+    aae_sph = AAE(flo_gt, flo_eva, spherical=True, of_mask=flo_mask)
+    epe_sph = EPE(flo_gt, flo_eva, spherical=True, of_mask=flo_mask)
+    rms_sph = RMSE(flo_gt, flo_eva, spherical=True, of_mask=flo_mask)
+    if erp_flo_error_filename_prefix is not None:
+        import image_io            # the reference's module (reference/src on sys.path); not part of this package
+        for name, fn, spherical in (("_aae_mat.jpg", AAE_mat, False), ("_aae_mat_sph.jpg", AAE_mat, True),
+                                    ("_epe_mat.jpg", EPE_mat, False), ("_epe_mat_sph.jpg", EPE_mat, True),
+                                    ("_rms_mat.jpg", RMSE_mat, False), ("_rms_mat_sph.jpg", RMSE_mat, True)):
+            mat, _ = fn(flo_gt, flo_eva, spherical, flo_mask)
+            image_io.image_save(image_io.visual_data(mat, min_ratio, max_ratio), erp_flo_error_filename_prefix + name)
+    return aae, epe, rms, aae_sph, epe_sph, rms_sph
+
+
+def opticalflow_metric_folder(of_dir, of_gt_dir, mask_filename_exp=None, result_csv_filename=None, visual_of_error=False,
+                              of_wraparound=True, skip_list=[]):
+    """The six metrics of every `.flo` file of a folder against the ground truth of the same name, one CSV row each
+    (src/flow_evaluate.py:283-350)."""
+    import csv
+    import os
+    from . import flow_io, flow_postproc
+    path = of_dir + ("result.csv" if result_csv_filename is None else result_csv_filename)
+    with open(path, mode="w", newline="", encoding="utf-8") as result_file:
+        writer = csv.writer(result_file, delimiter=",", quotechar='"', quoting=csv.QUOTE_MINIMAL)
+        writer.writerow(["flo_filename", "AAE", "EPE", "RMS", "SAAE", "SEPE", "SRMS"])
+        for filename in sorted(os.listdir(of_dir)):
+            if not filename.endswith(".flo"):
+                continue
+            if filename in skip_list:
+                print("skip {} in {}".format(filename, skip_list))
+                continue
+            flow = flow_io.read_flow_flo(of_dir + filename)
+            flow_gt = flow_io.read_flow_flo(of_gt_dir + filename)
+            if flow.shape != flow_gt.shape:        # the reference calls flow_postproc.flow_resize, which does not exist
+                raise AttributeError("module 'flow_postproc' has no attribute 'flow_resize'")
+            if of_wraparound:
+                flow = flow_postproc.erp_of_wraparound(flow)
+                flow_gt = flow_postproc.erp_of_wraparound(flow_gt)
+            mask = None
+            if mask_filename_exp is not None:
+                import image_io        # the reference's module
+                mask = image_io.image_read(of_gt_dir + mask_filename_exp.format(int(filename[0:4])))
+            prefix = of_dir + filename if visual_of_error else None
+            writer.writerow([filename, *opticalflow_metric(flow_gt, flow, prefix, mask, 0.1, 0.9, True)])
+            result_file.flush()

@@ -39,6 +39,14 @@ def get_cubemap_parameters(padding_size=0.0):
             "face_erp_range": cubemap_face_erp_range(padding_size)}
 
 
+def face_meshgrid(face_erp_range_sphere_list, erp_image_height):
+    """ERP pixel grid of the bounding box of one face, wrapped into the image (src/projection_cubemap.py:190-243).
+    Host geometry (the device plan evaluates the same box, `_geometry.cubemap_erp_bounding_box`)."""
+    x_min, x_max, y_min, y_max = _geometry.cubemap_erp_bounding_box(face_erp_range_sphere_list, erp_image_height)
+    face_erp_x, face_erp_y = np.meshgrid(np.linspace(x_min, x_max, x_max - x_min + 1), np.linspace(y_min, y_max, y_max - y_min + 1))
+    return np.remainder(face_erp_x, erp_image_height * 2), np.remainder(face_erp_y, erp_image_height)
+
+
 def erp2cubemap_image(erp_image_mat, padding_size=0.0, face_image_size=None):
     """ERP image -> 6 padded cube faces (+x, -x, +y, -y, +z, -z), src/projection_cubemap.py:127-187."""
     erp_image_mat = np.asarray(erp_image_mat)

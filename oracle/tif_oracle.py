@@ -1008,3 +1008,26 @@ def flow_metrics(gt, ev, spherical=False, of_mask=None):
     e, ok = epe_mat(gt, ev, spherical, of_mask)
     a, ok_a = aae_mat(gt, ev, None)
     return np.sum(e) / np.sum(ok), np.sqrt(np.sum(np.square(e)) / np.sum(ok)), np.sum(a) / np.sum(ok_a)
+
+
+def opticalflow_metric(flo_gt, flo_eva, flo_mask=None):
+    """flow_evaluate.py:220-246 without the error-map images: AAE, EPE, RMS, then the same three "spherical" (AAE is
+    always planar and unmasked, :156-164).  Every call zeroes the unusable pixels of BOTH arguments in place
+    (:84-85, :132-133, :185-186), so the later calls see what the earlier ones left -- reproduced here."""
+    def zero(mask):
+        ok = available_pixel(flo_gt, mask)
+        flo_gt[~ok] = 0
+        flo_eva[~ok] = 0
+
+    out = []
+    for spherical in (False, True):
+        a, ok_a = aae_mat(flo_gt, flo_eva, None)
+        zero(None)
+        out.append(np.sum(a) / np.sum(ok_a))
+        e, ok = epe_mat(flo_gt, flo_eva, spherical, flo_mask)
+        zero(flo_mask)
+        out.append(np.sum(e) / np.sum(ok))
+        e, ok = epe_mat(flo_gt, flo_eva, spherical, flo_mask)
+        zero(flo_mask)
+        out.append(np.sqrt(np.sum(np.square(e)) / np.sum(ok)))
+    return tuple(out)

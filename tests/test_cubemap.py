@@ -72,6 +72,21 @@ def test_oracle_against_live_reference():
             assert np.array_equal(fa, fb)
 
 
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_face_meshgrid_against_live_reference(pkg):
+    """projection_cubemap.face_meshgrid is host geometry: the product's own function against the reference's."""
+    import importlib
+    ref_shim.load_reference()
+    pc = importlib.import_module("projection_cubemap")
+    for pad in (0.0, 0.1, 0.4):
+        ranges = pc.get_cubemap_parameters(pad)["face_erp_range"]
+        for h in (64, 96, 250):
+            for f in range(6):
+                want = pc.face_meshgrid(ranges[f], h)
+                got = pkg.projection_cubemap.face_meshgrid(ranges[f], h)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
 def test_host_tables_match_oracle(pkg):
     geo = pkg._geometry
     for pad in (0.0, 0.4):

@@ -38,6 +38,12 @@ def test_oracle_metrics_against_live_reference():
             e_or, ok_or = tif_oracle.epe_mat(gt, ev, spherical, m)
             assert np.array_equal(ok_ref, ok_or) and np.array_equal(e_ref, e_or)
     assert np.array_equal(fe.available_pixel(gt.copy(), mask), tif_oracle.available_pixel(gt, mask))
+    # the six-metric summary: every metric zeroes unusable pixels of both flows in place, the later ones see that
+    for m in (None, mask):
+        ga, ea, gb, eb = gt.copy(), ev.copy(), gt.copy(), ev.copy()
+        want = fe.opticalflow_metric(ga, ea, None, m, verbose=False)
+        got = tif_oracle.opticalflow_metric(gb, eb, m)
+        assert np.allclose(got, want, rtol=1e-13, atol=0) and np.array_equal(ga, gb) and np.array_equal(ea, eb)
 
 
 def test_flo_round_trip(pkg, tmp_path):
@@ -81,3 +87,29 @@ def test_gpu_metrics(pkg, h):
     assert fe.EPE(gt.copy(), ev.copy()) == fe.EPE(gt.copy(), ev.copy())          # deterministic reduction
     with pytest.raises(AttributeError):
         fe.AAE_mat(gt.copy(), ev.copy(), True)
+    for m in (None, mask):
+        ga, ea, gb, eb = gt.copy(), ev.copy(), gt.copy(), ev.copy()
+        got = fe.opticalflow_metric(ga, ea, None, m, verbose=False)
+        want = tif_oracle.opticalflow_metric(gb, eb, m)
+        assert np.allclose(got, want, rtol=1e-11, atol=0) and np.array_equal(ga, gb) and np.array_equal(ea, eb)
+
+
+@pytest.mark.gpu
+def test_gpu_metric_folder(pkg, tmp_path):
+    """The folder driver: .flo files in, one CSV row of six metrics per file."""
+    fe, fio = pkg.flow_evaluate, pkg.flow_io
+    of_dir, gt_dir = str(tmp_path / "of") + "/", str(tmp_path / "gt") + "/"
+    import os
+    os.makedirs(of_dir), os.makedirs(gt_dir)
+    want = {}
+    for i in range(2):
+        gt, ev, _ = flows(48, seed=20 + i)
+        fio.flow_write(ev, of_dir + "%04d_flow.flo" % i)
+        fio.flow_write(gt, gt_dir + "%04d_flow.flo" % i)
+        g32, e32 = gt.astype(np.float32), ev.astype(np.float32)
+        want["%04d_flow.flo" % i] = tif_oracle.opticalflow_metric(tif_oracle.erp_of_wraparound(g32), tif_oracle.erp_of_wraparound(e32), None)
+    fe.opticalflow_metric_folder(of_dir, gt_dir, result_csv_filename="r.csv")
+    rows = [r.split(",") for r in open(of_dir + "r.csv").read().strip().splitlines()]
+    assert rows[0] == ["flo_filename", "AAE", "EPE", "RMS", "SAAE", "SEPE", "SRMS"] and len(rows) == 3
+    for r in rows[1:]:
+        assert np.allclose([float(v) for v in r[1:]], want[r[0]], rtol=1e-6)
