@@ -148,3 +148,46 @@ def test_sizes_that_are_not_tile_multiples(pkg, erp_h, wt):
             excuse |= dbg["edge_dist"] < 1e-3
         assert (((np.abs(got - want).max(axis=2)) > FLOW_TOL) & ~excuse).sum() == 0
     assert np.array_equal(pkg.flow_warp.warp_backward(tar, want), tif_oracle.warp_backward(tar, want))
+
+
+@pytest.mark.parametrize("pad", [0.0, 0.05, 0.6])
+def test_padding_extremes(pkg, pad):
+    """No padding (faces only touch, pixels on shared edges rely on the polygon epsilon) and a padding large enough
+    for most pixels to be seen by five or more faces."""
+    erp_h, wt = 64, 40
+    src, tar = synth.synth_images(erp_h, 21, smooth=True)
+    flows = synth.synth_flows(wt, 20, 1.0)
+    pico = pkg.projection_icosahedron
+    for full in (True, False):
+        got = pico.erp2ico_image(src, wt, pad, full)
+        want = tif_oracle.erp2ico_image(src, wt, pad, full)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    for blend in ("straightforward", "normwarp"):
+        want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, pad, src, tar, True, blend, return_debug=True)
+        got = pico.ico2erp_flow(flows, erp_h, pad, src, tar, True, blend)
+        excuse = dbg["seam_dist"] < 1e-5
+        if blend == "normwarp":
+            excuse |= dbg["edge_dist"] < 1e-3
+        assert (((np.abs(got - want).max(axis=2)) > FLOW_TOL) & ~excuse).sum() == 0, (pad, blend)
+
+
+@pytest.mark.parametrize("scale", [6.0, 20.0])
+def test_large_flows(pkg, scale):
+    """Tangent flows of tens of pixels on 60-pixel tangent images: end points leave their face, cross the seam and
+    the poles, and the lift leaves its small-angle fast path.  Smooth images, so that a 1e-4 px sampling difference
+    does not turn into a different weight."""
+    erp_h, wt = 128, 60
+    src, tar = synth.synth_images(erp_h, 5, smooth=True)
+    flows = [f * np.float32(scale) for f in synth.synth_flows(wt, 20, 0.5)]
+    pico = pkg.projection_icosahedron
+    for wrap in (True, False):
+        for blend in ("straightforward", "normwarp"):
+            want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, 0.3, src, tar, wrap, blend, return_debug=True)
+            got = pico.ico2erp_flow(flows, erp_h, 0.3, src, tar, wrap, blend)
+            excuse = dbg["seam_dist"] < 1e-5
+            if not wrap:
+                excuse |= dbg["fu_spread"] > 0.25 * want.shape[1]
+            if blend == "normwarp":
+                excuse |= dbg["edge_dist"] < 1e-3
+            bad = ((np.abs(got - want).max(axis=2)) > FLOW_TOL) & ~excuse
+            assert bad.sum() == 0, (scale, wrap, blend, int(bad.sum()), float(np.abs(got - want)[bad].max()))
