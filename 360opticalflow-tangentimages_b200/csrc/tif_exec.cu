@@ -754,7 +754,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
                 tail[j] = (b == batch - 1) & (yi == erp_h - 2) & (xi >= erp_w - 6);     // wide loads could leave the buffer
             }
         }
-        if (!NW) continue;
+        if constexpr (NW) {
         RawPair raw0[G], raw1[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
@@ -800,6 +800,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
             reinterpret_cast<uint4*>(records)[rec0 + bb] =
                 make_uint4(__float_as_uint(disp_x[j]), __float_as_uint(disp_y[j]), q0 | (q1 << 21), (q1 >> 11) | (q2 << 10));
         }
+        }       // if constexpr (NW)
     }
 }
 
@@ -1055,7 +1056,6 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     cudaStream_t stream = (cudaStream_t)stream_v;
     const int h = plan->erp_h, w = plan->erp_w, n_faces = plan->n_faces;
     const int n_tangent = (int)plan->tangent_pixels;
-    const unsigned by = (unsigned)((batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK);
     unsigned long long* nw_sums = (unsigned long long*)scratch;
     void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
     const int n_ref = (int)plan->referenced_tangent_pixels;
