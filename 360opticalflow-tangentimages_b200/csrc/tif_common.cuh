@@ -30,19 +30,22 @@
 // 128 threads x 765 x 7 x 1024 < 2^32: a block's partial sum fits a native 32-bit shared atomic
 #define TIF_NW_FIXED_SCALE 1024.0f
 
-// stage-1 staging: a block owns a TIF_S1_TILE x TIF_S1_TILE patch of the tangent stack; the ERP box its taps touch
+// stage-1 staging: a block owns a TIF_S1_TILE_W x TIF_S1_TILE_H patch of the tangent stack; the ERP box its taps touch
 // is copied asynchronously (cp.async) into a ring of TIF_S1_STAGES shared-memory stages, one image per stage.  The
 // plan picks the stage size (a power of two between the bounds below) from the boxes it finds.  16 KB stages (four
 // chunks per thread) measured slower at every ERP size than 8 KB ones with more patches on the direct path.
-#define TIF_S1_TILE 16
+#define TIF_S1_TILE_W 16
+#ifndef TIF_S1_TILE_H
+#define TIF_S1_TILE_H 8
+#endif
 #ifndef TIF_S1_STAGES
 #define TIF_S1_STAGES 4
 #endif
 #ifndef TIF_S1_MIN_STAGE_BYTES
-#define TIF_S1_MIN_STAGE_BYTES 4096
+#define TIF_S1_MIN_STAGE_BYTES 2048
 #endif
 #ifndef TIF_S1_MAX_STAGE_BYTES
-#define TIF_S1_MAX_STAGE_BYTES 8192
+#define TIF_S1_MAX_STAGE_BYTES 4096
 #endif
 // a stage size is taken when this share of the patches fits it (else the next larger one is tried)
 #ifndef TIF_S1_STAGED_SHARE

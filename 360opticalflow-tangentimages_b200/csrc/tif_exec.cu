@@ -245,7 +245,7 @@ k_erp2ico(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_f
 
 // ---- staged variant ---------------------------------------------------------------------------------
 // The direct kernel is bound by L1 wavefronts: every tap load of a warp touches 5-6 cache lines and each ERP
-// byte is fetched by several warps.  Here a block owns a 16 x 16 patch of the tangent stack; the plan knows the
+// byte is fetched by several warps.  Here a block owns a 16 x 8 patch of the tangent stack; the plan knows the
 // bounding box of its taps (median 21 x 18 ERP pixels at 2K), and that box is brought into shared memory with
 // 16-byte asynchronous copies (cp.async, no register staging), TIF_S1_STAGES - 1 images ahead of the blend.
 // The taps then come from shared memory (LDS, no L1 tag traffic) and the global reads are whole aligned rows.
@@ -269,10 +269,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 
 #ifndef TIF_ERP2ICO_STAGED_MIN_BLOCKS
-#define TIF_ERP2ICO_STAGED_MIN_BLOCKS 4
+#define TIF_ERP2ICO_STAGED_MIN_BLOCKS 8
 #endif
-#define TIF_S1_THREADS (TIF_S1_TILE * TIF_S1_TILE)
+#define TIF_S1_THREADS (TIF_S1_TILE_W * TIF_S1_TILE_H)
 #define TIF_S1_MAX_CHUNKS (TIF_S1_MAX_STAGE_BYTES / (16 * TIF_S1_THREADS))      // 16-byte chunks a thread copies per image
+static_assert(TIF_S1_MAX_CHUNKS >= 1 && TIF_S1_MAX_CHUNKS * 16 * TIF_S1_THREADS == TIF_S1_MAX_STAGE_BYTES, "stage size must be a whole number of chunks per thread");
 
 // one RGBA output pixel from a staged box: a0 = shared address of the aligned word holding the first tap, the
 // second tap row is `pitch` bytes on, `sh` = 8 x byte phase (the same for both rows: pitch is a multiple of 16)
@@ -306,7 +307,7 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
     extern __shared__ __align__(128) uint8_t stage[];
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int trow = ty * TIF_S1_TILE + tid / TIF_S1_TILE, tcol = tx * TIF_S1_TILE + tid % TIF_S1_TILE;
+    const int trow = ty * TIF_S1_TILE_H + tid / TIF_S1_TILE_W, tcol = tx * TIF_S1_TILE_W + tid % TIF_S1_TILE_W;
     const bool valid = trow < (int)(n_pix / tangent_w) && tcol < tangent_w;
     const int64_t p = (int64_t)trow * tangent_w + tcol;
     const int b_begin = blockIdx.y * batch_per_block_row;
@@ -443,16 +444,27 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 // the direction vector cancels in float32, and under normwarp the faces disagree by hundreds of ERP pixels
 // there, so the photometric weights turn a 1e-4 px error of the sampling position into a flow error above
 // the 1e-3 px tolerance
-// resident blocks per SM (register caps) measured best on B200 for each gather mode
+// block size and resident blocks per SM (register caps) measured best on B200 for each gather mode: 128-thread
+// blocks at the same occupancy beat 256-thread ones by 3-5 % (finer-grained block turnover of short-lived threads)
 #ifndef TIF_GATHER_MIN_BLOCKS
-#define TIF_GATHER_MIN_BLOCKS 6
+#define TIF_GATHER_MIN_BLOCKS 12
 #endif
 #ifndef TIF_GATHER1_MIN_BLOCKS
-#define TIF_GATHER1_MIN_BLOCKS 5
+#define TIF_GATHER1_MIN_BLOCKS 10
 #endif
 #ifndef TIF_GATHER2_MIN_BLOCKS
-#define TIF_GATHER2_MIN_BLOCKS 4
+#define TIF_GATHER2_MIN_BLOCKS 8
 #endif
+#ifndef TIF_GATHER2_THREADS
+#define TIF_GATHER2_THREADS 128
+#endif
+#ifndef TIF_GATHER1_THREADS
+#define TIF_GATHER1_THREADS 128
+#endif
+#ifndef TIF_GATHER0_THREADS
+#define TIF_GATHER0_THREADS 128
+#endif
+#define TIF_GATHER_THREADS_OF(MODE) (((MODE) == 2 || (MODE) == 4) ? TIF_GATHER2_THREADS : ((MODE) == 1 ? TIF_GATHER1_THREADS : TIF_GATHER0_THREADS))
 // images per k_gather thread: a divisor of the lift chunk (the records stay interleaved per lift chunk)
 #ifndef TIF_GATHER_IMGS
 #define TIF_GATHER_IMGS 4
@@ -572,12 +584,13 @@ __device__ __noinline__ void lift_precise(const LiftFace* F, int tcol, int trow,
 //   delta_theta = atan2(E, rho)     delta_colat = atan2(-N + E^2 cos / (h + rho), ...)
 // see small angles and float32 keeps ~1e-7 relative precision on the displacement itself.
 // The result is (delta_theta W / 2 pi, delta_colat H / pi); k_gather adds the pixel's own ERP position.
-// launch shape per variant, measured on B200: the sampling variants spill at 64 registers, 128 x 7 gives them 72
+// launch shape per variant, measured on B200: the sampling variants spill at 64 registers, 128 x 7 gives them 72;
+// the plain variant is 5 % faster in 64-thread blocks at the same 50 % occupancy
 #ifndef TIF_LIFT_MIN_BLOCKS
-#define TIF_LIFT_MIN_BLOCKS 4
+#define TIF_LIFT_MIN_BLOCKS 16
 #endif
 #ifndef TIF_LIFT_THREADS
-#define TIF_LIFT_THREADS 256
+#define TIF_LIFT_THREADS 64
 #endif
 #ifndef TIF_LIFT_NW_MIN_BLOCKS
 #define TIF_LIFT_NW_MIN_BLOCKS 7
@@ -821,7 +834,7 @@ __device__ __forceinline__ void red_shared_add(unsigned* addr, unsigned val) {
 // point).  MODE 2: normwarp pass B (weights from the sums of pass A, blend).  One thread per ERP pixel and chunk
 // of images; a warp owns an 8 x 4 pixel tile.
 template <int MODE>
-__global__ void __launch_bounds__(TIF_STITCH_THREADS, (MODE == 2 || MODE == 4) ? TIF_GATHER2_MIN_BLOCKS : (MODE == 1 ? TIF_GATHER1_MIN_BLOCKS : TIF_GATHER_MIN_BLOCKS))
+__global__ void __launch_bounds__(TIF_GATHER_THREADS_OF(MODE), (MODE == 2 || MODE == 4) ? TIF_GATHER2_MIN_BLOCKS : (MODE == 1 ? TIF_GATHER1_MIN_BLOCKS : TIF_GATHER_MIN_BLOCKS))
 k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
          const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
@@ -1062,8 +1075,10 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const unsigned lift_by = (unsigned)((batch + TIF_LIFT_IMGS - 1) / TIF_LIFT_IMGS);
     const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), lift_by);
     const dim3 lift_nw_grid((unsigned)((n_ref + TIF_LIFT_NW_THREADS - 1) / TIF_LIFT_NW_THREADS), lift_by);
-    const dim3 gather_grid((unsigned)((tile_threads(w, h) + TIF_STITCH_THREADS - 1) / TIF_STITCH_THREADS),
-                           (unsigned)((batch + TIF_GATHER_IMGS - 1) / TIF_GATHER_IMGS));
+    const unsigned gather_by = (unsigned)((batch + TIF_GATHER_IMGS - 1) / TIF_GATHER_IMGS);
+    const dim3 gather0_grid((unsigned)((tile_threads(w, h) + TIF_GATHER0_THREADS - 1) / TIF_GATHER0_THREADS), gather_by);
+    const dim3 gather1_grid((unsigned)((tile_threads(w, h) + TIF_GATHER1_THREADS - 1) / TIF_GATHER1_THREADS), gather_by);
+    const dim3 gather2_grid((unsigned)((tile_threads(w, h) + TIF_GATHER2_THREADS - 1) / TIF_GATHER2_THREADS), gather_by);
     const size_t lift_smem = sizeof(LiftFace) * n_faces;
     const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_GATHER_IMGS * n_faces;
 #define GATHER_ARGS                                                                                                  \
@@ -1078,9 +1093,9 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) {
             if (blend == TIF_BLEND_STRAIGHTFORWARD)
-                k_gather<0><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+                k_gather<0><<<gather0_grid, TIF_GATHER0_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             else
-                k_gather<3><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+                k_gather<3><<<gather0_grid, TIF_GATHER0_THREADS, gather_smem, stream>>>(GATHER_ARGS);
         }
     } else if (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) {
         if (!skip_lift)
@@ -1088,7 +1103,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
                                                              records, h, w, plan->tangent_w, n_tangent, batch);
         TIF_CUDA_CHECK(cudaGetLastError());
-        if (pass_mask & 3) k_gather<4><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        if (pass_mask & 3) k_gather<4><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
         if (pass_mask & (1 | 8)) {
             if (pass_mask & 1) TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
@@ -1098,10 +1113,10 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch);
             TIF_CUDA_CHECK(cudaGetLastError());
-            if (pass_mask & 1) k_gather<1><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+            if (pass_mask & 1) k_gather<1><<<gather1_grid, TIF_GATHER1_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
-        if (pass_mask & 2) k_gather<2><<<gather_grid, TIF_STITCH_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        if (pass_mask & 2) k_gather<2><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     }
 #undef GATHER_ARGS
     TIF_CUDA_CHECK(cudaGetLastError());

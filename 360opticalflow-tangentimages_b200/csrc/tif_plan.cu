@@ -474,11 +474,11 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         }
     }
     {
-        // stage-1 tile table: the bounding box of the taps of every 16 x 16 tangent patch.  Patches whose box fits a
+        // stage-1 tile table: the bounding box of the taps of every 16 x 8 tangent patch.  Patches whose box fits a
         // shared-memory stage are resampled from a staged copy of the box; the rest (polar caps, the seam, patches
         // spanning two faces) keep the direct gathers.
-        const int tile = TIF_S1_TILE;
-        const int tiles_x = (tangent_w + tile - 1) / tile, tiles_y = (int)((n_rows + tile - 1) / tile);
+        const int tile_w = TIF_S1_TILE_W, tile_h = TIF_S1_TILE_H;
+        const int tiles_x = (tangent_w + tile_w - 1) / tile_w, tiles_y = (int)((n_rows + tile_h - 1) / tile_h);
         const size_t n_tiles = (size_t)tiles_x * tiles_y;
         const uint32_t row_bytes = (uint32_t)erp_w * 3u;
         const bool alignable = row_bytes % 16u == 0 && ((size_t)erp_h * row_bytes) % 16u == 0;
@@ -492,8 +492,8 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
             for (int ty = 0; ty < tiles_y; ++ty)
                 for (int tx = 0; tx < tiles_x; ++tx) {
                     uint32_t x_lo = 0xffffffffu, x_hi = 0, y_lo = 0xffffffffu, y_hi = 0;
-                    for (int64_t y = (int64_t)ty * tile; y < (int64_t)(ty + 1) * tile && y < n_rows; ++y)
-                        for (int x = tx * tile; x < (tx + 1) * tile && x < tangent_w; ++x) {
+                    for (int64_t y = (int64_t)ty * tile_h; y < (int64_t)(ty + 1) * tile_h && y < n_rows; ++y)
+                        for (int x = tx * tile_w; x < (tx + 1) * tile_w && x < tangent_w; ++x) {
                             const uint32_t b = h_base[y * tangent_w + x] & 0x7fffffffu;
                             const uint32_t y0 = b / (uint32_t)erp_w, x0 = b - y0 * (uint32_t)erp_w;
                             x_lo = x0 < x_lo ? x0 : x_lo;

@@ -117,7 +117,7 @@ typedef struct TifPlanInfo {
     int64_t accepted_unique;        /* sum over ERP pixels of accepting faces */
     int64_t referenced_tangent_pixels; /* unique tangent pixels the stitch reads (P_ref) */
     int64_t device_bytes;           /* plan footprint in HBM */
-    int64_t stage1_patches;         /* 16 x 16 tangent patches of tif_erp2ico_u8 ... */
+    int64_t stage1_patches;         /* 16 x 8 tangent patches of tif_erp2ico_u8 ... */
     int64_t stage1_staged_patches;  /* ... and how many of them are resampled through shared memory (0: ERP rows are
                                        not 16-byte multiples, every patch takes the direct gathers) */
 } TifPlanInfo;

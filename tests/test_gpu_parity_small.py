@@ -130,7 +130,7 @@ def test_oracle_agrees_at_mid_size(pkg, smooth, offset):
 def test_sizes_that_are_not_tile_multiples(pkg, erp_h, wt):
     """Edge sizes: tangent width not a multiple of the 8-wide warp tile, ERP height not a multiple of 4, a tangent
     image wider than the ERP is tall.  ERP rows of 6 H bytes are 16-byte multiples only for H = 88: that case takes
-    the shared-memory staged resampler with partial 16 x 16 patches, the others the direct gathers (H = 45: an odd
+    the shared-memory staged resampler with partial 16 x 8 patches, the others the direct gathers (H = 45: an odd
     height, images that are not multiples of 4 bytes).  uint8 exact,
     membership implied by the flow parity."""
     src, tar = synth.synth_images(erp_h, 13)
