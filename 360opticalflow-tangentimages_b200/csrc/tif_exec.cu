@@ -665,11 +665,13 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     const float sp = cy0 * inv_n, cp = hp2 * inv_hp * inv_n;       // sin / cos of the pixel's latitude
     const float cos_d = bz0 * inv_hp, sin_d = a0 * inv_hp;        // longitude of the pixel against the face meridian
     const float s0 = (float)F.sin_phi0, c0 = (float)F.cos_phi0;
-    const float e1 = s0 * sin_d, e2 = cos_d;
-    const float n1 = fmaf(s0 * sp, cos_d, c0 * cp), n2c = -sp * sin_d;
-    const float u1 = fmaf(-s0 * cp, cos_d, c0 * sp), u2 = cp * sin_d;
+    // east / north / radial components of the tangent-plane step per pixel of flow: the pixel-to-gnomonic scales
+    // (kx, -ky) are folded into the frame, so that E, N, U are plain linear forms of (u, v)
+    const float kxf = (float)F.kx, nkyf = -(float)F.ky;
+    const float e1 = nkyf * (s0 * sin_d), e2 = kxf * cos_d;
+    const float n1 = nkyf * fmaf(s0 * sp, cos_d, c0 * cp), n2c = kxf * (-sp * sin_d);
+    const float u1 = nkyf * fmaf(-s0 * cp, cos_d, c0 * sp), u2 = kxf * (cp * sin_d);
     const float u0 = n2 * inv_n;
-    const float kxf = (float)F.kx, kyf = (float)F.ky;
     const float u_scale = (float)((double)erp_w / TIF_TWO_PI), v_scale = (float)((double)erp_h / TIF_PI);
     // own ERP position (plan stage 1), split into integer and fraction for the target sample
     int exi = 0, eyi = 0;
@@ -706,7 +708,7 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
             disp_x[j] = disp_y[j] = fx[j] = fy[j] = 0.0f;
             if (b >= batch) continue;
             const float2 uv = uvs[bb];
-            const float dx = uv.x * kxf, dy = -uv.y * kyf;
+            const float dx = uv.x, dy = uv.y;          // the scales live in e1 .. u2
             const float E = fmaf(dy, e1, dx * e2);
             const float N = fmaf(dy, n1, dx * n2c);
             const float U = fmaf(dy, u1, fmaf(dx, u2, u0));
