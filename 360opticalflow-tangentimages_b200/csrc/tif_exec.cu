@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(TIF_LIFT_THREADS_OF(SAMPLE), TIF_LIFT_BLOCKS_O
 k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
-       void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch) {
+       void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, float u_scale,
+       float v_scale /* W / 2 pi, H / pi: radians -> ERP pixels, rounded once on the host */) {
     constexpr bool NW = SAMPLE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
@@ -672,7 +673,6 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     const float n1 = nkyf * fmaf(s0 * sp, cos_d, c0 * cp), n2c = kxf * (-sp * sin_d);
     const float u1 = nkyf * fmaf(-s0 * cp, cos_d, c0 * sp), u2 = kxf * (cp * sin_d);
     const float u0 = n2 * inv_n;
-    const float u_scale = (float)((double)erp_w / TIF_TWO_PI), v_scale = (float)((double)erp_h / TIF_PI);
     // own ERP position (plan stage 1), split into integer and fraction for the target sample
     int exi = 0, eyi = 0;
     float exf = 0.0f, eyf = 0.0f;
@@ -1086,12 +1086,13 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
 #define GATHER_ARGS                                                                                                  \
     plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
         erp_src, nw_sums, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
+    const float lift_u_scale = (float)((double)w / TIF_TWO_PI), lift_v_scale = (float)((double)h / TIF_PI);
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
         if (!skip_lift)
             k_lift<0><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                                  n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
-                                                                 records, h, w, plan->tangent_w, n_tangent, batch);
+                                                                 records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) {
             if (blend == TIF_BLEND_STRAIGHTFORWARD)
@@ -1103,7 +1104,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if (!skip_lift)
             k_lift<2><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
-                                                             records, h, w, plan->tangent_w, n_tangent, batch);
+                                                             records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) k_gather<4><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
@@ -1113,7 +1114,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
                 k_lift<1><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
                                                                     plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
-                                                                    n_tangent, batch);
+                                                                    n_tangent, batch, lift_u_scale, lift_v_scale);
             TIF_CUDA_CHECK(cudaGetLastError());
             if (pass_mask & 1) k_gather<1><<<gather1_grid, TIF_GATHER1_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             TIF_CUDA_CHECK(cudaGetLastError());
