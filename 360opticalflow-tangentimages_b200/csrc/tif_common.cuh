@@ -78,7 +78,8 @@ struct TifPlan {
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order
     float2* d_s2_snap;             // [K][H*W] ERP position of the sample's tangent pixel minus the ERP pixel (x wrapped to +-W/2)
     uint8_t* d_ref_mark;           // [P] 1 where a tangent pixel is referenced by at least one ERP pixel
-    int32_t* d_ref_list;           // [P_ref] the referenced tangent pixels, in 8x4-tile order (work list of k_lift)
+    int32_t* d_ref_list;           // [P_ref] the referenced tangent pixels, in 8x4-tile order (work list of k_lift), each as
+                                   //  face << 25 | row inside the face << 11 | column
     double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
 };
 

@@ -639,8 +639,10 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     // the work list holds only tangent pixels that some ERP pixel reads (half of the stack), in tile order
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_ref) return;
-    const int p = __ldg(ref_list + idx);
-    const int trow = p / tangent_w, tcol = p - trow * tangent_w;
+    const uint32_t ref = (uint32_t)__ldg(ref_list + idx);       // face << 25 | row inside the face << 11 | column
+    const LiftFace& F = sh_face[TIF_E_FACE(ref)];
+    const int tcol = (int)TIF_E_IX(ref), trow = F.first_row + (int)TIF_E_IY(ref);
+    const int p = trow * tangent_w + tcol;
     const int b0 = blockIdx.y * TIF_LIFT_IMGS;
     const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
     // all flows of the chunk are requested before anything depends on them (the kernel is latency bound)
@@ -648,7 +650,6 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
 #pragma unroll
     for (int bb = 0; bb < TIF_LIFT_IMGS; ++bb)
         uvs[bb] = (b0 + bb < batch) ? __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p)) : make_float2(0.0f, 0.0f);
-    const LiftFace& F = sh_face[__ldg(row_face + trow)];
 
     // ---- per tangent pixel, once for the chunk of images -------------------------------------------------
     float a0, bz0, cy0;

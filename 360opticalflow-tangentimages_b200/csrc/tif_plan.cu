@@ -448,8 +448,19 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     {
         // work list of the lift kernel: referenced tangent pixels in 8 x 4 tile order, so that a warp works on a
         // compact patch of one face (plan-time bookkeeping through the host: 1 byte per tangent pixel)
+        // An entry names its pixel as face << 25 | row inside the face << 11 | column (the layout of the membership
+        // entries), so that the kernel needs neither a division by the tangent width nor the row -> face table.
         uint8_t* h_mark = (uint8_t*)malloc((size_t)n_tangent);
         int32_t* h_list = (int32_t*)malloc(sizeof(int32_t) * (size_t)(plan->referenced_tangent_pixels + 1));
+        int32_t* h_face_of_row = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_rows);
+        int32_t* h_first_row = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_faces);
+        {
+            int64_t row = 0;
+            for (int f = 0; f < n_faces; ++f) {
+                h_first_row[f] = (int32_t)row;
+                for (int i = 0; i < faces[f].tangent_h; ++i) h_face_of_row[row++] = f;
+            }
+        }
         cudaError_t ea = cudaMemcpy(h_mark, plan->d_ref_mark, (size_t)n_tangent, cudaMemcpyDeviceToHost);
         int64_t n_list = 0;
         if (ea == cudaSuccess) {
@@ -457,9 +468,13 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
                 for (int tx = 0; tx < tangent_w; tx += 8)
                     for (int64_t y = ty; y < ty + 4 && y < n_rows; ++y)
                         for (int x = tx; x < tx + 8 && x < tangent_w; ++x)
-                            if (h_mark[y * tangent_w + x] && n_list < plan->referenced_tangent_pixels)
-                                h_list[n_list++] = (int32_t)(y * tangent_w + x);
+                            if (h_mark[y * tangent_w + x] && n_list < plan->referenced_tangent_pixels) {
+                                const int f = h_face_of_row[y];
+                                h_list[n_list++] = (int32_t)(((uint32_t)f << 25) | ((uint32_t)(y - h_first_row[f]) << 11) | (uint32_t)x);
+                            }
         }
+        free(h_face_of_row);
+        free(h_first_row);
         int st = dev_alloc(&plan->d_ref_list, (size_t)(plan->referenced_tangent_pixels + 1), plan);
         cudaError_t eb = cudaSuccess;
         if (st == TIF_OK) eb = cudaMemcpy(plan->d_ref_list, h_list, sizeof(int32_t) * (size_t)n_list, cudaMemcpyHostToDevice);
