@@ -731,9 +731,23 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
                     fy[j] = (float)(end[1] - fay);
                 }
             } else {
-                const float dtheta = atan2_fast(E, rm);
+                // atan2(E, rm) = 2 atan(E / (h + rm)) with h = |(E, rm)|: the reciprocal of h + rm is needed anyway
+                // (next line), and the half angle stays inside the short polynomial up to a 45 degree longitude step
+                const float r_hp = rcp_newton(fmaxf(h + rm, 1e-30f));
+                const float q_half = E * r_hp;
+                float dtheta;
+                if (rm > 0.0f && fabsf(q_half) <= 0.4143f) {
+                    const float s_half = q_half * q_half;
+                    float pr = 7.901539654e-02f;
+                    pr = fmaf(pr, s_half, -1.382412463e-01f);
+                    pr = fmaf(pr, s_half, 1.997184753e-01f);
+                    pr = fmaf(pr, s_half, -3.333275616e-01f);
+                    dtheta = 2.0f * fmaf(pr, q_half * s_half, q_half);
+                } else {
+                    dtheta = atan2_fast(E, rm);
+                }
                 // h sin(lat) - z cos(lat) = -N + (h - rm) sin(lat), and h - rm = E^2 / (h + rm)
-                const float yc = rm > 0.0f ? fmaf(E * E, sp * rcp_newton(h + rm), -N) : fmaf(h, sp, -z * cp);
+                const float yc = rm > 0.0f ? fmaf(E * E, sp * r_hp, -N) : fmaf(h, sp, -z * cp);
                 const float xc = fmaf(z, sp, h * cp);
                 const float dcolat = atan2_fast(yc, xc);
                 disp_x[j] = dtheta * u_scale;
