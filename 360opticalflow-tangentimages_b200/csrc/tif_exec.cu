@@ -855,8 +855,8 @@ __global__ void __launch_bounds__(TIF_GATHER_THREADS_OF(MODE), (MODE == 2 || MOD
 k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
          const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
          const double* __restrict__ face_mult_sum, const void* __restrict__ records, const uint8_t* __restrict__ erp_src,
-         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, float* __restrict__ out, int erp_h, int erp_w,
-         int tangent_w, int n_tangent, int batch, int wrap_around) {
+         unsigned long long* __restrict__ nw_sums /* [B][F] fixed point */, const float* __restrict__ nw_scale /* [B][F] */,
+         float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, int wrap_around) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* sh_offset = reinterpret_cast<int*>(smem_raw);                       // [F] first pixel of each face
     unsigned* sh_sum = reinterpret_cast<unsigned*>(sh_offset + n_faces);      // MODE 1: [CHUNK][F] partial sums
@@ -867,17 +867,9 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     if (MODE == 1) {
         for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x) sh_sum[i] = 0u;
     } else if (MODE == 2) {
-        for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x) {
-            const int bb = i / n_faces, f = i - bb * n_faces;
-            float inv = 0.0f;
-            if (b0 + bb < batch) {
-                // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
-                const double total = (double)nw_sums[(size_t)(b0 + bb) * n_faces + f] / (double)TIF_NW_FIXED_SCALE;
-                const double mean = total / (3.0 * face_mult_sum[f]);
-                inv = (float)(-1.4426950408889634 / (3.0 * mean));       // exp(-x / (3 mean)) = 2^(x inv)
-            }
-            sh_inv_mean[i] = inv;
-        }
+        // [b0 .. b0 + IMGS) x F is one contiguous run of the table k_nw_face_scale wrote
+        for (int i = threadIdx.x; i < TIF_GATHER_IMGS * n_faces; i += blockDim.x)
+            sh_inv_mean[i] = (b0 * n_faces + i < batch * n_faces) ? nw_scale[(size_t)b0 * n_faces + i] : 0.0f;
     }
     __syncthreads();
 
@@ -1060,11 +1052,30 @@ static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
     return (raw + 255) / 256 * 256;
 }
 
+// ... followed by [B][F] float: -log2(e) / (3 mean_f) of every face and image (k_nw_face_scale)
+static size_t nw_header_bytes(const TifPlan* plan, int batch) {
+    const size_t raw = (size_t)batch * plan->n_faces * sizeof(float);
+    return nw_sums_bytes(plan, batch) + (raw + 255) / 256 * 256;
+}
+
+// The normwarp weights are exp(-sum_ch|diff| / (3 mean_f)) = 2^(sum_ch|diff| * scale_f): one thread per face and image
+// turns the fixed-point sums of k_gather<1> into scale_f, instead of every block of k_gather<2> repeating the two
+// float64 divisions for all its faces.
+__global__ void k_nw_face_scale(const unsigned long long* __restrict__ nw_sums, const double* __restrict__ face_mult_sum,
+                                int n_faces, int batch, float* __restrict__ scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * n_faces) return;
+    // np.mean over all accepted samples x 3 channels, duplicates counted (projection.py:57)
+    const double total = (double)nw_sums[i] / (double)TIF_NW_FIXED_SCALE;
+    const double mean = total / (3.0 * face_mult_sum[i % n_faces]);
+    scale[i] = (float)(-1.4426950408889634 / (3.0 * mean));         // exp(-x / (3 mean)) = 2^(x scale)
+}
+
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
     const size_t rec = (blend == TIF_BLEND_NORMWARP || blend == TIF_BLEND_CUBEMAP_WARP_ERROR) ? sizeof(uint4) : sizeof(float2);
     const size_t padded = (size_t)(batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK * TIF_BATCH_CHUNK;      // whole chunks
-    return (int64_t)(nw_sums_bytes(plan, batch) + padded * (size_t)plan->tangent_pixels * rec);
+    return (int64_t)(nw_header_bytes(plan, batch) + padded * (size_t)plan->tangent_pixels * rec);
 }
 
 extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, const uint8_t* erp_src,
@@ -1087,7 +1098,8 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const int h = plan->erp_h, w = plan->erp_w, n_faces = plan->n_faces;
     const int n_tangent = (int)plan->tangent_pixels;
     unsigned long long* nw_sums = (unsigned long long*)scratch;
-    void* records = (unsigned char*)scratch + nw_sums_bytes(plan, batch);
+    float* nw_scale = (float*)((unsigned char*)scratch + nw_sums_bytes(plan, batch));
+    void* records = (unsigned char*)scratch + nw_header_bytes(plan, batch);
     const int n_ref = (int)plan->referenced_tangent_pixels;
     const unsigned lift_by = (unsigned)((batch + TIF_LIFT_IMGS - 1) / TIF_LIFT_IMGS);
     const dim3 lift_grid((unsigned)((n_ref + TIF_LIFT_THREADS - 1) / TIF_LIFT_THREADS), lift_by);
@@ -1100,7 +1112,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const size_t gather_smem = sizeof(int) * n_faces + sizeof(unsigned) * TIF_GATHER_IMGS * n_faces;
 #define GATHER_ARGS                                                                                                  \
     plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
-        erp_src, nw_sums, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
+        erp_src, nw_sums, nw_scale, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
     const float lift_u_scale = (float)((double)w / TIF_TWO_PI), lift_v_scale = (float)((double)h / TIF_PI);
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
@@ -1134,7 +1146,12 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             if (pass_mask & 1) k_gather<1><<<gather1_grid, TIF_GATHER1_THREADS, gather_smem, stream>>>(GATHER_ARGS);
             TIF_CUDA_CHECK(cudaGetLastError());
         }
-        if (pass_mask & 2) k_gather<2><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        if (pass_mask & 2) {
+            k_nw_face_scale<<<(unsigned)((batch * n_faces + 127) / 128), 128, 0, stream>>>(nw_sums, plan->d_face_mult_sum, n_faces,
+                                                                                          batch, nw_scale);
+            TIF_CUDA_CHECK(cudaGetLastError());
+            k_gather<2><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        }
     }
 #undef GATHER_ARGS
     TIF_CUDA_CHECK(cudaGetLastError());

@@ -75,7 +75,7 @@ class HostPipeline:
                     _ops.erp2ico_out(p, s["tar"][:n], True, s["tan_tar"][:n])
                     _ops.ico2erp_flow_out(p, s["flows"][:n], s["src"][:n], s["tar"][:n], self.blend, self.wrap_around,
                                           s["out"][:n], s["scratch"])
-                    launches += 4 if self.blend == _lib.BLEND_STRAIGHTFORWARD else 5
+                    launches += 4 if self.blend == _lib.BLEND_STRAIGHTFORWARD else 6
                     s["ev_run"].record(self.s_run)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(s["ev_run"])

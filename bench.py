@@ -240,7 +240,7 @@ def run_ours(args):
     scratch = torch.empty(max(int(plan.lib.tif_ico2erp_scratch_bytes(plan.handle, B, lib.BLEND_NORMWARP)), 8),
                           dtype=torch.uint8, device=device)
     # erp2ico x2; stitch = k_lift + k_gather (normwarp: k_lift, k_gather<sums>, k_gather<blend>)
-    launches_per_step = 4 if blend == lib.BLEND_STRAIGHTFORWARD else 5
+    launches_per_step = 4 if blend == lib.BLEND_STRAIGHTFORWARD else 6
 
     # The two resamplings and the stitch are independent of each other: they run on separate streams so that
     # their blocks share the SMs (each kernel alone is issue/latency bound and leaves slots idle).
