@@ -52,6 +52,14 @@
 #define TIF_S1_STAGED_SHARE 0.93
 #endif
 
+struct LiftFace {          // per-face constants of the end-point lift (k_lift), built once with the plan
+    double sin_phi0, cos_phi0;
+    double xmin, ymax;
+    double kx, ky;              // 1 / pixel2gnomonic ratios (gnomonic_projection.py:188-194)
+    int first_row;              // first row of the face in the tangent stack
+    int pad[3];                 // 64 bytes: copied to shared memory in 16-byte pieces
+};
+
 struct TifPlan {
     int n_faces, erp_h, erp_w, tangent_w;
     int kind;                      // TIF_PLAN_ICOSAHEDRON | TIF_PLAN_CUBEMAP
@@ -62,6 +70,7 @@ struct TifPlan {
     int64_t device_bytes;
     TifFace* h_faces;              // host copy
     TifFace* d_faces;              // [F]
+    LiftFace* d_lift_faces;        // [F]
     int32_t* d_pix_face;           // [P / Wt] face of every tangent row (ragged stacks)
     // stage 1: per tangent pixel
     uint32_t* d_s1_base;           // [P] (y0*W + x0) | TIF_S1_OUTSIDE ; taps (x0,x0+1) x (y0,y0+1) are always in range

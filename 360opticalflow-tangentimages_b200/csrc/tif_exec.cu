@@ -473,13 +473,6 @@ static_assert(TIF_BATCH_CHUNK % TIF_GATHER_IMGS == 0, "k_gather groups must not 
 #define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
 #define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
 
-struct LiftFace {          // per-face constants of the end-point lift, staged in shared memory
-    double sin_phi0, cos_phi0;
-    double xmin, ymax;
-    double kx, ky;              // 1 / pixel2gnomonic ratios (gnomonic_projection.py:188-194)
-    int first_row;              // first row of the face in the tangent stack
-    int pad;
-};
 
 // reciprocal for x in the normal range: MUFU.RCP + one Newton step (no denormal / range branches)
 __device__ __forceinline__ float rcp_newton(float x) {
@@ -614,7 +607,7 @@ static_assert(TIF_LIFT_IMGS % TIF_LIFT_GROUP == 0, "the images of a thread are s
 // images stay uint8, so scipy rounds every sample, projection.py:103-104).
 template <int SAMPLE>
 __global__ void __launch_bounds__(TIF_LIFT_THREADS_OF(SAMPLE), TIF_LIFT_BLOCKS_OF(SAMPLE))
-k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict__ row_face,
+k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __restrict__ row_face,
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
        void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, float u_scale,
@@ -622,19 +615,10 @@ k_lift(const TifFace* __restrict__ faces, int n_faces, const int32_t* __restrict
     constexpr bool NW = SAMPLE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
-    for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
-        const TifFace& F = faces[f];
-        LiftFace lf;
-        lf.sin_phi0 = F.sin_phi0;
-        lf.cos_phi0 = F.cos_phi0;
-        lf.xmin = F.xmin;
-        lf.ymax = F.ymax;
-        lf.kx = 1.0 / F.p2g_x;
-        lf.ky = 1.0 / F.p2g_y;
-        lf.first_row = F.pix_offset / tangent_w;
-        lf.pad = 0;
-        sh_face[f] = lf;
-    }
+    // the per-face constants come ready from the plan (the reciprocals are float64 divisions): 16-byte copies
+    static_assert(sizeof(LiftFace) % 16 == 0, "LiftFace is copied in 16-byte pieces");
+    for (int i = threadIdx.x; i < n_faces * (int)(sizeof(LiftFace) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(sh_face)[i] = __ldg(reinterpret_cast<const uint4*>(lift_faces) + i);
     __syncthreads();
     // the work list holds only tangent pixels that some ERP pixel reads (half of the stack), in tile order
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,7 +1101,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
         if (!skip_lift)
-            k_lift<0><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<0><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                                  n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
                                                                  records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
         TIF_CUDA_CHECK(cudaGetLastError());
@@ -1129,7 +1113,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         }
     } else if (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) {
         if (!skip_lift)
-            k_lift<2><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
+            k_lift<2><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
                                                              records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
         TIF_CUDA_CHECK(cudaGetLastError());
@@ -1138,7 +1122,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if (pass_mask & (1 | 8)) {
             if (pass_mask & 1) TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             if (!skip_lift)
-                k_lift<1><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_faces, n_faces, plan->d_pix_face,
+                k_lift<1><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face,
                                                                     plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
                                                                     tangent_flow, erp_tar, records, h, w, plan->tangent_w,
                                                                     n_tangent, batch, lift_u_scale, lift_v_scale);

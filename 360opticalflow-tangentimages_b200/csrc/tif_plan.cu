@@ -256,6 +256,7 @@ static int dev_alloc(T** p, size_t n, TifPlan* plan) {
 extern "C" int tif_plan_destroy(TifPlan* plan) {
     if (!plan) return TIF_OK;
     cudaFree(plan->d_faces);
+    cudaFree(plan->d_lift_faces);
     cudaFree(plan->d_pix_face);
     cudaFree(plan->d_s1_base);
     cudaFree(plan->d_s1_frac64);
@@ -357,6 +358,7 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     }
 
     PLAN_TRY(dev_alloc(&plan->d_faces, n_faces, plan));
+    PLAN_TRY(dev_alloc(&plan->d_lift_faces, n_faces, plan));
     PLAN_TRY(dev_alloc(&plan->d_pix_face, n_rows, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_base, n_tangent, plan));
     PLAN_TRY(dev_alloc(&plan->d_s1_frac64, n_tangent, plan));
@@ -381,6 +383,24 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     (void)scratch_bytes;
 
     PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_faces, faces, sizeof(TifFace) * n_faces, cudaMemcpyHostToDevice, stream), "copy faces"));
+    LiftFace* h_lift = (LiftFace*)malloc(sizeof(LiftFace) * (size_t)n_faces);
+    for (int f = 0; f < n_faces; ++f) {
+        LiftFace lf;
+        lf.sin_phi0 = faces[f].sin_phi0;
+        lf.cos_phi0 = faces[f].cos_phi0;
+        lf.xmin = faces[f].xmin;
+        lf.ymax = faces[f].ymax;
+        lf.kx = 1.0 / faces[f].p2g_x;
+        lf.ky = 1.0 / faces[f].p2g_y;
+        lf.first_row = faces[f].pix_offset / tangent_w;
+        lf.pad[0] = lf.pad[1] = lf.pad[2] = 0;
+        h_lift[f] = lf;
+    }
+    {
+        const cudaError_t el = cudaMemcpy(plan->d_lift_faces, h_lift, sizeof(LiftFace) * n_faces, cudaMemcpyHostToDevice);
+        free(h_lift);
+        PLAN_TRY(cuda_status(el, "copy lift faces"));
+    }
     PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_pix_face, h_row_face, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, stream), "copy row->face"));
     PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gx, tables->gnom_x, sizeof(double) * n_faces * tangent_w, cudaMemcpyHostToDevice, stream), "copy gnom_x"));
     PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gy, tables->gnom_y, sizeof(double) * n_rows, cudaMemcpyHostToDevice, stream), "copy gnom_y"));
