@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 UNITS = {
     "tif_plan.cu": ["-fmad=false"],
     "tif_exec.cu": [],
+    "tif_warp.cu": [],
     "tif_rotate.cu": [],
     "tif_metrics.cu": [],
 }
@@ -49,7 +50,7 @@ def build_library(force=False, verbose=False):
     and the library is replaced atomically."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     defs = os.environ.get("TIF_NVCC_DEFS", "").split()        # experiment knobs, e.g. -DTIF_STITCH_MIN_BLOCKS=6
-    sources = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "tif_common.cuh"),
+    sources = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "tif_common.cuh"), os.path.join(CSRC, "tif_bilinear.cuh"),
                                                         os.path.join(INCLUDE, "tif_b200.h")]
     want = _digest(sources, (ARCH, COMMON[:4], sorted(UNITS.items()), defs))
     stamp = os.path.join(BUILD_DIR, "libtif_b200.stamp")

@@ -410,5 +410,10 @@ def get_plan(padding_size, erp_height, tangent_width, device=None, level=0, kind
 
 
 def clear_plans():
+    """Drop every cached plan; their device tables are freed as soon as no caller holds a plan any more."""
+    import sys
     with _plans_lock:
         _plans.clear()
+    ops = sys.modules.get(__package__ + "._ops")
+    if ops is not None:
+        ops.unregister_all()

@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
 
 TIF_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 BLEND_STRAIGHTFORWARD = 0
 BLEND_NORMWARP = 1
 BLEND_CUBEMAP_INSIDE = 2
@@ -23,6 +23,9 @@ DTYPE_F32 = 0
 DTYPE_F64 = 1
 MAX_FACES = 128
 MAX_TANGENT_DIM = 2048
+IPC_HANDLE_BYTES = 64
+PACK_RGB = 0
+PACK_GRAY_CV = 1
 
 
 class TifFace(C.Structure):
@@ -71,11 +74,13 @@ SYMBOLS = {
     "tif_plan_export_stage1": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "tif_plan_export_stage2": (C.c_int, [_VP, _VP, _VP, _VP]),
     "tif_erp2ico_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "tif_pack_tangent_u8": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "tif_ico2erp_scratch_bytes": (C.c_int64, [_VP, C.c_int, C.c_int]),
     "tif_ico2erp_flow_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
     "tif_ico2erp_flow_f32_ex": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, _VP]),
     "tif_warp_backward_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_warp_backward_f32": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "tif_warp_backward_f64": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_flow_warp_meshgrid": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_rotation_motion_vector_f64": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_flow_cross_covariance_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
@@ -89,6 +94,12 @@ SYMBOLS = {
     "tif_flow_error_mats": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "tif_reduce_f64_scratch_bytes": (C.c_int64, [C.c_int]),
     "tif_reduce_f64": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP]),
+    "tif_ipc_alloc": (C.c_int, [C.POINTER(_VP), C.c_int64]),
+    "tif_ipc_free": (C.c_int, [_VP]),
+    "tif_ipc_export": (C.c_int, [_VP, C.c_char_p]),
+    "tif_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    "tif_ipc_close": (C.c_int, [_VP]),
+    "tif_ipc_copy_async": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "tif_erp_of_wraparound": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _VP]),
 }
 

@@ -5,17 +5,30 @@ stream, and the ops make the kernels addressable from torch programs.  Every op 
 and launches hand-written sm_100a kernels through ctypes; there is no eager / CPU implementation
 registered, so calling one with CPU tensors raises.
 """
+import itertools
+import weakref
+
 import torch
 
 from . import _geometry, _lib
 
-_registry = {}          # plan id -> Plan (custom ops cannot take Python objects)
+# op handle -> Plan (custom ops cannot take Python objects).  Handles are a monotonically increasing counter, never
+# reused, and the registry holds the plans weakly: dropping the last strong reference (`_geometry.clear_plans()`)
+# lets Plan.__del__ run tif_plan_destroy and return the plan's HBM.
+_registry = weakref.WeakValueDictionary()
+_next_handle = itertools.count(1)
 
 
 def register_plan(plan):
-    pid = id(plan)
-    _registry[pid] = plan
-    return pid
+    handle = getattr(plan, "op_handle", None)
+    if handle is None:
+        handle = plan.op_handle = next(_next_handle)
+    _registry[handle] = plan
+    return handle
+
+
+def unregister_all():
+    _registry.clear()
 
 
 def _stream():
@@ -59,13 +72,15 @@ def _erp2ico(erp, plan, full_face_image):
 
 
 def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out, scratch=None, pass_mask=3):
-    """tif_ico2erp_flow_f32 on the current stream into a caller-owned [B,H,W,2] float32 tensor.
+    """tif_ico2erp_flow_f32 on the current stream into a caller-owned [B,H,W,2] float32 tensor, or -- `out` given as an
+    int -- to a raw device address with room for it (a slice of a peer-mapped sharding.PeerGatherBuffer).
     Inputs must be contiguous; `scratch` (uint8, >= tif_ico2erp_scratch_bytes) is allocated here when omitted."""
-    _need_cuda(tangent_flow, erp_src, erp_tar, out)
+    out_is_ptr = isinstance(out, int)
+    _need_cuda(tangent_flow, erp_src, erp_tar, None if out_is_ptr else out)
     batch = tangent_flow.shape[0]
     if tangent_flow.dtype != torch.float32 or tuple(tangent_flow.shape) != (batch, p.tangent_pixels, 2) or not tangent_flow.is_contiguous():
         raise ValueError("ico2erp_flow expects contiguous float32 [B,%d,2]" % p.tangent_pixels)
-    if out.dtype != torch.float32 or tuple(out.shape) != (batch, p.erp_h, p.erp_w, 2) or not out.is_contiguous():
+    if not out_is_ptr and (out.dtype != torch.float32 or tuple(out.shape) != (batch, p.erp_h, p.erp_w, 2) or not out.is_contiguous()):
         raise ValueError("ico2erp_flow output must be contiguous float32 [B,%d,%d,2]" % (p.erp_h, p.erp_w))
     src_ptr = tar_ptr = None
     if blend in (_lib.BLEND_NORMWARP, _lib.BLEND_CUBEMAP_WARP_ERROR):
@@ -81,7 +96,8 @@ def ico2erp_flow_out(p, tangent_flow, erp_src, erp_tar, blend, wrap_around, out,
     scratch_ptr = scratch.data_ptr()
     with torch.cuda.device(tangent_flow.device):
         _lib.check(p.lib.tif_ico2erp_flow_f32_ex(p.handle, tangent_flow.data_ptr(), src_ptr, tar_ptr, batch, int(blend),
-                                                 int(wrap_around), out.data_ptr(), scratch_ptr, int(pass_mask), _stream()),
+                                                 int(wrap_around), out if out_is_ptr else out.data_ptr(), scratch_ptr,
+                                                 int(pass_mask), _stream()),
                    "tif_ico2erp_flow_f32")
     return out
 
@@ -119,8 +135,10 @@ def _warp_backward(image, flow, mode):
             fn, name = lib.tif_warp_backward_u8, "tif_warp_backward_u8"
         elif image.dtype == torch.float32:
             fn, name = lib.tif_warp_backward_f32, "tif_warp_backward_f32"
+        elif image.dtype == torch.float64:
+            fn, name = lib.tif_warp_backward_f64, "tif_warp_backward_f64"
         else:
-            raise ValueError("warp_backward image must be uint8 or float32, got %s" % image.dtype)
+            raise ValueError("warp_backward image must be uint8, float32 or float64, got %s" % image.dtype)
         _lib.check(fn(image.data_ptr(), flow.data_ptr(), _flow_dtype(flow), b, h, w, ch, int(mode), out.data_ptr(),
                       _stream()), name)
     return out

@@ -52,6 +52,12 @@
 #define TIF_S1_STAGED_SHARE 0.93
 #endif
 
+// normwarp: tangent pixels (work-list entries) lifted per block of k_lift_nw; their samples follow in the same block
+#define TIF_NW_BLOCK 128
+// images per thread in the stitch kernels (plan entries are read once per chunk); byte offsets into the images of a
+// chunk are 32-bit, which bounds the ERP size a plan accepts
+#define TIF_MAX_CHUNK_IMAGES 4
+
 struct LiftFace {          // per-face constants of the end-point lift (k_lift), built once with the plan
     double sin_phi0, cos_phi0;
     double xmin, ymax;
@@ -90,6 +96,11 @@ struct TifPlan {
     int32_t* d_ref_list;           // [P_ref] the referenced tangent pixels, in 8x4-tile order (work list of k_lift), each as
                                    //  face << 25 | row inside the face << 11 | column
     double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
+    // normwarp (icosahedron plans): the accepted samples regrouped by the tangent pixel they snap to
+    int4* d_ref_pos;               // [P_ref] own ERP position of every work-list entry: floor(x), floor(y), float bits of the fractions
+    uint2* d_smp;                  // [S] work-list order: {ERP row << 16 | column, face << 24 | plane k << 16 | multiplicity << 8 | entry % TIF_NW_BLOCK}
+    uint32_t* d_blk_smp;           // [ceil(P_ref / TIF_NW_BLOCK) + 1] first sample of every block of TIF_NW_BLOCK work-list entries
+    int64_t n_samples;             // S = accepted_unique
 };
 
 void tif_set_error(const char* fmt, ...);

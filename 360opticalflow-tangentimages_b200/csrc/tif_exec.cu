@@ -15,130 +15,8 @@
 #define TIF_BATCH_CHUNK 4          // images per thread (plan entries amortised over the chunk)
 #endif
 
-// ------------------------------------------------------------------------------------------------
-// bilinear with scipy's uint8 rounding
-// ------------------------------------------------------------------------------------------------
-// scipy accumulates p*wy*wx over the taps (y0,x0),(y0,x1),(y1,x0),(y1,x1) in double and stores
-// uint8 as trunc(t + 0.5).  The fast path evaluates t in float32; its error is < 2e-4 for 8-bit
-// data, so the rounding is already decided unless t + 0.5 lies within GUARD of an integer.  Only
-// then (about 1e-3 of samples) is the exact float64 expression evaluated.
-#define TIF_ROUND_GUARD 5.0e-4f
+#include "tif_bilinear.cuh"
 
-__device__ __forceinline__ float bilinear_f32(float p00, float p01, float p10, float p11, float wx0, float wx1,
-                                              float wy0, float wy1) {
-    return (p00 * wy0) * wx0 + (p01 * wy0) * wx1 + (p10 * wy1) * wx0 + (p11 * wy1) * wx1;
-}
-
-__device__ __noinline__ double bilinear_f64_exact(double p00, double p01, double p10, double p11, double fx, double fy) {
-    // scipy get_spline_interpolation_weights(order=1): w0 = 1 - f ; w1 = 1 - w0.  No FMA contraction.
-    const double wx0 = __dsub_rn(1.0, fx), wx1 = __dsub_rn(1.0, wx0);
-    const double wy0 = __dsub_rn(1.0, fy), wy1 = __dsub_rn(1.0, wy0);
-    double t = __dmul_rn(__dmul_rn(p00, wy0), wx0);
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn(p01, wy0), wx1));
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn(p10, wy1), wx0));
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn(p11, wy1), wx1));
-    return t;
-}
-
-__device__ __forceinline__ uint8_t scipy_round_u8(double t) {
-    t = t > 0.0 ? t + 0.5 : 0.0;
-    t = t > 255.0 ? 255.0 : t;
-    return (uint8_t)t;
-}
-
-__device__ __forceinline__ uint8_t round_u8_guarded(float t, float p00, float p01, float p10, float p11, double fx,
-                                                    double fy) {
-    const float r = t + 0.5f;
-    const float fl = floorf(r);
-    const float fr = r - fl;
-    if (fr < TIF_ROUND_GUARD || fr > 1.0f - TIF_ROUND_GUARD)
-        return scipy_round_u8(bilinear_f64_exact((double)p00, (double)p01, (double)p10, (double)p11, fx, fy));
-    return (uint8_t)fminf(fmaxf(fl, 0.0f), 255.0f);
-}
-
-// ------------------------------------------------------------------------------------------------
-// stage 1: ERP -> tangent images
-// ------------------------------------------------------------------------------------------------
-// The two taps of one image row are 6 consecutive bytes (R0 G0 B0 R1 G1 B1) at an arbitrary byte
-// address.  They are fetched with two or three aligned 4-byte loads and funnel-shifted into place
-// instead of six byte loads (the third word is only needed at byte phase 3).  `o` = address & 3.  The
-// caller guarantees that 12 bytes from the aligned address are readable.
-struct RawPair {
-    uint32_t w0, w1, w2;
-};
-
-__device__ __forceinline__ RawPair load_raw_pair(const uint8_t* __restrict__ p, unsigned o) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - o);
-    RawPair r;
-    r.w0 = __ldg(q);
-    r.w1 = __ldg(q + 1);
-    r.w2 = 0u;
-#ifdef TIF_TAP_LOAD3
-    r.w2 = __ldg(q + 2);
-#else
-    if (o == 3) r.w2 = __ldg(q + 2);
-#endif
-    return r;
-}
-
-__device__ __forceinline__ void align_pair(const RawPair& r, unsigned o, uint32_t& lo /* R0 G0 B0 R1 */,
-                                           uint32_t& hi /* G1 B1 . . */) {
-    const unsigned sh = o * 8;
-    lo = __funnelshift_r(r.w0, r.w1, sh);
-    hi = __funnelshift_r(r.w1, r.w2, sh);
-}
-
-__device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ p, unsigned o, uint32_t& lo, uint32_t& hi) {
-    const RawPair r = load_raw_pair(p, o);
-    align_pair(r, o, lo, hi);
-}
-
-__device__ __forceinline__ void load_tap_pair_bytes(const uint8_t* __restrict__ p, uint32_t& lo, uint32_t& hi) {
-    lo = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
-    hi = (uint32_t)__ldg(p + 4) | ((uint32_t)__ldg(p + 5) << 8);
-}
-
-#define TIF_BYTE(w, k) __byte_perm((w), 0u, 0x4440u | (k))       // zero-extended byte k: one PRMT, no XU conversion
-
-// Fixed-point bilinear: weights scaled by 2^24 (exactly rounded from the float64 scipy weights), so the
-// top byte of p00 W00 + p01 W01 + p10 W10 + p11 W11 + 2^23 is scipy's trunc(t + 0.5).  The fixed-point
-// sum is within 255 * 4 * 2^-25 = 3.1e-5 (510 units of 2^-24) of t, and scipy's own float64 sum within
-// 1e-13; if t + 0.5 lies within 1024 units (2^-14) of an integer the exact float64 expression decides
-// instead (3.7e-4 of the pixels, i.e. about one warp in 85 takes the slow branch).
-#define TIF_FIX_ONE 16777216.0
-#define TIF_FIX_HALF 0x00800000u
-#ifndef TIF_FIX_GUARD
-#define TIF_FIX_GUARD 0x00000400u
-#endif
-
-// The accumulator carries the rounding half AND the guard: acc = sum + 2^23 + G.  The sample is undecided when the
-// low 24 bits of acc are below 2 G (one AND, 2 G is a power of two); otherwise subtracting G again would not borrow
-// from the top byte, so the top byte of acc itself is the rounded value.
-static_assert((TIF_FIX_GUARD & (TIF_FIX_GUARD - 1u)) == 0u, "TIF_FIX_GUARD must be a power of two");
-__device__ __forceinline__ uint32_t fix_bilinear(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, uint32_t w00,
-                                                 uint32_t w01, uint32_t w10, uint32_t w11) {
-    return p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (TIF_FIX_HALF + TIF_FIX_GUARD);
-}
-
-__device__ __forceinline__ bool fix_undecided(uint32_t acc) {
-    return (acc & (0x01000000u - 2u * TIF_FIX_GUARD)) == 0u;
-}
-
-// one RGBA output pixel from the two aligned tap pairs (R: bytes 0,3 of lo; G: byte 1 of lo, byte 0 of hi;
-// B: byte 2 of lo, byte 1 of hi)
-__device__ __forceinline__ uint32_t erp2ico_pixel(uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1, uint32_t w00,
-                                                  uint32_t w01, uint32_t w10, uint32_t w11, const double2& fr) {
-    uint32_t ar = fix_bilinear(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), w00, w01, w10, w11);
-    uint32_t ag = fix_bilinear(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), w00, w01, w10, w11);
-    uint32_t ab = fix_bilinear(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), w00, w01, w10, w11);
-    if (fix_undecided(ar) | fix_undecided(ag) | fix_undecided(ab)) {
-        ar = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 0), TIF_BYTE(lo0, 3), TIF_BYTE(lo1, 0), TIF_BYTE(lo1, 3), fr.x, fr.y)) << 24;
-        ag = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 1), TIF_BYTE(hi0, 0), TIF_BYTE(lo1, 1), TIF_BYTE(hi1, 0), fr.x, fr.y)) << 24;
-        ab = (uint32_t)scipy_round_u8(bilinear_f64_exact(TIF_BYTE(lo0, 2), TIF_BYTE(hi0, 1), TIF_BYTE(lo1, 2), TIF_BYTE(hi1, 1), fr.x, fr.y)) << 24;
-    }
-    // top bytes -> R | G<<8 | B<<16 | 255<<24
-    return __byte_perm(__byte_perm(ar, ag, 0x0073u), ab, 0x0710u) | 0xff000000u;
-}
 
 // A warp owns an 8 x 4 tile of the tangent stack, not a 32 x 1 strip: tangent rows are tilted against ERP
 // rows (steeply on the polar faces), so a strip touches ~21 cache lines per tap load and a tile ~9.
@@ -470,7 +348,24 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
 #define TIF_GATHER_IMGS 4
 #endif
 static_assert(TIF_BATCH_CHUNK % TIF_GATHER_IMGS == 0, "k_gather groups must not straddle lift chunks");
-#define TIF_POLAR_SIN2 0.01f          // sin^2(colat) < 0.01
+// The float32 lift keeps ~6e-8 relative precision on the displacement.  Next to a pole a tangent-plane step turns
+// into a longitude displacement of hundreds of ERP pixels and the faces disagree by as much, so under normwarp the
+// photometric weights amplify the rounding of the sampling position: flow error ~ spread x position error, both
+// proportional to W / sin(colatitude).  The float64 band therefore widens with the ERP width: sin(colatitude) below
+// 0.1 W / 2048 (5.7 degrees at 2K, 10.8 at 3840, 11.5 at 4096), measured max error 4e-4 px on IID-noise images.
+struct PolarBand {
+    float sin2;       // tangent pixel: sin^2(colatitude) below this takes the float64 lift
+    float tan;        // end point: horizontal part below tan x |polar part|
+};
+
+static PolarBand polar_band(int erp_w) {
+    double s = 0.1 * (erp_w > 2048 ? (double)erp_w / 2048.0 : 1.0);
+    if (s > 0.7) s = 0.7;
+    PolarBand b;
+    b.sin2 = (float)(s * s);
+    b.tan = (float)(s / sqrt(1.0 - s * s));
+    return b;
+}
 #define TIF_RGB_FIX 8192.0f           // target samples are kept as 21-bit fixed point (3 channels in 64 bits)
 
 
@@ -526,6 +421,11 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     if (ay > ax) r = (float)TIF_HALF_PI - r;
     if (x < 0.0f) r = (float)TIF_PI - r;
     return y < 0.0f ? -r : r;
+}
+
+// 2^23 + byte k of w (one PRMT): differences of two such floats are the exact byte differences
+__device__ __forceinline__ float byte_m(uint32_t w, unsigned k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | k));
 }
 
 // floor / fraction without the XU pipe (|x| < 2^22): round to nearest with the 1.5*2^23 trick, then fix down
@@ -611,7 +511,7 @@ k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __re
        const int32_t* __restrict__ ref_list, int n_ref, const double* __restrict__ s1_ex,
        const double* __restrict__ s1_ey, const float* __restrict__ tflow, const uint8_t* __restrict__ erp_tar,
        void* __restrict__ records, int erp_h, int erp_w, int tangent_w, int n_tangent, int batch, float u_scale,
-       float v_scale /* W / 2 pi, H / pi: radians -> ERP pixels, rounded once on the host */) {
+       float v_scale /* W / 2 pi, H / pi: radians -> ERP pixels, rounded once on the host */, PolarBand polar) {
     constexpr bool NW = SAMPLE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
@@ -646,7 +546,7 @@ k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __re
         cy0 = (float)fma(gy0, F.cos_phi0, F.sin_phi0);
     }
     const float hp2 = fmaf(a0, a0, bz0 * bz0), n2 = hp2 + cy0 * cy0;
-    const bool polar_pixel = hp2 < TIF_POLAR_SIN2 * n2;
+    const bool polar_pixel = hp2 < polar.sin2 * n2;
     const float inv_hp = rsqrtf(fmaxf(hp2, 1e-30f)), inv_n = rsqrtf(n2);
     const float sp = cy0 * inv_n, cp = hp2 * inv_hp * inv_n;       // sin / cos of the pixel's latitude
     const float cos_d = bz0 * inv_hp, sin_d = a0 * inv_hp;        // longitude of the pixel against the face meridian
@@ -701,7 +601,7 @@ k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __re
             const float z = fmaf(U, sp, N * cp);            // part along the polar axis
             const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
             int xi = 0, yi = 0;
-            if (polar_pixel || h < 0.1f * fabsf(z)) {       // pixel or end point within ~5.7 degrees of a pole
+            if (polar_pixel || h < polar.tan * fabsf(z)) {       // pixel or end point inside the polar band
                 float disp[2];
                 double end[2];
                 lift_precise(&F, tcol, trow, uv.x, uv.y, erp_w, erp_h, NW ? s1_ex : nullptr, s1_ey, p, disp, end);
@@ -1029,6 +929,459 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
     }
 }
 
+// ================================================================================================
+// normwarp (face_blending_method="normwarp", projection.py:15-61) in two kernels
+// ================================================================================================
+// The weight of a sample is exp(-mean_ch|tar(end point) - src(ERP pixel)| / G_f) with G_f the mean of that warp error
+// over ALL samples of the face, so every sample's error is needed twice: for G_f and for the blend.
+//
+//   k_lift_nw   a block lifts TIF_NW_BLOCK work-list entries (tangent pixels) x 4 images: displacement to HBM
+//               (32 bytes per tangent pixel and chunk), bilinear sample of the target image at the end point to
+//               SHARED memory.  It then walks the plan's sample list of exactly those tangent pixels (d_smp,
+//               tangent-pixel major, one sample per thread and step, coalesced): |target sample - source pixel| per
+//               channel goes to the dense plane [k][pixel] of the chunk (one 16-byte store for the 4 images, read
+//               back coalesced by the blend) and, times the multiplicity, as fixed point into the face sums.
+//               The target samples never leave the SM, and no pass gathers them per ERP pixel.
+//   k_blend_nw  one thread per ERP pixel x 4 images, faces in index order: flow = displacement + snap offset,
+//               weight = 2^(error x scale_f) from the stored errors, weighted mean, final wrap.
+#ifndef TIF_NW_LIFT_MIN_BLOCKS
+#define TIF_NW_LIFT_MIN_BLOCKS 6
+#endif
+#ifndef TIF_NW_BLEND_THREADS
+#define TIF_NW_BLEND_THREADS 128
+#endif
+#ifndef TIF_NW_BLEND_MIN_BLOCKS
+#define TIF_NW_BLEND_MIN_BLOCKS 8
+#endif
+#define TIF_NW_IMGS 4
+static_assert(TIF_NW_IMGS == TIF_MAX_CHUNK_IMAGES, "tif_plan_create bounds the ERP size by the chunk's byte offsets");
+// per-thread fixed-point error sums are flushed (warp reduction + one shared 64-bit atomic) every this many samples:
+// 32 lanes x 16 samples x 765 x 7 x 1024 < 2^32
+#define TIF_NW_FLUSH 16
+#ifndef TIF_NW_MAX_F32_DISP
+#define TIF_NW_MAX_F32_DISP 32.0f
+#endif
+
+struct LiftFrame {      // local east / north / radial frame of a tangent pixel's own direction (see k_lift)
+    float sp, cp;       // sin / cos of its latitude
+    float e1, e2, n1, n2c, u1, u2, u0;
+    bool polar;
+};
+
+__device__ __forceinline__ LiftFrame lift_frame(const LiftFace& F, int tcol, int frow, float polar_sin2) {
+    const double gx0 = fma((double)tcol, F.kx, F.xmin);
+    const double gy0 = fma(-(double)frow, F.ky, F.ymax);
+    // own direction (east, toward the face meridian, polar axis) before normalisation
+    const float a0 = (float)gx0;
+    const float bz0 = (float)fma(-gy0, F.sin_phi0, F.cos_phi0);
+    const float cy0 = (float)fma(gy0, F.cos_phi0, F.sin_phi0);
+    const float hp2 = fmaf(a0, a0, bz0 * bz0), n2 = hp2 + cy0 * cy0;
+    LiftFrame fr;
+    fr.polar = hp2 < polar_sin2 * n2;
+    const float inv_hp = rsqrtf(fmaxf(hp2, 1e-30f)), inv_n = rsqrtf(n2);
+    fr.sp = cy0 * inv_n;
+    fr.cp = hp2 * inv_hp * inv_n;
+    const float cos_d = bz0 * inv_hp, sin_d = a0 * inv_hp;        // longitude of the pixel against the face meridian
+    const float s0 = (float)F.sin_phi0, c0 = (float)F.cos_phi0;
+    const float kxf = (float)F.kx, nkyf = -(float)F.ky;
+    fr.e1 = nkyf * (s0 * sin_d);
+    fr.e2 = kxf * cos_d;
+    fr.n1 = nkyf * fmaf(s0 * fr.sp, cos_d, c0 * fr.cp);
+    fr.n2c = kxf * (-fr.sp * sin_d);
+    fr.u1 = nkyf * fmaf(-s0 * fr.cp, cos_d, c0 * fr.sp);
+    fr.u2 = kxf * (fr.cp * sin_d);
+    fr.u0 = n2 * inv_n;
+    return fr;
+}
+
+// float32 displacement (ERP pixels) of the end point of one flow vector; false: the end point (or the pixel) lies in
+// the polar band and the float64 route has to decide
+__device__ __forceinline__ bool lift_fast(const LiftFrame& fr, float2 uv, float u_scale, float v_scale, float polar_tan,
+                                          float& disp_x, float& disp_y) {
+    const float dx = uv.x, dy = uv.y;          // the pixel-to-gnomonic scales live in e1 .. u2
+    const float E = fmaf(dy, fr.e1, dx * fr.e2);
+    const float N = fmaf(dy, fr.n1, dx * fr.n2c);
+    const float U = fmaf(dy, fr.u1, fmaf(dx, fr.u2, fr.u0));
+    const float rm = fmaf(U, fr.cp, -N * fr.sp);          // horizontal part in the pixel's meridian plane
+    const float z = fmaf(U, fr.sp, N * fr.cp);            // part along the polar axis
+    const float h = sqrt_newton(fmaxf(fmaf(E, E, rm * rm), 1e-30f));
+    if (fr.polar || h < polar_tan * fabsf(z)) return false;
+    // atan2(E, rm) = 2 atan(E / (h + rm)) with h = |(E, rm)|: the reciprocal of h + rm is needed anyway (below), and
+    // the half angle stays inside the short polynomial up to a 45 degree longitude step
+    const float r_hp = rcp_newton(fmaxf(h + rm, 1e-30f));
+    const float q_half = E * r_hp;
+    float dtheta;
+    if (rm > 0.0f && fabsf(q_half) <= 0.4143f) {
+        const float s_half = q_half * q_half;
+        float pr = 7.901539654e-02f;
+        pr = fmaf(pr, s_half, -1.382412463e-01f);
+        pr = fmaf(pr, s_half, 1.997184753e-01f);
+        pr = fmaf(pr, s_half, -3.333275616e-01f);
+        dtheta = 2.0f * fmaf(pr, q_half * s_half, q_half);
+    } else {
+        dtheta = atan2_fast(E, rm);
+    }
+    // h sin(lat) - z cos(lat) = -N + (h - rm) sin(lat), and h - rm = E^2 / (h + rm)
+    const float yc = rm > 0.0f ? fmaf(E * E, fr.sp * r_hp, -N) : fmaf(h, fr.sp, -z * fr.cp);
+    const float xc = fmaf(z, fr.sp, h * fr.cp);
+    disp_x = dtheta * u_scale;
+    disp_y = atan2_fast(yc, xc) * v_scale;
+    // float32 keeps ~1.2e-7 of the displacement: beyond TIF_NW_MAX_F32_DISP pixels the rounding of the sampling
+    // position (times the image gradient, times the disagreement of the faces, which grows with the displacement
+    // itself) would show in the photometric weights, so such end points take the float64 route as well
+    return fmaxf(fabsf(disp_x), fabsf(disp_y)) <= TIF_NW_MAX_F32_DISP;
+}
+
+template <bool SRC_ALIGNED /* erp_src is 4-byte aligned: source pixels come as aligned words */>
+__global__ void __launch_bounds__(TIF_NW_BLOCK, TIF_NW_LIFT_MIN_BLOCKS)
+k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __restrict__ ref_list, int n_ref,
+          const int4* __restrict__ ref_pos, const double* __restrict__ s1_ex, const double* __restrict__ s1_ey,
+          const uint2* __restrict__ smp, const uint32_t* __restrict__ blk_smp, const float* __restrict__ tflow,
+          const uint8_t* __restrict__ erp_src, const uint8_t* __restrict__ erp_tar, float2* __restrict__ disp_rec,
+          float4* __restrict__ dplane, unsigned long long* __restrict__ nw_sums, int erp_h, int erp_w, int tangent_w,
+          int n_tangent, int max_k, int batch, int wrap_around, float u_scale, float v_scale, PolarBand polar) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // target sample of every (image, tangent pixel) of the block: value = tap (y0, x0) [exact bytes, sh_base] + a small
+    // float remainder [sh_lift.xyz].  Kept apart because |sample - source pixel| is often a few grey levels while the
+    // sample itself is up to 255: as one float32 its rounding (1.5e-5) would reach the weights of smooth images, whose
+    // face mean is small, wherever the faces disagree by hundreds of pixels (garbage estimator flows next to a pole).
+    float4* sh_lift = reinterpret_cast<float4*>(smem_raw);                                   // [4][TIF_NW_BLOCK] remainder rgb, x code
+    uint32_t* sh_base = reinterpret_cast<uint32_t*>(sh_lift + TIF_NW_IMGS * TIF_NW_BLOCK);   // [4][TIF_NW_BLOCK] R | G << 8 | B << 16
+    LiftFace* sh_face = reinterpret_cast<LiftFace*>(sh_base + TIF_NW_IMGS * TIF_NW_BLOCK);   // [F]
+    unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_face + n_faces);   // [4][F]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_faces * (int)(sizeof(LiftFace) / 16); i += TIF_NW_BLOCK)
+        reinterpret_cast<uint4*>(sh_face)[i] = __ldg(reinterpret_cast<const uint4*>(lift_faces) + i);
+    for (int i = tid; i < TIF_NW_IMGS * n_faces; i += TIF_NW_BLOCK) sh_sum[i] = 0ull;
+    __syncthreads();
+
+    const int b0 = blockIdx.y * TIF_NW_IMGS;
+    const int n_img = min(TIF_NW_IMGS, batch - b0);
+    const unsigned image_bytes = (unsigned)erp_h * (unsigned)erp_w * 3u;
+    const unsigned row_bytes = (unsigned)erp_w * 3u;
+    // a chunk past the end of the batch repeats the last image (its results land in scratch that nobody reads)
+    unsigned img_off[TIF_NW_IMGS];
+#pragma unroll
+    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) img_off[bb] = (unsigned)min(bb, n_img - 1) * image_bytes;
+
+    // the first sample-list entry of this thread (phase 2) is requested now: its latency hides behind phase 1
+    const uint32_t s_begin = __ldg(blk_smp + blockIdx.x), s_end = __ldg(blk_smp + blockIdx.x + 1);
+    const unsigned lane = (unsigned)tid & 31u;
+    const uint32_t i_first = s_begin + (uint32_t)tid;
+    const uint2 sm_first = i_first < s_end ? __ldg(smp + i_first) : make_uint2(0u, 0u);
+
+    // ---- phase 1: lift one work-list entry per thread --------------------------------------------------------
+    const int idx = blockIdx.x * TIF_NW_BLOCK + tid;
+    if (idx < n_ref) {
+        const uint32_t ref = (uint32_t)__ldg(ref_list + idx);       // face << 25 | row inside the face << 11 | column
+        const int4 pos = __ldg(ref_pos + idx);                      // own ERP position: floor x, floor y, fractions
+        const LiftFace& F = sh_face[TIF_E_FACE(ref)];
+        const int tcol = (int)TIF_E_IX(ref), frow = (int)TIF_E_IY(ref);
+        const int p = (F.first_row + frow) * tangent_w + tcol;
+        const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
+        float2 uvs[TIF_NW_IMGS];
+#pragma unroll
+        for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
+            uvs[bb] = __ldg(flow_chunk + ((unsigned)min(bb, n_img - 1) * (unsigned)n_tangent + (unsigned)p));
+        const LiftFrame fr = lift_frame(F, tcol, frow, polar.sin2);
+        const float exf = __int_as_float(pos.z), eyf = __int_as_float(pos.w);
+        const uint8_t* __restrict__ tar_chunk = erp_tar + (size_t)b0 * image_bytes;
+        float2* __restrict__ disp_out = disp_rec + ((size_t)blockIdx.y * n_tangent + p) * TIF_NW_IMGS;
+        constexpr int G = TIF_LIFT_GROUP;
+        constexpr unsigned kNoSample = 0xffffffffu;
+#pragma unroll
+        for (int g0 = 0; g0 < TIF_NW_IMGS; g0 += G) {
+            float fx[G], fy[G];
+            int xcode[G];
+            unsigned off[G];             // byte offset of the first tap in the chunk of target images
+            bool tail[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int bb = g0 + j;
+                const float2 uv = uvs[bb];
+                float dx, dy;
+                int xi, yi;
+                if (lift_fast(fr, uv, u_scale, v_scale, polar.tan, dx, dy)) {
+                    int di, dj;
+                    float df, dg;
+                    split_floor(dx, di, df);
+                    split_floor(dy, dj, dg);
+                    xi = pos.x + di;
+                    yi = pos.y + dj;
+                    fx[j] = exf + df;
+                    fy[j] = eyf + dg;
+                    if (fx[j] >= 1.0f) { fx[j] -= 1.0f; xi += 1; }
+                    if (fy[j] >= 1.0f) { fy[j] -= 1.0f; yi += 1; }
+                } else {
+                    float disp[2];
+                    double end[2];
+                    lift_precise(&F, tcol, F.first_row + frow, uv.x, uv.y, erp_w, erp_h, s1_ex, s1_ey, p, disp, end);
+                    dx = disp[0];
+                    dy = disp[1];
+                    const double fax = floor(end[0]), fay = floor(end[1]);
+                    xi = (int)fax;
+                    yi = (int)fay;
+                    fx[j] = (float)(end[0] - fax);
+                    fy[j] = (float)(end[1] - fay);
+                }
+                disp_out[bb] = make_float2(dx, dy);
+                // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
+                // periodic (the seam conventions only move the end point by whole image widths); own position in
+                // [-0.5, W - 0.5) plus at most half a turn: one fold brings x into [0, W).  The gap (W-1, W) and
+                // anything outside [0, H-1] vertically reads 255 outright.
+                if (xi >= erp_w) xi -= erp_w;
+                else if (xi < 0) xi += erp_w;
+                xcode[j] = 2 * xi + (fx[j] != 0.0f ? 1 : 0);
+                const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx[j] == 0.0f));
+                const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy[j] == 0.0f));
+                off[j] = kNoSample;
+                tail[j] = false;
+                if (x_ok & y_ok) {
+                    if (xi == erp_w - 1) { xi = erp_w - 2; fx[j] = 1.0f; }
+                    if (yi == erp_h - 1) { yi = erp_h - 2; fy[j] = 1.0f; }
+                    off[j] = img_off[bb] + (unsigned)((yi * erp_w + xi) * 3);
+                    // the wide loads could leave the buffer next to the end of the last image of the batch
+                    tail[j] = (b0 + bb >= batch - 1) & (yi == erp_h - 2) & (xi >= erp_w - 6);
+                }
+            }
+            RawPair raw0[G], raw1[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                raw0[j].w0 = raw0[j].w1 = raw0[j].w2 = raw1[j].w0 = raw1[j].w1 = raw1[j].w2 = 0u;
+                if (off[j] != kNoSample && !tail[j]) {
+                    const uint8_t* r0 = tar_chunk + off[j];
+                    const uint8_t* r1 = r0 + row_bytes;
+                    raw0[j] = load_raw_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3));
+                    raw1[j] = load_raw_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+                uint32_t base = 0x00ffffffu;                 // outside: 255 outright
+                if (off[j] != kNoSample) {
+                    const uint8_t* r0 = tar_chunk + off[j];
+                    const uint8_t* r1 = r0 + row_bytes;
+                    uint32_t lo0, hi0, lo1, hi1;
+                    if (tail[j]) {
+                        load_tap_pair_bytes(r0, lo0, hi0);
+                        load_tap_pair_bytes(r1, lo1, hi1);
+                    } else {
+                        align_pair(raw0[j], (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
+                        align_pair(raw1[j], (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
+                    }
+                    // sample - tap(y0, x0) = w01 (p01 - p00) + w10 (p10 - p00) + w11 (p11 - p00): byte differences are
+                    // exact (2^23 + a) - (2^23 + b), the products see small numbers
+                    const float w01 = (1.0f - fy[j]) * fx[j], w10 = fy[j] * (1.0f - fx[j]), w11 = fy[j] * fx[j];
+                    const float a0 = byte_m(lo0, 0), a1 = byte_m(lo0, 1), a2 = byte_m(lo0, 2);
+                    t0 = fmaf(w11, byte_m(lo1, 3) - a0, fmaf(w10, byte_m(lo1, 0) - a0, w01 * (byte_m(lo0, 3) - a0)));
+                    t1 = fmaf(w11, byte_m(hi1, 0) - a1, fmaf(w10, byte_m(lo1, 1) - a1, w01 * (byte_m(hi0, 0) - a1)));
+                    t2 = fmaf(w11, byte_m(hi1, 1) - a2, fmaf(w10, byte_m(lo1, 2) - a2, w01 * (byte_m(hi0, 1) - a2)));
+                    base = lo0 & 0x00ffffffu;
+                }
+                sh_lift[(g0 + j) * TIF_NW_BLOCK + tid] = make_float4(t0, t1, t2, __int_as_float(xcode[j]));
+                sh_base[(g0 + j) * TIF_NW_BLOCK + tid] = base;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: the samples of this block's tangent pixels, one per thread and step ------------------------
+    // Software pipeline, two steps deep: the list entry of step i + 2 and the source pixels of step i + 1 are in
+    // flight while step i is evaluated (the chain entry -> source pixel is two dependent global loads, and a block
+    // has only about three steps to hide them in).
+    const uint8_t* __restrict__ src_chunk = erp_src + (size_t)b0 * image_bytes;
+    const uint32_t last_word = (uint32_t)(((size_t)n_img * image_bytes - 1) >> 2);      // last readable word of the chunk
+    float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.y * max_k * ((size_t)erp_h * erp_w);
+    const int n_pix = erp_h * erp_w;
+    auto load_entry = [&](uint32_t i) { return i < s_end ? __ldg(smp + i) : make_uint2(0u, 0u); };
+    struct SrcWords {
+        uint32_t w[2 * TIF_NW_IMGS];
+    };
+    // source pixel of a sample in the 4 images: 3 bytes at an arbitrary phase, fetched as two aligned words each
+    auto load_src = [&](const uint2& sm, SrcWords& sw) {
+        const uint32_t a = ((sm.x >> 16) * (uint32_t)erp_w + (sm.x & 0xffffu)) * 3u;
+#pragma unroll
+        for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
+            const uint32_t ab = img_off[bb] + a;
+            if (SRC_ALIGNED) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(src_chunk);
+                const uint32_t wi = ab >> 2;
+                sw.w[2 * bb] = __ldg(q + wi);
+                sw.w[2 * bb + 1] = __ldg(q + min(wi + 1u, last_word));
+            } else {
+                const uint8_t* q = src_chunk + ab;
+                sw.w[2 * bb] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+                sw.w[2 * bb + 1] = 0u;
+            }
+        }
+    };
+    int cur_f = -1, pending = 0;
+    unsigned acc[TIF_NW_IMGS];
+#pragma unroll
+    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] = 0u;
+    auto flush = [&]() {
+        if (cur_f >= 0) {
+#pragma unroll
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
+                const unsigned total = __reduce_add_sync(0xffffffffu, acc[bb]);
+                if (lane == 0 && total) atomicAdd(&sh_sum[bb * n_faces + cur_f], (unsigned long long)total);
+                acc[bb] = 0u;
+            }
+        }
+        pending = 0;
+    };
+    uint2 sm_next = load_entry(i_first + TIF_NW_BLOCK);
+    SrcWords sw_cur;
+    load_src(sm_first, sw_cur);
+    uint2 sm = sm_first;
+    // warp-uniform trip count: the loop runs while the warp's first lane still has a sample
+    for (uint32_t i = i_first; i - lane < s_end; i += TIF_NW_BLOCK) {
+        const bool has = i < s_end;
+        const uint2 sm_next2 = load_entry(i + 2 * TIF_NW_BLOCK);
+        SrcWords sw_next;
+        load_src(sm_next, sw_next);
+        const int c = (int)(sm.x & 0xffffu);
+        const int pix = (int)(sm.x >> 16) * erp_w + c;
+        const int f = (int)(sm.y >> 24), k = (int)((sm.y >> 16) & 0xffu);
+        const float mult = (float)((sm.y >> 8) & 7u);
+        const unsigned local = sm.y & (TIF_NW_BLOCK - 1);
+        float d[TIF_NW_IMGS];
+        unsigned fixed[TIF_NW_IMGS];
+#pragma unroll
+        for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
+            const uint32_t spx = SRC_ALIGNED ? __funnelshift_r(sw_cur.w[2 * bb], sw_cur.w[2 * bb + 1], ((img_off[bb] + (uint32_t)pix * 3u) & 3u) * 8u)
+                                             : sw_cur.w[2 * bb];
+            const float4 L = sh_lift[bb * TIF_NW_BLOCK + local];
+            const uint32_t tb = sh_base[bb * TIF_NW_BLOCK + local];
+            const float s0 = byte_m(spx, 0), s1 = byte_m(spx, 1), s2 = byte_m(spx, 2);        // 2^23 + source pixel
+            d[bb] = fabsf(L.x + (byte_m(tb, 0) - s0)) + fabsf(L.y + (byte_m(tb, 1) - s1)) + fabsf(L.z + (byte_m(tb, 2) - s2));
+            // the reference samples at c + fu after its seam fix (:350-361): the end point taken the short way round
+            // from this column; outside [0, W-1] reads 255.  2 (x_end - c) in [-W, W] <=> short way without a fold
+            // (wrap_around=False leaves theta_t wrapped into [-pi, pi): always inside).  Rare: seam columns only.
+            const int t = __float_as_int(L.w) - 2 * c;
+            if (wrap_around && (unsigned)(t + erp_w) > 2u * (unsigned)erp_w)
+                d[bb] = (8388608.0f + 255.0f - s0) + (8388608.0f + 255.0f - s1) + (8388608.0f + 255.0f - s2);
+            // face-global sum of |diff| (x multiplicity) as order-independent fixed point: round to nearest through
+            // the 2^23 mantissa trick (765 x 7 x 1024 < 2^23)
+            fixed[bb] = __float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f)) - 0x4B000000u;
+        }
+        if (has) dplane_chunk[(size_t)k * n_pix + pix] = make_float4(d[0], d[1], d[2], d[3]);
+        // lanes hold consecutive samples of a list sorted by tangent pixel, hence by face: the warp almost always
+        // sees one face and keeps per-thread partial sums; a warp straddling two faces uses shared atomics directly
+        const int f0 = __shfl_sync(0xffffffffu, f, 0);          // lane 0 is valid: the valid lanes are a prefix
+        if (__all_sync(0xffffffffu, !has || f == f0)) {
+            if (f0 != cur_f || pending >= TIF_NW_FLUSH) {
+                flush();
+                cur_f = f0;
+            }
+#pragma unroll
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] += has ? fixed[bb] : 0u;
+            ++pending;
+        } else if (has) {
+#pragma unroll
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) atomicAdd(&sh_sum[bb * n_faces + f], (unsigned long long)fixed[bb]);
+        }
+        sm = sm_next;
+        sm_next = sm_next2;
+        sw_cur = sw_next;
+    }
+    flush();
+    __syncthreads();
+    for (int i = tid; i < TIF_NW_IMGS * n_faces; i += TIF_NW_BLOCK) {
+        const int bb = i / n_faces, f = i - bb * n_faces;
+        if (bb < n_img && sh_sum[i]) atomicAdd(&nw_sums[(size_t)(b0 + bb) * n_faces + f], sh_sum[i]);
+    }
+}
+
+__global__ void __launch_bounds__(TIF_NW_BLEND_THREADS, TIF_NW_BLEND_MIN_BLOCKS)
+k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
+           const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
+           const float2* __restrict__ disp_rec, const float4* __restrict__ dplane, const float* __restrict__ nw_scale,
+           float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int max_k, int batch,
+           int wrap_around) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sh_scale = reinterpret_cast<float4*>(smem_raw);                   // [F] -log2(e) / (3 mean_f) of the 4 images
+    int* sh_offset = reinterpret_cast<int*>(sh_scale + n_faces);              // [F] first pixel of each face
+    const int b0 = blockIdx.y * TIF_NW_IMGS;
+    for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
+        sh_offset[f] = faces[f].pix_offset;
+        float sc[TIF_NW_IMGS];
+#pragma unroll
+        for (int bb = 0; bb < TIF_NW_IMGS; ++bb) sc[bb] = (b0 + bb < batch) ? nw_scale[(size_t)(b0 + bb) * n_faces + f] : 0.0f;
+        sh_scale[f] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    }
+    __syncthreads();
+    const int n_pix = erp_h * erp_w;
+    int r, c;
+    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, erp_h, r, c)) return;
+    const int pix = r * erp_w + c;
+    const int cnt = (int)s2_count[pix];
+    const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
+    const float4* __restrict__ disp_chunk = reinterpret_cast<const float4*>(disp_rec + (size_t)blockIdx.y * n_tangent * TIF_NW_IMGS);
+    const float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.y * max_k * (size_t)n_pix + pix;
+    float acc_u[TIF_NW_IMGS], acc_v[TIF_NW_IMGS], acc_w[TIF_NW_IMGS];
+#pragma unroll
+    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+    uint32_t e_next = 0u;
+    float2 sn_next = make_float2(0.0f, 0.0f);
+    float4 d_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (cnt > 0) {
+        e_next = __ldg(s2_entries + pix);
+        sn_next = __ldg(s2_snap + pix);
+        d_next = __ldg(dplane_chunk);
+    }
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t e = e_next;
+        const float2 sn = sn_next;
+        const float4 dd = d_next;
+        if (k + 1 < cnt) {                           // next entry in flight while this one is blended
+            e_next = __ldg(s2_entries + (size_t)(k + 1) * n_pix + pix);
+            sn_next = __ldg(s2_snap + (size_t)(k + 1) * n_pix + pix);
+            d_next = __ldg(dplane_chunk + (size_t)(k + 1) * n_pix);
+        }
+        const int f = (int)TIF_E_FACE(e);
+        const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
+        const float4 q01 = __ldg(disp_chunk + 2u * tpix), q23 = __ldg(disp_chunk + 2u * tpix + 1u);
+        const float4 sc = sh_scale[f];
+        const float du[TIF_NW_IMGS] = {q01.x, q01.z, q23.x, q23.z}, dv[TIF_NW_IMGS] = {q01.y, q01.w, q23.y, q23.w};
+        const float de[TIF_NW_IMGS] = {dd.x, dd.y, dd.z, dd.w}, ds[TIF_NW_IMGS] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+        for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
+            float fu = du[bb] + sn.x;        // end point minus this ERP pixel, the short way round
+            const float fv = dv[bb] + sn.y;
+            if (fu > half_w) fu -= wf;
+            else if (fu < -half_w) fu += wf;
+            // wrap_around=False: the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
+            if (!wrap_around) fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
+            const float w = exp2_approx(de[bb] * ds[bb]);         // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
+            acc_u[bb] = fmaf(fu, w, acc_u[bb]);
+            acc_v[bb] = fmaf(fv, w, acc_v[bb]);
+            acc_w[bb] += w;
+        }
+    }
+    const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
+#pragma unroll
+    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
+        const int b = b0 + bb;
+        if (b >= batch) break;
+        float u = acc_u[bb], v = acc_v[bb];
+        if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393
+            const float inv = 1.0f / acc_w[bb];
+            u *= inv;
+            v *= inv;
+        }
+        if (wrap_around) {            // flow_postproc.erp_of_wraparound, flow_postproc.py:28-42
+            if (c < split) {
+                if (u > half_w) u -= wf;
+            } else if (c < erp_w - 1) {
+                if (u < -half_w) u += wf;
+            }
+        }
+        reinterpret_cast<float2*>(out)[(size_t)b * n_pix + pix] = make_float2(u, v);
+    }
+}
+
 // scratch = [B][F] uint64 face sums (padded to 256 bytes) + one record per tangent pixel and image:
 // float2 displacement (straightforward) or uint4 displacement + packed target sample (normwarp)
 static size_t nw_sums_bytes(const TifPlan* plan, int batch) {
@@ -1055,9 +1408,23 @@ __global__ void k_nw_face_scale(const unsigned long long* __restrict__ nw_sums, 
     scale[i] = (float)(-1.4426950408889634 / (3.0 * mean));         // exp(-x / (3 mean)) = 2^(x scale)
 }
 
+// normwarp scratch after the header: displacement of every tangent pixel (float2 x 4 images per chunk) + the dense
+// warp-error planes [chunk][k][H*W] (float4 = the 4 images of the chunk)
+static size_t nw_disp_bytes(const TifPlan* plan, int batch) {
+    const size_t chunks = (size_t)(batch + TIF_NW_IMGS - 1) / TIF_NW_IMGS;
+    return chunks * (size_t)plan->tangent_pixels * TIF_NW_IMGS * sizeof(float2);
+}
+
+static size_t nw_plane_bytes(const TifPlan* plan, int batch) {
+    const size_t chunks = (size_t)(batch + TIF_NW_IMGS - 1) / TIF_NW_IMGS;
+    return chunks * (size_t)plan->max_faces_per_pixel * (size_t)plan->erp_h * plan->erp_w * sizeof(float4);
+}
+
 extern "C" int64_t tif_ico2erp_scratch_bytes(const TifPlan* plan, int batch, int blend) {
     if (!plan || batch <= 0) return 0;
-    const size_t rec = (blend == TIF_BLEND_NORMWARP || blend == TIF_BLEND_CUBEMAP_WARP_ERROR) ? sizeof(uint4) : sizeof(float2);
+    if (blend == TIF_BLEND_NORMWARP)
+        return (int64_t)(nw_header_bytes(plan, batch) + nw_disp_bytes(plan, batch) + nw_plane_bytes(plan, batch));
+    const size_t rec = (blend == TIF_BLEND_CUBEMAP_WARP_ERROR) ? sizeof(uint4) : sizeof(float2);
     const size_t padded = (size_t)(batch + TIF_BATCH_CHUNK - 1) / TIF_BATCH_CHUNK * TIF_BATCH_CHUNK;      // whole chunks
     return (int64_t)(nw_header_bytes(plan, batch) + padded * (size_t)plan->tangent_pixels * rec);
 }
@@ -1098,12 +1465,13 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
     plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries, plan->d_s2_snap, plan->d_face_mult_sum, records,   \
         erp_src, nw_sums, nw_scale, erp_flow, h, w, plan->tangent_w, n_tangent, batch, wrap_around
     const float lift_u_scale = (float)((double)w / TIF_TWO_PI), lift_v_scale = (float)((double)h / TIF_PI);
+    const PolarBand polar = polar_band(w);
     const bool skip_lift = (pass_mask & 4) != 0;       // profiling: reuse the records of an earlier call
     if (blend == TIF_BLEND_STRAIGHTFORWARD || blend == TIF_BLEND_CUBEMAP_INSIDE) {
         if (!skip_lift)
             k_lift<0><<<lift_grid, TIF_LIFT_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                                  n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, nullptr,
-                                                                 records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
+                                                                 records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale, polar);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) {
             if (blend == TIF_BLEND_STRAIGHTFORWARD)
@@ -1115,26 +1483,44 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if (!skip_lift)
             k_lift<2><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face, plan->d_ref_list,
                                                              n_ref, plan->d_s1_ex, plan->d_s1_ey, tangent_flow, erp_tar,
-                                                             records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale);
+                                                             records, h, w, plan->tangent_w, n_tangent, batch, lift_u_scale, lift_v_scale, polar);
         TIF_CUDA_CHECK(cudaGetLastError());
         if (pass_mask & 3) k_gather<4><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
     } else {
-        if (pass_mask & (1 | 8)) {
-            if (pass_mask & 1) TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
-            if (!skip_lift)
-                k_lift<1><<<lift_nw_grid, TIF_LIFT_NW_THREADS, lift_smem, stream>>>(plan->d_lift_faces, n_faces, plan->d_pix_face,
-                                                                    plan->d_ref_list, n_ref, plan->d_s1_ex, plan->d_s1_ey,
-                                                                    tangent_flow, erp_tar, records, h, w, plan->tangent_w,
-                                                                    n_tangent, batch, lift_u_scale, lift_v_scale);
-            TIF_CUDA_CHECK(cudaGetLastError());
-            if (pass_mask & 1) k_gather<1><<<gather1_grid, TIF_GATHER1_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+        if (plan->kind != TIF_PLAN_ICOSAHEDRON || !plan->d_smp) {
+            tif_set_error("tif_ico2erp_flow_f32: the normwarp blend needs an icosahedron plan");
+            return TIF_ERR_INVALID_ARG;
+        }
+        const unsigned chunks = (unsigned)((batch + TIF_NW_IMGS - 1) / TIF_NW_IMGS);
+        float2* disp_rec = (float2*)records;
+        float4* dplane = (float4*)((unsigned char*)records + nw_disp_bytes(plan, batch));
+        if ((pass_mask & (1 | 8)) && !skip_lift) {
+            TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
+            const dim3 grid((unsigned)((n_ref + TIF_NW_BLOCK - 1) / TIF_NW_BLOCK), chunks);
+            const size_t smem = (sizeof(float4) + sizeof(uint32_t)) * TIF_NW_IMGS * TIF_NW_BLOCK + sizeof(LiftFace) * n_faces +
+                                sizeof(unsigned long long) * TIF_NW_IMGS * n_faces;
+#define LIFT_NW_ARGS                                                                                                    \
+    plan->d_lift_faces, n_faces, plan->d_ref_list, n_ref, plan->d_ref_pos, plan->d_s1_ex, plan->d_s1_ey, plan->d_smp,   \
+        plan->d_blk_smp, tangent_flow, erp_src, erp_tar, disp_rec, dplane, nw_sums, h, w, plan->tangent_w, n_tangent,  \
+        plan->max_faces_per_pixel, batch, wrap_around, lift_u_scale, lift_v_scale, polar
+            // every image of the batch starts on a word boundary when the buffer does and H * W * 3 is a multiple of 4
+            if (reinterpret_cast<uintptr_t>(erp_src) % 4 == 0 && ((size_t)h * w * 3) % 4 == 0)
+                k_lift_nw<true><<<grid, TIF_NW_BLOCK, smem, stream>>>(LIFT_NW_ARGS);
+            else
+                k_lift_nw<false><<<grid, TIF_NW_BLOCK, smem, stream>>>(LIFT_NW_ARGS);
+#undef LIFT_NW_ARGS
             TIF_CUDA_CHECK(cudaGetLastError());
         }
         if (pass_mask & 2) {
             k_nw_face_scale<<<(unsigned)((batch * n_faces + 127) / 128), 128, 0, stream>>>(nw_sums, plan->d_face_mult_sum, n_faces,
                                                                                           batch, nw_scale);
             TIF_CUDA_CHECK(cudaGetLastError());
-            k_gather<2><<<gather2_grid, TIF_GATHER2_THREADS, gather_smem, stream>>>(GATHER_ARGS);
+            const dim3 grid((unsigned)((tile_threads(w, h) + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), chunks);
+            const size_t smem = (sizeof(float4) + sizeof(int)) * n_faces;
+            k_blend_nw<<<grid, TIF_NW_BLEND_THREADS, smem, stream>>>(plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries,
+                                                                    plan->d_s2_snap, disp_rec, dplane, nw_scale, erp_flow, h, w,
+                                                                    plan->tangent_w, n_tangent, plan->max_faces_per_pixel, batch,
+                                                                    wrap_around);
         }
     }
 #undef GATHER_ARGS
@@ -1147,168 +1533,4 @@ extern "C" int tif_ico2erp_flow_f32(const TifPlan* plan, const float* tangent_fl
                                     void* scratch, void* stream) {
     return tif_ico2erp_flow_f32_ex(plan, tangent_flow, erp_src, erp_tar, batch, blend, wrap_around, erp_flow, scratch, 3,
                                    stream);
-}
-
-// ------------------------------------------------------------------------------------------------
-// flow_warp.warp_backward
-// ------------------------------------------------------------------------------------------------
-template <typename ImgT, typename FlowT, int MODE>
-__global__ void __launch_bounds__(256)
-k_warp_backward(const ImgT* __restrict__ image, const FlowT* __restrict__ flow, ImgT* __restrict__ out, int batch,
-                int h, int w, int channels) {
-    const int64_t n_pix = (int64_t)h * w;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (pix >= n_pix) return;
-    const int r = (int)(pix / w), c = (int)(pix - (int64_t)r * w);
-    const size_t gi = (size_t)b * n_pix + pix;
-    // flow_warp.py:75-76: mesh grid + flow, in float64
-    double x = (double)c + (double)flow[2 * gi];
-    double y = (double)r + (double)flow[2 * gi + 1];
-    ImgT* o = out + gi * channels;
-    if (MODE == TIF_WARP_CONSTANT255) {
-        if (x < 0.0 || x > (double)(w - 1) || y < 0.0 || y > (double)(h - 1)) {
-            for (int ch = 0; ch < channels; ++ch) o[ch] = (ImgT)255;
-            return;
-        }
-    } else {
-        x = scipy_wrap(x, w);
-        y = scipy_wrap(y, h);
-    }
-    double x0 = floor(x), y0 = floor(y);
-    if (x0 > (double)(w - 2)) x0 = (double)(w - 2);
-    if (y0 > (double)(h - 2)) y0 = (double)(h - 2);
-    if (x0 < 0.0) x0 = 0.0;
-    if (y0 < 0.0) y0 = 0.0;
-    const double fx = x - x0, fy = y - y0;
-    const ImgT* r0 = image + ((size_t)b * n_pix + (size_t)y0 * w + (size_t)x0) * channels;
-    const ImgT* r1 = r0 + (size_t)w * channels;
-    if (sizeof(ImgT) == 1) {
-        const float fxf = (float)fx, fyf = (float)fy;
-        const float wx0 = 1.0f - fxf, wy0 = 1.0f - fyf;
-        for (int ch = 0; ch < channels; ++ch) {
-            const float p00 = (float)__ldg(r0 + ch), p01 = (float)__ldg(r0 + channels + ch);
-            const float p10 = (float)__ldg(r1 + ch), p11 = (float)__ldg(r1 + channels + ch);
-            const float t = bilinear_f32(p00, p01, p10, p11, wx0, fxf, wy0, fyf);
-            o[ch] = (ImgT)round_u8_guarded(t, p00, p01, p10, p11, fx, fy);
-        }
-    } else {
-        for (int ch = 0; ch < channels; ++ch) {
-            const double t = bilinear_f64_exact((double)__ldg(r0 + ch), (double)__ldg(r0 + channels + ch),
-                                                (double)__ldg(r1 + ch), (double)__ldg(r1 + channels + ch), fx, fy);
-            o[ch] = (ImgT)t;
-        }
-    }
-}
-
-template <typename ImgT>
-static int launch_warp(const ImgT* image, const void* flow, int flow_dtype, int batch, int h, int w, int channels,
-                       int mode, ImgT* out, void* stream_v) {
-    if (!image || !flow || !out || batch <= 0 || h < 2 || w < 2 || channels <= 0) {
-        tif_set_error("tif_warp_backward: invalid argument");
-        return TIF_ERR_INVALID_ARG;
-    }
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    const int threads = 256;
-    dim3 grid((unsigned)(((int64_t)h * w + threads - 1) / threads), (unsigned)batch);
-    if (flow_dtype == TIF_DTYPE_F32 && mode == TIF_WARP_WRAP)
-        k_warp_backward<ImgT, float, TIF_WARP_WRAP><<<grid, threads, 0, stream>>>(image, (const float*)flow, out, batch, h, w, channels);
-    else if (flow_dtype == TIF_DTYPE_F32 && mode == TIF_WARP_CONSTANT255)
-        k_warp_backward<ImgT, float, TIF_WARP_CONSTANT255><<<grid, threads, 0, stream>>>(image, (const float*)flow, out, batch, h, w, channels);
-    else if (flow_dtype == TIF_DTYPE_F64 && mode == TIF_WARP_WRAP)
-        k_warp_backward<ImgT, double, TIF_WARP_WRAP><<<grid, threads, 0, stream>>>(image, (const double*)flow, out, batch, h, w, channels);
-    else if (flow_dtype == TIF_DTYPE_F64 && mode == TIF_WARP_CONSTANT255)
-        k_warp_backward<ImgT, double, TIF_WARP_CONSTANT255><<<grid, threads, 0, stream>>>(image, (const double*)flow, out, batch, h, w, channels);
-    else {
-        tif_set_error("tif_warp_backward: unknown flow dtype %d / mode %d", flow_dtype, mode);
-        return TIF_ERR_INVALID_ARG;
-    }
-    TIF_CUDA_CHECK(cudaGetLastError());
-    return TIF_OK;
-}
-
-extern "C" int tif_warp_backward_u8(const uint8_t* image, const void* flow, int flow_dtype, int batch, int h, int w,
-                                    int channels, int mode, uint8_t* out, void* stream) {
-    return launch_warp<uint8_t>(image, flow, flow_dtype, batch, h, w, channels, mode, out, stream);
-}
-
-extern "C" int tif_warp_backward_f32(const float* image, const void* flow, int flow_dtype, int batch, int h, int w,
-                                     int channels, int mode, float* out, void* stream) {
-    return launch_warp<float>(image, flow, flow_dtype, batch, h, w, channels, mode, out, stream);
-}
-
-// ------------------------------------------------------------------------------------------------
-// flow_warp.flow_warp_meshgrid / flow_postproc.erp_of_wraparound
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_meshgrid(const T* __restrict__ fu, const T* __restrict__ fv, T* __restrict__ out, int batch, int h, int w) {
-    const int64_t n_pix = (int64_t)h * w;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (pix >= n_pix) return;
-    const int r = (int)(pix / w), c = (int)(pix - (int64_t)r * w);
-    double eu = (double)c + (double)fu[(size_t)b * n_pix + pix];
-    double ev = (double)r + (double)fv[(size_t)b * n_pix + pix];
-    // flow_warp.py:41-49: one wrap each way, not a modulo
-    if (eu >= (double)w - 0.5) eu -= (double)w;
-    if (eu < -0.5) eu += (double)w;
-    if (ev >= (double)h - 0.5) ev -= (double)h;
-    if (ev < -0.5) ev += (double)h;
-    out[((size_t)b * 2 + 0) * n_pix + pix] = (T)eu;
-    out[((size_t)b * 2 + 1) * n_pix + pix] = (T)ev;
-}
-
-extern "C" int tif_flow_warp_meshgrid(const void* flow_u, const void* flow_v, int dtype, int batch, int h, int w,
-                                      void* out, void* stream_v) {
-    if (!flow_u || !flow_v || !out || batch <= 0 || h <= 0 || w <= 0) {
-        tif_set_error("tif_flow_warp_meshgrid: invalid argument");
-        return TIF_ERR_INVALID_ARG;
-    }
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    dim3 grid((unsigned)(((int64_t)h * w + 255) / 256), (unsigned)batch);
-    if (dtype == TIF_DTYPE_F32)
-        k_meshgrid<float><<<grid, 256, 0, stream>>>((const float*)flow_u, (const float*)flow_v, (float*)out, batch, h, w);
-    else if (dtype == TIF_DTYPE_F64)
-        k_meshgrid<double><<<grid, 256, 0, stream>>>((const double*)flow_u, (const double*)flow_v, (double*)out, batch, h, w);
-    else
-        return TIF_ERR_INVALID_ARG;
-    TIF_CUDA_CHECK(cudaGetLastError());
-    return TIF_OK;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_wraparound(T* __restrict__ flow, int batch, int h, int w, double thr) {
-    const int64_t n_pix = (int64_t)h * w;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (pix >= n_pix) return;
-    const int c = (int)(pix % w);
-    const int split = (int)((double)w - 1.0 - thr);
-    T* p = flow + ((size_t)b * n_pix + pix) * 2;
-    const double u = (double)p[0];
-    if (c < split) {
-        if (u > thr) p[0] = (T)(u - (double)w);
-    } else if (c < w - 1) {
-        if (u < -thr) p[0] = (T)(u + (double)w);
-    }
-}
-
-extern "C" int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold,
-                                     void* stream_v) {
-    if (!erp_flow || batch <= 0 || h <= 0 || w <= 0) {
-        tif_set_error("tif_erp_of_wraparound: invalid argument");
-        return TIF_ERR_INVALID_ARG;
-    }
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    dim3 grid((unsigned)(((int64_t)h * w + 255) / 256), (unsigned)batch);
-    if (dtype == TIF_DTYPE_F32)
-        k_wraparound<float><<<grid, 256, 0, stream>>>((float*)erp_flow, batch, h, w, u_threshold);
-    else if (dtype == TIF_DTYPE_F64)
-        k_wraparound<double><<<grid, 256, 0, stream>>>((double*)erp_flow, batch, h, w, u_threshold);
-    else
-        return TIF_ERR_INVALID_ARG;
-    TIF_CUDA_CHECK(cudaGetLastError());
-    return TIF_OK;
 }

@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "tif_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -239,6 +241,51 @@ __global__ void k_count_marks(const uint8_t* __restrict__ mark, int64_t n, unsig
 }
 
 // ------------------------------------------------------------------------------------------------
+// normwarp sample list: the accepted (ERP pixel, face) samples regrouped by the tangent pixel they snap to, in the
+// order of the lift kernel's work list.  k_lift_nw lifts TIF_NW_BLOCK tangent pixels per block and then walks the
+// samples of exactly those pixels (projection.py:52-58 needs |tar(end point) - src(ERP pixel)| per sample).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sample_ref_index(uint32_t e, const TifFace* __restrict__ faces, int tangent_w,
+                                                const int32_t* __restrict__ ref_index) {
+    const int64_t tpix = (int64_t)faces[TIF_E_FACE(e)].pix_offset + (int64_t)TIF_E_IY(e) * tangent_w + TIF_E_IX(e);
+    return ref_index[tpix];
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_plan_samples(const uint8_t* __restrict__ count, const uint32_t* __restrict__ entries, const TifFace* __restrict__ faces,
+               const int32_t* __restrict__ ref_index, int erp_h, int erp_w, int tangent_w, uint32_t* __restrict__ per_ref,
+               const uint32_t* __restrict__ start, uint2* __restrict__ smp) {
+    const int64_t n_pix = (int64_t)erp_h * erp_w;
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= n_pix) return;
+    const int r = (int)(pix / erp_w), c = (int)(pix - (int64_t)r * erp_w);
+    const int n = count[pix];
+    for (int k = 0; k < n; ++k) {
+        const uint32_t e = entries[(int64_t)k * n_pix + pix];
+        const int ref = sample_ref_index(e, faces, tangent_w, ref_index);
+        const uint32_t slot = atomicAdd(&per_ref[ref], 1u);
+        if (FILL)
+            smp[start[ref] + slot] = make_uint2(((uint32_t)r << 16) | (uint32_t)c,
+                                                (TIF_E_FACE(e) << 24) | ((uint32_t)k << 16) | (TIF_E_MULT(e) << 8) | ((uint32_t)ref % TIF_NW_BLOCK));
+    }
+}
+
+// own ERP position of every work-list entry, split into integer and fraction (the lift adds the displacement to it
+// when it samples the target image; float64 only here, once per plan)
+__global__ void __launch_bounds__(256)
+k_plan_ref_pos(const int32_t* __restrict__ ref_list, int n_ref, const LiftFace* __restrict__ lift_faces, int tangent_w,
+               const double* __restrict__ s1_ex, const double* __restrict__ s1_ey, int4* __restrict__ ref_pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const uint32_t ref = (uint32_t)ref_list[i];
+    const int64_t p = (int64_t)(lift_faces[TIF_E_FACE(ref)].first_row + (int)TIF_E_IY(ref)) * tangent_w + (int)TIF_E_IX(ref);
+    const double ex = s1_ex[p], ey = s1_ey[p];
+    const double fx = floor(ex), fy = floor(ey);
+    ref_pos[i] = make_int4((int)fx, (int)fy, __float_as_int((float)(ex - fx)), __float_as_int((float)(ey - fy)));
+}
+
+// ------------------------------------------------------------------------------------------------
 // plan lifetime
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -269,22 +316,39 @@ extern "C" int tif_plan_destroy(TifPlan* plan) {
     cudaFree(plan->d_ref_mark);
     cudaFree(plan->d_ref_list);
     cudaFree(plan->d_face_mult_sum);
+    cudaFree(plan->d_ref_pos);
+    cudaFree(plan->d_smp);
+    cudaFree(plan->d_blk_smp);
     free(plan->h_faces);
     free(plan);
     return TIF_OK;
 }
+
+// device scratch of tif_plan_create, released on every exit path
+struct PlanScratch {
+    double *gx = nullptr, *gy = nullptr, *rows = nullptr, *cols = nullptr;
+    int* status = nullptr;
+    unsigned long long* msum = nullptr;
+    int32_t* ref_index = nullptr;
+    uint32_t *per_ref = nullptr, *smp_start = nullptr;
+    ~PlanScratch() {
+        cudaFree(gx);
+        cudaFree(gy);
+        cudaFree(rows);
+        cudaFree(cols);
+        cudaFree(status);
+        cudaFree(msum);
+        cudaFree(ref_index);
+        cudaFree(per_ref);
+        cudaFree(smp_start);
+    }
+};
 
 #define PLAN_TRY(expr)              \
     do {                            \
         int _s = (expr);            \
         if (_s != TIF_OK) {         \
             tif_plan_destroy(plan); \
-            cudaFree(d_gx);         \
-            cudaFree(d_gy);         \
-            cudaFree(d_rows);       \
-            cudaFree(d_cols);       \
-            cudaFree(d_status);     \
-            cudaFree(d_msum);       \
             return _s;              \
         }                           \
     } while (0)
@@ -293,6 +357,11 @@ static int cuda_status(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return TIF_OK;
     tif_set_error("%s failed: %s", what, cudaGetErrorString(e));
     return TIF_ERR_CUDA;
+}
+
+template <typename T>
+static int scratch_alloc(T** p, size_t n) {
+    return cuda_status(cudaMalloc((void**)p, n * sizeof(T)), "cudaMalloc (plan scratch)");
 }
 
 extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int erp_w, int tangent_w,
@@ -313,8 +382,11 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
             return TIF_ERR_INVALID_ARG;
         }
     }
-    if ((int64_t)erp_h * erp_w >= (int64_t)1 << 31) {
-        tif_set_error("tif_plan_create: ERP larger than 2^31 pixels");
+    // the execute kernels address the images of a batch chunk (TIF_MAX_CHUNK_IMAGES images of H*W*3 bytes) with 32-bit
+    // byte offsets, and the sample list packs an ERP row / column into 16 bits each
+    if ((int64_t)erp_h * erp_w * 3 * TIF_MAX_CHUNK_IMAGES >= (int64_t)1 << 32 || erp_h > 65535 || erp_w > 65535) {
+        tif_set_error("tif_plan_create: ERP of %d x %d is beyond the supported size (%d * H * W * 3 bytes must stay below 2^32)",
+                      erp_w, erp_h, TIF_MAX_CHUNK_IMAGES);
         return TIF_ERR_UNSUPPORTED;
     }
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -328,8 +400,8 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         }
         n_tangent += (int64_t)faces[f].tangent_h * tangent_w;
     }
-    if (n_tangent >= (int64_t)1 << 31) {
-        tif_set_error("tif_plan_create: tangent stack larger than 2^31 pixels");
+    if (n_tangent >= (int64_t)1 << 29) {           // 32-bit byte offsets into a chunk of float2 flows
+        tif_set_error("tif_plan_create: tangent stack larger than 2^29 pixels");
         return TIF_ERR_UNSUPPORTED;
     }
     const int64_t n_rows = n_tangent / tangent_w;
@@ -344,17 +416,20 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     plan->tangent_pixels = n_tangent;
     plan->kind = kind;
     plan->h_faces = (TifFace*)malloc(sizeof(TifFace) * n_faces);
+    if (!plan->h_faces) {
+        free(plan);
+        return TIF_ERR_ALLOC;
+    }
     memcpy(plan->h_faces, faces, sizeof(TifFace) * n_faces);
 
-    double *d_gx = nullptr, *d_gy = nullptr, *d_rows = nullptr, *d_cols = nullptr;
-    int* d_status = nullptr;
-    unsigned long long* d_msum = nullptr;
-
-    int32_t* h_row_face = (int32_t*)malloc(sizeof(int32_t) * n_rows);
+    PlanScratch sc;          // freed by its destructor on every return below
+    std::vector<int32_t> h_row_face((size_t)n_rows), h_first_row((size_t)n_faces);
     {
         int64_t row = 0;
-        for (int f = 0; f < n_faces; ++f)
+        for (int f = 0; f < n_faces; ++f) {
+            h_first_row[f] = (int32_t)row;
             for (int i = 0; i < faces[f].tangent_h; ++i) h_row_face[row++] = f;
+        }
     }
 
     PLAN_TRY(dev_alloc(&plan->d_faces, n_faces, plan));
@@ -368,62 +443,52 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     PLAN_TRY(dev_alloc(&plan->d_face_mult_sum, n_faces, plan));
     PLAN_TRY(dev_alloc(&plan->d_ref_mark, n_tangent, plan));
     uint8_t* d_mark = plan->d_ref_mark;
-    int64_t scratch_bytes = 0;
-    {
-        TifPlan tmp;   // scratch is not part of the plan footprint
-        tmp.device_bytes = 0;
-        PLAN_TRY(dev_alloc(&d_gx, (size_t)n_faces * tangent_w, &tmp));
-        PLAN_TRY(dev_alloc(&d_gy, n_rows, &tmp));
-        PLAN_TRY(dev_alloc(&d_rows, (size_t)erp_h * 2, &tmp));
-        PLAN_TRY(dev_alloc(&d_cols, (size_t)n_faces * erp_w * 2, &tmp));
-        PLAN_TRY(dev_alloc(&d_status, 2, &tmp));
-        PLAN_TRY(dev_alloc(&d_msum, n_faces + 1, &tmp));
-        scratch_bytes = tmp.device_bytes;
-    }
-    (void)scratch_bytes;
+    PLAN_TRY(scratch_alloc(&sc.gx, (size_t)n_faces * tangent_w));
+    PLAN_TRY(scratch_alloc(&sc.gy, (size_t)n_rows));
+    PLAN_TRY(scratch_alloc(&sc.rows, (size_t)erp_h * 2));
+    PLAN_TRY(scratch_alloc(&sc.cols, (size_t)n_faces * erp_w * 2));
+    PLAN_TRY(scratch_alloc(&sc.status, 2));
+    PLAN_TRY(scratch_alloc(&sc.msum, (size_t)n_faces + 1));
 
     PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_faces, faces, sizeof(TifFace) * n_faces, cudaMemcpyHostToDevice, stream), "copy faces"));
-    LiftFace* h_lift = (LiftFace*)malloc(sizeof(LiftFace) * (size_t)n_faces);
-    for (int f = 0; f < n_faces; ++f) {
-        LiftFace lf;
-        lf.sin_phi0 = faces[f].sin_phi0;
-        lf.cos_phi0 = faces[f].cos_phi0;
-        lf.xmin = faces[f].xmin;
-        lf.ymax = faces[f].ymax;
-        lf.kx = 1.0 / faces[f].p2g_x;
-        lf.ky = 1.0 / faces[f].p2g_y;
-        lf.first_row = faces[f].pix_offset / tangent_w;
-        lf.pad[0] = lf.pad[1] = lf.pad[2] = 0;
-        h_lift[f] = lf;
-    }
     {
-        const cudaError_t el = cudaMemcpy(plan->d_lift_faces, h_lift, sizeof(LiftFace) * n_faces, cudaMemcpyHostToDevice);
-        free(h_lift);
-        PLAN_TRY(cuda_status(el, "copy lift faces"));
+        std::vector<LiftFace> h_lift((size_t)n_faces);
+        for (int f = 0; f < n_faces; ++f) {
+            LiftFace lf;
+            lf.sin_phi0 = faces[f].sin_phi0;
+            lf.cos_phi0 = faces[f].cos_phi0;
+            lf.xmin = faces[f].xmin;
+            lf.ymax = faces[f].ymax;
+            lf.kx = 1.0 / faces[f].p2g_x;
+            lf.ky = 1.0 / faces[f].p2g_y;
+            lf.first_row = faces[f].pix_offset / tangent_w;
+            lf.pad[0] = lf.pad[1] = lf.pad[2] = 0;
+            h_lift[f] = lf;
+        }
+        PLAN_TRY(cuda_status(cudaMemcpy(plan->d_lift_faces, h_lift.data(), sizeof(LiftFace) * n_faces, cudaMemcpyHostToDevice), "copy lift faces"));
     }
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_pix_face, h_row_face, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, stream), "copy row->face"));
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gx, tables->gnom_x, sizeof(double) * n_faces * tangent_w, cudaMemcpyHostToDevice, stream), "copy gnom_x"));
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_gy, tables->gnom_y, sizeof(double) * n_rows, cudaMemcpyHostToDevice, stream), "copy gnom_y"));
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_rows, tables->row_sincos, sizeof(double) * erp_h * 2, cudaMemcpyHostToDevice, stream), "copy row table"));
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(d_cols, tables->col_sincos, sizeof(double) * n_faces * erp_w * 2, cudaMemcpyHostToDevice, stream), "copy column table"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(plan->d_pix_face, h_row_face.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, stream), "copy row->face"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(sc.gx, tables->gnom_x, sizeof(double) * n_faces * tangent_w, cudaMemcpyHostToDevice, stream), "copy gnom_x"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(sc.gy, tables->gnom_y, sizeof(double) * n_rows, cudaMemcpyHostToDevice, stream), "copy gnom_y"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(sc.rows, tables->row_sincos, sizeof(double) * erp_h * 2, cudaMemcpyHostToDevice, stream), "copy row table"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(sc.cols, tables->col_sincos, sizeof(double) * n_faces * erp_w * 2, cudaMemcpyHostToDevice, stream), "copy column table"));
     PLAN_TRY(cuda_status(cudaMemsetAsync(d_mark, 0, n_tangent, stream), "memset"));
-    PLAN_TRY(cuda_status(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), stream), "memset"));
-    PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, (n_faces + 1) * sizeof(unsigned long long), stream), "memset"));
-    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan upload"));   // h_row_face is pageable
-    free(h_row_face);
+    PLAN_TRY(cuda_status(cudaMemsetAsync(sc.status, 0, 2 * sizeof(int), stream), "memset"));
+    PLAN_TRY(cuda_status(cudaMemsetAsync(sc.msum, 0, (n_faces + 1) * sizeof(unsigned long long), stream), "memset"));
+    PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan upload"));   // the host tables are pageable
 
     const int threads = 256;
     k_plan_stage1<<<(unsigned)((n_tangent + threads - 1) / threads), threads, 0, stream>>>(
-        plan->d_faces, plan->d_pix_face, d_gx, d_gy, erp_h, erp_w, tangent_w, n_tangent, kind, plan->d_s1_base,
+        plan->d_faces, plan->d_pix_face, sc.gx, sc.gy, erp_h, erp_w, tangent_w, n_tangent, kind, plan->d_s1_base,
         plan->d_s1_frac64, plan->d_s1_ex, plan->d_s1_ey);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage1 launch"));
 
     const unsigned blocks2 = (unsigned)((n_erp + threads - 1) / threads);
-    k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, d_rows,
-                                                         d_cols, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, d_status);
+    k_plan_stage2<false><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, sc.rows,
+                                                         sc.cols, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, sc.status);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<count> launch"));
     int h_status[2] = {0, 0};
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, stream), "read max count"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(h_status, sc.status, sizeof(h_status), cudaMemcpyDeviceToHost, stream), "read max count"));
     PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan stage 2 count"));
     plan->max_faces_per_pixel = h_status[0] > 0 ? h_status[0] : 1;
     if (plan->max_faces_per_pixel > 255) {
@@ -432,81 +497,108 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
     }
     PLAN_TRY(dev_alloc(&plan->d_s2_entries, (size_t)plan->max_faces_per_pixel * n_erp, plan));
     PLAN_TRY(dev_alloc(&plan->d_s2_snap, (size_t)plan->max_faces_per_pixel * n_erp, plan));
-    k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, d_rows,
-                                                        d_cols, plan->d_s2_count, plan->d_s2_entries,
-                                                        plan->max_faces_per_pixel, d_mark, d_msum, plan->d_s1_ex, plan->d_s1_ey,
-                                                        plan->d_s2_snap, d_status);
+    k_plan_stage2<true><<<blocks2, threads, 0, stream>>>(plan->d_faces, n_faces, erp_h, erp_w, tangent_w, kind, sc.rows,
+                                                        sc.cols, plan->d_s2_count, plan->d_s2_entries,
+                                                        plan->max_faces_per_pixel, d_mark, sc.msum, plan->d_s1_ex, plan->d_s1_ey,
+                                                        plan->d_s2_snap, sc.status);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_stage2<fill> launch"));
-    k_count_marks<<<1024, 256, 0, stream>>>(d_mark, n_tangent, d_msum + n_faces);
+    k_count_marks<<<1024, 256, 0, stream>>>(d_mark, n_tangent, sc.msum + n_faces);
     PLAN_TRY(cuda_status(cudaGetLastError(), "k_count_marks launch"));
-    unsigned long long* h_msum = (unsigned long long*)malloc(sizeof(unsigned long long) * (n_faces + 1));
-    cudaError_t e1 = cudaMemcpyAsync(h_msum, d_msum, sizeof(unsigned long long) * (n_faces + 1), cudaMemcpyDeviceToHost, stream);
-    cudaError_t e2 = cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, stream);
-    cudaError_t e3 = cudaStreamSynchronize(stream);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        free(h_msum);
-        PLAN_TRY(cuda_status(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "plan stage 2 fill"));
+    {
+        std::vector<unsigned long long> h_msum((size_t)n_faces + 1);
+        PLAN_TRY(cuda_status(cudaMemcpyAsync(h_msum.data(), sc.msum, sizeof(unsigned long long) * (n_faces + 1), cudaMemcpyDeviceToHost, stream), "read face sums"));
+        PLAN_TRY(cuda_status(cudaMemcpyAsync(h_status, sc.status, sizeof(h_status), cudaMemcpyDeviceToHost, stream), "read status"));
+        PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan stage 2 fill"));
+        std::vector<double> h_fm((size_t)n_faces);
+        for (int f = 0; f < n_faces; ++f) h_fm[f] = (double)h_msum[f];
+        plan->referenced_tangent_pixels = (int64_t)h_msum[n_faces];
+        PLAN_TRY(cuda_status(cudaMemcpy(plan->d_face_mult_sum, h_fm.data(), sizeof(double) * n_faces, cudaMemcpyHostToDevice), "copy face multiplicity sums"));
     }
-    double* h_fm = (double*)malloc(sizeof(double) * n_faces);
-    for (int f = 0; f < n_faces; ++f) h_fm[f] = (double)h_msum[f];
-    plan->referenced_tangent_pixels = (int64_t)h_msum[n_faces];
-    free(h_msum);
-    e1 = cudaMemcpy(plan->d_face_mult_sum, h_fm, sizeof(double) * n_faces, cudaMemcpyHostToDevice);
-    free(h_fm);
-    PLAN_TRY(cuda_status(e1, "copy face multiplicity sums"));
     if (h_status[1] != 0) {
         tif_set_error("tif_plan_create: %d membership entries out of range (tangent index outside the face or multiplicity > 7)", h_status[1]);
         PLAN_TRY(TIF_ERR_RANGE);
     }
-    // accepted_unique = sum of per-pixel counts; computed from the mark pass' sibling: reuse k_count_marks
-    PLAN_TRY(cuda_status(cudaMemsetAsync(d_msum, 0, sizeof(unsigned long long), stream), "memset"));
-    k_count_marks<<<1024, 256, 0, stream>>>(plan->d_s2_count, n_erp, d_msum);
+    // accepted_unique = sum of the per-pixel counts
+    PLAN_TRY(cuda_status(cudaMemsetAsync(sc.msum, 0, sizeof(unsigned long long), stream), "memset"));
+    k_count_marks<<<1024, 256, 0, stream>>>(plan->d_s2_count, n_erp, sc.msum);
     unsigned long long h_acc = 0;
-    PLAN_TRY(cuda_status(cudaMemcpyAsync(&h_acc, d_msum, sizeof(h_acc), cudaMemcpyDeviceToHost, stream), "read accepted"));
+    PLAN_TRY(cuda_status(cudaMemcpyAsync(&h_acc, sc.msum, sizeof(h_acc), cudaMemcpyDeviceToHost, stream), "read accepted"));
     PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "plan finish"));
     plan->accepted_unique = (int64_t)h_acc;
+    const int64_t n_ref = plan->referenced_tangent_pixels;
+    std::vector<int32_t> h_ref_index;           // tangent pixel -> position in the work list, -1 = unreferenced
     {
-        // work list of the lift kernel: referenced tangent pixels in 8 x 4 tile order, so that a warp works on a
-        // compact patch of one face (plan-time bookkeeping through the host: 1 byte per tangent pixel)
+        // work list of the lift kernels: referenced tangent pixels in 8 x 4 tile order, so that a warp works on a
+        // compact patch of one face (plan-time bookkeeping through the host: 1 byte per tangent pixel).
         // An entry names its pixel as face << 25 | row inside the face << 11 | column (the layout of the membership
         // entries), so that the kernel needs neither a division by the tangent width nor the row -> face table.
-        uint8_t* h_mark = (uint8_t*)malloc((size_t)n_tangent);
-        int32_t* h_list = (int32_t*)malloc(sizeof(int32_t) * (size_t)(plan->referenced_tangent_pixels + 1));
-        int32_t* h_face_of_row = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_rows);
-        int32_t* h_first_row = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_faces);
-        {
-            int64_t row = 0;
-            for (int f = 0; f < n_faces; ++f) {
-                h_first_row[f] = (int32_t)row;
-                for (int i = 0; i < faces[f].tangent_h; ++i) h_face_of_row[row++] = f;
-            }
-        }
-        cudaError_t ea = cudaMemcpy(h_mark, plan->d_ref_mark, (size_t)n_tangent, cudaMemcpyDeviceToHost);
+        std::vector<uint8_t> h_mark((size_t)n_tangent);
+        std::vector<int32_t> h_list((size_t)n_ref + 1);
+        h_ref_index.assign((size_t)n_tangent, -1);
+        PLAN_TRY(cuda_status(cudaMemcpy(h_mark.data(), plan->d_ref_mark, (size_t)n_tangent, cudaMemcpyDeviceToHost), "read referenced marks"));
         int64_t n_list = 0;
-        if (ea == cudaSuccess) {
-            for (int64_t ty = 0; ty < n_rows; ty += 4)
-                for (int tx = 0; tx < tangent_w; tx += 8)
-                    for (int64_t y = ty; y < ty + 4 && y < n_rows; ++y)
-                        for (int x = tx; x < tx + 8 && x < tangent_w; ++x)
-                            if (h_mark[y * tangent_w + x] && n_list < plan->referenced_tangent_pixels) {
-                                const int f = h_face_of_row[y];
-                                h_list[n_list++] = (int32_t)(((uint32_t)f << 25) | ((uint32_t)(y - h_first_row[f]) << 11) | (uint32_t)x);
-                            }
-        }
-        free(h_face_of_row);
-        free(h_first_row);
-        int st = dev_alloc(&plan->d_ref_list, (size_t)(plan->referenced_tangent_pixels + 1), plan);
-        cudaError_t eb = cudaSuccess;
-        if (st == TIF_OK) eb = cudaMemcpy(plan->d_ref_list, h_list, sizeof(int32_t) * (size_t)n_list, cudaMemcpyHostToDevice);
-        free(h_mark);
-        free(h_list);
-        PLAN_TRY(st);
-        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "referenced pixel list"));
-        if (n_list != plan->referenced_tangent_pixels) {
+        for (int64_t ty = 0; ty < n_rows; ty += 4)
+            for (int tx = 0; tx < tangent_w; tx += 8)
+                for (int64_t y = ty; y < ty + 4 && y < n_rows; ++y)
+                    for (int x = tx; x < tx + 8 && x < tangent_w; ++x)
+                        if (h_mark[y * tangent_w + x] && n_list < n_ref) {
+                            const int f = h_row_face[y];
+                            h_ref_index[y * tangent_w + x] = (int32_t)n_list;
+                            h_list[n_list++] = (int32_t)(((uint32_t)f << 25) | ((uint32_t)(y - h_first_row[f]) << 11) | (uint32_t)x);
+                        }
+        PLAN_TRY(dev_alloc(&plan->d_ref_list, (size_t)n_ref + 1, plan));
+        PLAN_TRY(cuda_status(cudaMemcpy(plan->d_ref_list, h_list.data(), sizeof(int32_t) * (size_t)n_list, cudaMemcpyHostToDevice), "referenced pixel list"));
+        if (n_list != n_ref) {
             tif_set_error("tif_plan_create: referenced pixel list (%lld) disagrees with the mark count (%lld)",
-                          (long long)n_list, (long long)plan->referenced_tangent_pixels);
+                          (long long)n_list, (long long)n_ref);
             PLAN_TRY(TIF_ERR_RANGE);
         }
+    }
+    if (kind == TIF_PLAN_ICOSAHEDRON && n_ref > 0) {
+        // normwarp: own ERP position of every work-list entry, and the accepted samples grouped by work-list entry
+        PLAN_TRY(dev_alloc(&plan->d_ref_pos, (size_t)n_ref, plan));
+        k_plan_ref_pos<<<(unsigned)((n_ref + 255) / 256), 256, 0, stream>>>(plan->d_ref_list, (int)n_ref, plan->d_lift_faces, tangent_w,
+                                                                         plan->d_s1_ex, plan->d_s1_ey, plan->d_ref_pos);
+        PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_ref_pos launch"));
+        const int64_t n_smp = plan->accepted_unique;
+        const int64_t n_blk = (n_ref + TIF_NW_BLOCK - 1) / TIF_NW_BLOCK;
+        if (n_smp >= (int64_t)1 << 32) {
+            tif_set_error("tif_plan_create: %lld accepted samples (max 2^32)", (long long)n_smp);
+            PLAN_TRY(TIF_ERR_UNSUPPORTED);
+        }
+        PLAN_TRY(scratch_alloc(&sc.ref_index, (size_t)n_tangent));
+        PLAN_TRY(scratch_alloc(&sc.per_ref, (size_t)n_ref));
+        PLAN_TRY(scratch_alloc(&sc.smp_start, (size_t)n_ref));
+        PLAN_TRY(dev_alloc(&plan->d_smp, (size_t)n_smp + 1, plan));
+        PLAN_TRY(dev_alloc(&plan->d_blk_smp, (size_t)n_blk + 1, plan));
+        PLAN_TRY(cuda_status(cudaMemcpy(sc.ref_index, h_ref_index.data(), sizeof(int32_t) * (size_t)n_tangent, cudaMemcpyHostToDevice), "copy work-list index"));
+        PLAN_TRY(cuda_status(cudaMemsetAsync(sc.per_ref, 0, sizeof(uint32_t) * (size_t)n_ref, stream), "memset"));
+        k_plan_samples<false><<<blocks2, threads, 0, stream>>>(plan->d_s2_count, plan->d_s2_entries, plan->d_faces, sc.ref_index, erp_h,
+                                                              erp_w, tangent_w, sc.per_ref, nullptr, nullptr);
+        PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_samples<count> launch"));
+        std::vector<uint32_t> h_cnt((size_t)n_ref), h_blk((size_t)n_blk + 1);
+        PLAN_TRY(cuda_status(cudaMemcpyAsync(h_cnt.data(), sc.per_ref, sizeof(uint32_t) * (size_t)n_ref, cudaMemcpyDeviceToHost, stream), "read sample counts"));
+        PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "sample counts"));
+        uint64_t run = 0;
+        for (int64_t i = 0; i < n_ref; ++i) {        // exclusive scan in work-list order
+            if (i % TIF_NW_BLOCK == 0) h_blk[(size_t)(i / TIF_NW_BLOCK)] = (uint32_t)run;
+            const uint32_t c = h_cnt[(size_t)i];
+            h_cnt[(size_t)i] = (uint32_t)run;
+            run += c;
+        }
+        h_blk[(size_t)n_blk] = (uint32_t)run;
+        if ((int64_t)run != n_smp) {
+            tif_set_error("tif_plan_create: sample list (%llu) disagrees with the accepted count (%lld)", (unsigned long long)run, (long long)n_smp);
+            PLAN_TRY(TIF_ERR_RANGE);
+        }
+        PLAN_TRY(cuda_status(cudaMemcpy(sc.smp_start, h_cnt.data(), sizeof(uint32_t) * (size_t)n_ref, cudaMemcpyHostToDevice), "copy sample offsets"));
+        PLAN_TRY(cuda_status(cudaMemcpy(plan->d_blk_smp, h_blk.data(), sizeof(uint32_t) * ((size_t)n_blk + 1), cudaMemcpyHostToDevice), "copy block sample ranges"));
+        PLAN_TRY(cuda_status(cudaMemsetAsync(sc.per_ref, 0, sizeof(uint32_t) * (size_t)n_ref, stream), "memset"));
+        k_plan_samples<true><<<blocks2, threads, 0, stream>>>(plan->d_s2_count, plan->d_s2_entries, plan->d_faces, sc.ref_index, erp_h,
+                                                             erp_w, tangent_w, sc.per_ref, sc.smp_start, plan->d_smp);
+        PLAN_TRY(cuda_status(cudaGetLastError(), "k_plan_samples<fill> launch"));
+        PLAN_TRY(cuda_status(cudaStreamSynchronize(stream), "sample list"));
+        plan->n_samples = n_smp;
     }
     {
         // stage-1 tile table: the bounding box of the taps of every 16 x 8 tangent patch.  Patches whose box fits a
@@ -517,72 +609,57 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         const size_t n_tiles = (size_t)tiles_x * tiles_y;
         const uint32_t row_bytes = (uint32_t)erp_w * 3u;
         const bool alignable = row_bytes % 16u == 0 && ((size_t)erp_h * row_bytes) % 16u == 0;
-        uint32_t* h_base = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_tangent);
-        uint2* h_tiles = (uint2*)malloc(sizeof(uint2) * n_tiles);
-        uint32_t* h_need = (uint32_t*)malloc(sizeof(uint32_t) * n_tiles);     // bytes of a stage the box needs, 0 = unusable
-        cudaError_t ea = cudaMemcpy(h_base, plan->d_s1_base, sizeof(uint32_t) * (size_t)n_tangent, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> h_base((size_t)n_tangent), h_need(n_tiles);     // h_need: bytes of a stage the box needs, 0 = unusable
+        std::vector<uint2> h_tiles(n_tiles);
+        PLAN_TRY(cuda_status(cudaMemcpy(h_base.data(), plan->d_s1_base, sizeof(uint32_t) * (size_t)n_tangent, cudaMemcpyDeviceToHost), "read stage-1 taps"));
         int64_t staged = 0;
         int stage_bytes = TIF_S1_MIN_STAGE_BYTES;
-        if (ea == cudaSuccess) {
-            for (int ty = 0; ty < tiles_y; ++ty)
-                for (int tx = 0; tx < tiles_x; ++tx) {
-                    uint32_t x_lo = 0xffffffffu, x_hi = 0, y_lo = 0xffffffffu, y_hi = 0;
-                    for (int64_t y = (int64_t)ty * tile_h; y < (int64_t)(ty + 1) * tile_h && y < n_rows; ++y)
-                        for (int x = tx * tile_w; x < (tx + 1) * tile_w && x < tangent_w; ++x) {
-                            const uint32_t b = h_base[y * tangent_w + x] & 0x7fffffffu;
-                            const uint32_t y0 = b / (uint32_t)erp_w, x0 = b - y0 * (uint32_t)erp_w;
-                            x_lo = x0 < x_lo ? x0 : x_lo;
-                            x_hi = x0 > x_hi ? x0 : x_hi;
-                            y_lo = y0 < y_lo ? y0 : y_lo;
-                            y_hi = y0 > y_hi ? y0 : y_hi;
-                        }
-                    uint2 d = make_uint2(0u, 0u);
-                    uint32_t need = 0u;
-                    if (alignable && x_lo <= x_hi) {
-                        const uint32_t xb0 = (x_lo * 3u) & ~15u;
-                        uint32_t xb1 = ((x_hi + 2u) * 3u + 15u) & ~15u;       // taps x0, x0 + 1: 6 bytes from x0 * 3
-                        if (xb1 > row_bytes) xb1 = row_bytes;
-                        const uint32_t pitch = xb1 - xb0, rows = y_hi + 2u - y_lo;
-                        // 16 bytes of slack: the aligned 12-byte window of the last tap may end past its row
-                        const size_t bytes = (size_t)rows * pitch + 16u;
-                        if (bytes <= TIF_S1_MAX_STAGE_BYTES && y_hi + 1u < (uint32_t)erp_h) {
-                            d = make_uint2(y_lo * row_bytes + xb0, rows | (pitch << 16));
-                            need = (uint32_t)bytes;
-                        }
+        for (int ty = 0; ty < tiles_y; ++ty)
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                uint32_t x_lo = 0xffffffffu, x_hi = 0, y_lo = 0xffffffffu, y_hi = 0;
+                for (int64_t y = (int64_t)ty * tile_h; y < (int64_t)(ty + 1) * tile_h && y < n_rows; ++y)
+                    for (int x = tx * tile_w; x < (tx + 1) * tile_w && x < tangent_w; ++x) {
+                        const uint32_t b = h_base[y * tangent_w + x] & 0x7fffffffu;
+                        const uint32_t y0 = b / (uint32_t)erp_w, x0 = b - y0 * (uint32_t)erp_w;
+                        x_lo = x0 < x_lo ? x0 : x_lo;
+                        x_hi = x0 > x_hi ? x0 : x_hi;
+                        y_lo = y0 < y_lo ? y0 : y_lo;
+                        y_hi = y0 > y_hi ? y0 : y_hi;
                     }
-                    h_tiles[(size_t)ty * tiles_x + tx] = d;
-                    h_need[(size_t)ty * tiles_x + tx] = need;
+                uint2 d = make_uint2(0u, 0u);
+                uint32_t need = 0u;
+                if (alignable && x_lo <= x_hi) {
+                    const uint32_t xb0 = (x_lo * 3u) & ~15u;
+                    uint32_t xb1 = ((x_hi + 2u) * 3u + 15u) & ~15u;       // taps x0, x0 + 1: 6 bytes from x0 * 3
+                    if (xb1 > row_bytes) xb1 = row_bytes;
+                    const uint32_t pitch = xb1 - xb0, rows = y_hi + 2u - y_lo;
+                    // 16 bytes of slack: the aligned 12-byte window of the last tap may end past its row
+                    const size_t bytes = (size_t)rows * pitch + 16u;
+                    if (bytes <= TIF_S1_MAX_STAGE_BYTES && y_hi + 1u < (uint32_t)erp_h) {
+                        d = make_uint2(y_lo * row_bytes + xb0, rows | (pitch << 16));
+                        need = (uint32_t)bytes;
+                    }
                 }
-            // the smallest stage that holds most boxes (small stages leave more shared memory to the L1 and more
-            // stages in the ring); what does not fit is resampled by direct gathers
-            for (;;) {
-                staged = 0;
-                for (size_t i = 0; i < n_tiles; ++i) staged += h_need[i] != 0u && h_need[i] <= (uint32_t)stage_bytes;
-                if ((double)staged >= TIF_S1_STAGED_SHARE * (double)n_tiles || stage_bytes >= TIF_S1_MAX_STAGE_BYTES) break;
-                stage_bytes *= 2;
+                h_tiles[(size_t)ty * tiles_x + tx] = d;
+                h_need[(size_t)ty * tiles_x + tx] = need;
             }
-            for (size_t i = 0; i < n_tiles; ++i)
-                if (h_need[i] == 0u || h_need[i] > (uint32_t)stage_bytes) h_tiles[i] = make_uint2(0u, 0u);
+        // the smallest stage that holds most boxes (small stages leave more shared memory to the L1 and more
+        // stages in the ring); what does not fit is resampled by direct gathers
+        for (;;) {
+            staged = 0;
+            for (size_t i = 0; i < n_tiles; ++i) staged += h_need[i] != 0u && h_need[i] <= (uint32_t)stage_bytes;
+            if ((double)staged >= TIF_S1_STAGED_SHARE * (double)n_tiles || stage_bytes >= TIF_S1_MAX_STAGE_BYTES) break;
+            stage_bytes *= 2;
         }
-        free(h_need);
+        for (size_t i = 0; i < n_tiles; ++i)
+            if (h_need[i] == 0u || h_need[i] > (uint32_t)stage_bytes) h_tiles[i] = make_uint2(0u, 0u);
         plan->s1_stage_bytes = stage_bytes;
-        int st = dev_alloc(&plan->d_s1_tiles, n_tiles, plan);
-        cudaError_t eb = cudaSuccess;
-        if (st == TIF_OK) eb = cudaMemcpy(plan->d_s1_tiles, h_tiles, sizeof(uint2) * n_tiles, cudaMemcpyHostToDevice);
-        free(h_base);
-        free(h_tiles);
-        PLAN_TRY(st);
-        PLAN_TRY(cuda_status(ea != cudaSuccess ? ea : eb, "stage-1 tile table"));
+        PLAN_TRY(dev_alloc(&plan->d_s1_tiles, n_tiles, plan));
+        PLAN_TRY(cuda_status(cudaMemcpy(plan->d_s1_tiles, h_tiles.data(), sizeof(uint2) * n_tiles, cudaMemcpyHostToDevice), "stage-1 tile table"));
         plan->s1_tiles_x = tiles_x;
         plan->s1_tiles_y = tiles_y;
         plan->s1_staged_tiles = staged;
     }
-    cudaFree(d_gx);
-    cudaFree(d_gy);
-    cudaFree(d_rows);
-    cudaFree(d_cols);
-    cudaFree(d_status);
-    cudaFree(d_msum);
     *plan_out = plan;
     return TIF_OK;
 }

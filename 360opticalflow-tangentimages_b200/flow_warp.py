@@ -7,7 +7,7 @@
     global_rotation_warping(erp_image, erp_flow, forward_warp=True, rotation_type="3D")  (row f2)
 
 numpy in -> numpy out with the reference's dtypes; torch CUDA tensors with a leading batch axis stay
-on the device.  flow2rotation_2d (the "2D" rotation type, scipy.stats based) is not on the accelerated path.
+on the device.  flow2rotation_2d (the "2D" rotation type) reduces its six sums on the device as well.
 """
 import numpy as np
 import torch
@@ -38,8 +38,8 @@ def warp_backward(image_target, of_forward):
     """Backward warp: out(y,x) = bilinear(image_target, (y+v, x+u)) (src/flow_warp.py:54-88).
 
     [H,W,C] images use scipy's mode='wrap' (period n-1), [H,W] images mode='constant' with 255;
-    uint8 images are rounded half-up.  float64 images are computed in float64 on the device side of the
-    bilinear (float32 storage), other float images likewise.
+    uint8 images are rounded half-up; float32 / float64 images are accumulated in float64 in scipy's order and
+    stored in their own dtype, so the result equals the reference's bit for bit.
     """
     if isinstance(image_target, torch.Tensor):
         mode = _lib.WARP_WRAP
@@ -55,10 +55,10 @@ def warp_backward(image_target, of_forward):
     else:
         raise ValueError("The image shape is %s, do not support." % (image_target.shape,))
     dev = _device()
-    if img.dtype == np.uint8:
+    if img.dtype in (np.uint8, np.float32, np.float64):
         img_dev = torch.from_numpy(np.ascontiguousarray(img)).to(dev)[None]
-    else:
-        img_dev = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)[None]
+    else:           # other dtypes: scipy computes in float64 and casts back to the image's dtype
+        img_dev = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float64)).to(dev)[None]
     out = _ops.ops.warp_backward(img_dev, torch.from_numpy(flow).to(dev)[None], mode)[0].cpu().numpy()
     out = out.astype(image_target.dtype, copy=False)
     return out if image_target.ndim == 3 else out[:, :, 0]

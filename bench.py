@@ -4,19 +4,22 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
   python bench.py --impl reference --steps K --warmup W    (CPU port of the reference, all host cores)
 
-Workload (BASELINE.json configs[1] / configs[3]): synthetic 2048x1024 ERP pairs, 20 tangent faces,
-padding 0.3, 480x416 tangent images, tangent flows injected on the device (the per-face DIS estimator is
-a fixed CPU stage, excluded).  One step = one pass of the hot path over a batch of --batch pairs per GPU
-(32 pairs: 1.9 GB of inputs per GPU, far larger than the 126 MB L2).  Pairs are independent, so ranks
-shard the batch with no data-path collective (weak scaling: per-GPU batch fixed).
+Headline workload (BASELINE.json configs[1] / configs[3]): synthetic 2048x1024 ERP pairs, 20 tangent faces,
+padding 0.3, 480x416 tangent images, normwarp blend, tangent flows injected on the device (the per-face DIS
+estimator is a fixed CPU stage, excluded).  One step = one pass of the hot path over a batch of --batch pairs per GPU
+(32 pairs: 1.9 GB of inputs per GPU, far larger than the 126 MB L2).  Pairs are independent, so ranks shard the batch
+with no data-path collective inside the step (weak scaling: per-GPU batch fixed); at N>1 the run is repeated with the
+one exchange the path has -- collecting the stitched flows on rank 0 -- fused into the stitch (`gather`).
+
+The same JSON line also carries, under `configs`, short device-resident runs of the other shapes BASELINE.json names
+(config #3: 3840x1920 with the flow_warp evaluation; config #5: 4096x2048 with the 80-face subdivision; the
+straightforward blend at 2K), each with its per-kernel roofline fractions (N=1 only; --no-extra-configs skips them).
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,22 +38,36 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frame pairs per GPU per step")
     ap.add_argument("--height", type=int, default=1024, help="ERP height (width = 2x)")
+    ap.add_argument("--level", type=int, default=0, choices=[0, 1], help="1: the 80-face subdivision (config #5)")
     ap.add_argument("--blend", default="normwarp", choices=["straightforward", "normwarp"],
                     help="face_blending_method; normwarp is the reference pipeline's default (flow_estimate.py:104)")
+    ap.add_argument("--warp", action="store_true", help="add warp_backward(tar, stitched flow) to the step (config #3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the run with the collection of the flows on rank 0")
+    ap.add_argument("--gather-mode", default="fused", choices=["fused", "copy", "nccl"],
+                    help="fused: the blend kernel stores into rank 0's peer-mapped buffer; copy: local result + "
+                         "cudaMemcpyAsync to the peer buffer on a side stream; nccl: dist.gather after each step")
     ap.add_argument("--serial", action="store_true", help="launch the step's kernels on one stream (no overlap)")
     ap.add_argument("--kernel-reps", type=int, default=10)
     return ap.parse_args()
 
 
+def workload_name(height, level, blend, warp):
+    return ("synthetic %dx%d ERP pairs, %d tangent faces %s, padding 0.3, blend %s, wrap_around, tangent flows injected "
+            "(DIS excluded)%s" % (2 * height, height, 80 if level else 20, "480 x {346,416,485,502}" if level else "480x416",
+                                 blend, ", + warp_backward(tar, flow)" if warp else ""))
+
+
 def workload_config(args, n_gpus):
-    return {"workload": "synthetic %dx%d ERP pairs, 20 tangent faces 480x416, padding 0.3, blend %s, wrap_around, "
-                        "tangent flows injected (DIS excluded)" % (2 * args.height, args.height, args.blend),
+    per_pair = 2 * args.height * 2 * args.height * 3 + 20 * 416 * 480 * 8
+    return {"workload": workload_name(args.height, args.level, args.blend, args.warp),
             "pairs_per_gpu_per_step": args.batch, "global_pairs_per_step": args.batch * n_gpus,
-            "sharding": "batch across ranks, no data-path collective",
-            "streams": "1 (serial)" if args.serial else "3 (resample src | resample tar | stitch overlap)", "l2": "inputs (%.1f GB/GPU/step) exceed the 126 MB L2"
-            % (args.batch * (2 * args.height * 2 * args.height * 3 + 20 * 416 * 480 * 8) / 1e9)}
+            "sharding": "batch across ranks, no data-path collective inside the step (the collection of the stitched "
+                        "flows on rank 0 is reported under `gather`)",
+            "streams": "1 (serial)" if args.serial else "3 (resample src | resample tar | stitch)",
+            "l2": "inputs (%.1f GB/GPU/step) exceed the 126 MB L2" % (args.batch * per_pair / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -157,8 +174,7 @@ class ClockSampler:
 
 def bind_to_gpu_numa_node(index):
     """One process per GPU: run on the CPUs NVML reports as local to the GPU, so that the pinned staging buffers of
-    the end-to-end pipeline are first-touched on that NUMA node (the host<->device copies of the ranks otherwise
-    share one node's memory controllers).  Returns the number of CPUs bound to, or None."""
+    the end-to-end pipeline are first-touched on that NUMA node.  Returns the number of CPUs bound to, or None."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -176,23 +192,199 @@ def bind_to_gpu_numa_node(index):
 
 
 def synth_device(torch, plan, batch, seed, device):
-    """Synthetic pairs on the device: IID uint8 images, analytic tangent flows."""
+    """Synthetic pairs on the device: IID uint8 images, analytic tangent flows (level 1: the same
+    formula with f/80 and every face's own height)."""
     import math
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     h, w = plan.erp_h, plan.erp_w
     src = torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8, device=device, generator=g)
     tar = torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8, device=device, generator=g)
-    ht, wt, nf = plan.tangent_h, plan.tangent_w, plan.n_faces
-    yy = torch.arange(ht, device=device, dtype=torch.float64).view(1, ht, 1)
-    xx = torch.arange(wt, device=device, dtype=torch.float64).view(1, 1, wt)
-    ff = torch.arange(nf, device=device, dtype=torch.float64).view(nf, 1, 1) / nf
-    u = (4.0 * torch.sin(2 * math.pi * (xx / wt + ff)) + 1.5).expand(nf, ht, wt)
-    v = (3.0 * torch.cos(2 * math.pi * (yy / ht - ff)) - 0.5).expand(nf, ht, wt)
-    one = torch.stack((u, v), -1).to(torch.float32).reshape(1, plan.tangent_pixels, 2)
+    wt, nf = plan.tangent_w, plan.n_faces
+    xx = torch.arange(wt, device=device, dtype=torch.float64).view(1, wt)
+    parts = []
+    for f, ht in enumerate(plan.face_heights):
+        yy = torch.arange(ht, device=device, dtype=torch.float64).view(ht, 1)
+        u = (4.0 * torch.sin(2 * math.pi * (xx / wt + f / nf)) + 1.5).expand(ht, wt)
+        v = (3.0 * torch.cos(2 * math.pi * (yy / ht - f / nf)) - 0.5).expand(ht, wt)
+        parts.append(torch.stack((u, v), -1).to(torch.float32).reshape(-1, 2))
+    one = torch.cat(parts).reshape(1, plan.tangent_pixels, 2)
     jitter = torch.rand((batch, 1, 2), device=device, generator=g) - 0.5      # per-pair offset so pairs differ
     flows = (one + jitter).contiguous()
     return src, tar, flows
+
+
+def load_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+class Workload:
+    """One configuration resident on one GPU: plan, synthetic inputs, outputs, scratch, and its step."""
+
+    def __init__(self, torch, pkg, device, height, level, blend_name, batch, seed, warp):
+        self.torch, self.pkg, self.device = torch, pkg, device
+        self.ops, self.lib = pkg._ops, pkg._lib
+        self.height, self.level, self.blend_name, self.batch, self.warp = height, level, blend_name, batch, warp
+        self.blend = self.lib.BLEND_NORMWARP if blend_name == "normwarp" else self.lib.BLEND_STRAIGHTFORWARD
+        t0 = time.perf_counter()
+        self.plan = plan = pkg._geometry.get_plan(PAD, height, TANGENT_W, device, level)
+        torch.cuda.synchronize()
+        self.plan_build_ms = 1e3 * (time.perf_counter() - t0)
+        self.src, self.tar, self.flows = synth_device(torch, plan, batch, seed, device)
+        self.tan_src = torch.empty((batch, plan.tangent_pixels, 4), dtype=torch.uint8, device=device)
+        self.tan_tar = torch.empty_like(self.tan_src)
+        self.out = torch.empty((batch, plan.erp_h, plan.erp_w, 2), dtype=torch.float32, device=device)
+        self.warped = torch.empty_like(self.tar) if warp else None
+        need = int(plan.lib.tif_ico2erp_scratch_bytes(plan.handle, batch, self.blend))
+        self.scratch = torch.empty(max(need, 8), dtype=torch.uint8, device=device)
+        self.side = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+        self.fork, self.joins = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
+        # erp2ico x2; stitch = k_lift + k_gather, or (normwarp) k_lift_nw + k_nw_face_scale + k_blend_nw; + warp
+        self.launches_per_step = (4 if self.blend == self.lib.BLEND_STRAIGHTFORWARD else 5) + (1 if warp else 0)
+        self.out_target = self.out        # a raw peer address while the gather is fused into the stitch
+
+    def _warp(self):
+        lib = self.lib.load()
+        p, t = self.plan, self.torch
+        self.lib.check(lib.tif_warp_backward_u8(self.tar.data_ptr(), self.out.data_ptr(), self.lib.DTYPE_F32, self.batch, p.erp_h,
+                                                p.erp_w, 3, self.lib.WARP_WRAP, self.warped.data_ptr(),
+                                                t.cuda.current_stream().cuda_stream), "tif_warp_backward_u8")
+
+    def step(self, serial=False):
+        ops, plan, t = self.ops, self.plan, self.torch
+        if serial:
+            ops.erp2ico_out(plan, self.src, True, self.tan_src)
+            ops.erp2ico_out(plan, self.tar, True, self.tan_tar)
+            ops.ico2erp_flow_out(plan, self.flows, self.src, self.tar, self.blend, True, self.out_target, self.scratch)
+        else:
+            # the two resamplings and the stitch are independent of each other: separate streams let their blocks
+            # share the SMs (`streams` in the JSON line reports what that buys against one stream)
+            main = t.cuda.current_stream()
+            self.fork.record(main)
+            for s_, img, dst, ev in ((self.side[0], self.src, self.tan_src, self.joins[0]),
+                                     (self.side[1], self.tar, self.tan_tar, self.joins[1])):
+                s_.wait_event(self.fork)
+                with t.cuda.stream(s_):
+                    ops.erp2ico_out(plan, img, True, dst)
+                    ev.record(s_)
+            ops.ico2erp_flow_out(plan, self.flows, self.src, self.tar, self.blend, True, self.out_target, self.scratch)
+            main.wait_event(self.joins[0])
+            main.wait_event(self.joins[1])
+        if self.warp:
+            self._warp()
+
+    def kernels(self):
+        """name -> (launcher, algorithmic bytes per launch, launches per step); bytes per SURVEY.md section 8d."""
+        ops, plan, lib = self.ops, self.plan, self.lib
+        B, hw = self.batch, plan.erp_h * plan.erp_w
+        P, Pref = plan.tangent_pixels, plan.referenced_tangent_pixels
+        sf, nw = lib.BLEND_STRAIGHTFORWARD, lib.BLEND_NORMWARP
+        a = (self.flows, self.src, self.tar)
+        ks = {"k_erp2ico": (lambda: ops.erp2ico_out(plan, self.src, True, self.tan_src), B * (hw * 3 + P * 4), 2)}
+        if self.blend == sf:
+            # pass_mask: 8 = the lift kernel only, 4 = skip the lift (reuse its records), 1|2 = the gather
+            ks["k_lift<straightforward>"] = (lambda: ops.ico2erp_flow_out(plan, a[0], None, None, sf, True, self.out, self.scratch, 8), B * 8 * Pref, 1)
+            ks["k_gather<straightforward>"] = (lambda: ops.ico2erp_flow_out(plan, a[0], None, None, sf, True, self.out, self.scratch, 4 | 3), B * 8 * hw, 1)
+        else:
+            # k_lift_nw = end-point lift + target samples + warp error of every sample + face sums (reads the referenced
+            # tangent flows and both ERP images); k_blend_nw = weights + blend (writes the ERP flow)
+            ks["k_lift_nw"] = (lambda: ops.ico2erp_flow_out(plan, a[0], a[1], a[2], nw, True, self.out, self.scratch, 1), B * (8 * Pref + 6 * hw), 1)
+            ks["k_blend_nw"] = (lambda: ops.ico2erp_flow_out(plan, a[0], a[1], a[2], nw, True, self.out, self.scratch, 2), B * 8 * hw, 1)
+        if self.warp:
+            ks["k_warp_backward"] = (self._warp, B * hw * (3 + 8 + 3), 1)
+        return ks
+
+    def step_bytes(self):
+        return sum(nbytes * per_step for _, nbytes, per_step in self.kernels().values())
+
+
+def time_steps(torch, dist, world, device, fn, steps, warmup, sampler=None):
+    """K steps between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.02)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler is not None else None
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, clocks
+
+
+def kernel_rooflines(torch, wl, reps, peak_gbs, traffic):
+    """Every kernel of the step alone: CUDA events around `reps` back-to-back launches (inputs >> L2)."""
+    out = {}
+    key = "h%d_l%d" % (wl.height, wl.level)
+    per_pair = traffic.get("bytes_per_pair", {}).get(key, {})
+    for name, (fn, nbytes, per_step) in wl.kernels().items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        tr = per_pair.get(name)
+        out[name] = {"ms": ms, "launches_per_step": per_step, "algorithmic_bytes": nbytes, "gbs": gbs, "frac": gbs / peak_gbs,
+                     "traffic": tr * wl.batch if tr else None,
+                     "dram_over_algorithmic": (tr * wl.batch / nbytes) if tr else None}
+    return out
+
+
+def roofline_block(wl, ktimes, ms_per_step, peak_gbs, peak_src):
+    weight = {k: v["ms"] * v["launches_per_step"] for k, v in ktimes.items()}
+    dominant = max(weight, key=weight.get)
+    step_gbs = wl.step_bytes() / (ms_per_step * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": dominant, "achieved": ktimes[dominant]["gbs"], "peak": peak_gbs, "unit": "GB/s",
+            "frac": ktimes[dominant]["frac"], "traffic": ktimes[dominant]["traffic"], "peak_source": peak_src,
+            "share_of_step": weight[dominant] / sum(weight.values()),
+            "step_frac": step_gbs / peak_gbs, "step_algorithmic_bytes": wl.step_bytes(), "step_gbs": step_gbs,
+            "sum_of_kernel_ms": sum(weight.values()), "kernels": ktimes}
+
+
+def pcie_probe(torch, device, mib=256, reps=6):
+    """Raw pinned-memory copy ceiling of this rank's link: H2D alone, D2H alone, both at once."""
+    n = mib << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=device), torch.empty(n, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def run(h2d, d2h):
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize(device)
+        return n * reps / (time.perf_counter() - t0) / 1e9
+    run(True, True)
+    return {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "both_gbs_each_direction": run(True, True)}
 
 
 def run_ours(args):
@@ -224,74 +416,7 @@ def run_ours(args):
             os.close(saved)
     entry.build()
     pkg = entry.load_package()
-    ops, lib = pkg._ops, pkg._lib
-    blend = lib.BLEND_NORMWARP if args.blend == "normwarp" else lib.BLEND_STRAIGHTFORWARD
 
-    t0 = time.perf_counter()
-    plan = pkg._geometry.get_plan(PAD, args.height, TANGENT_W, device)
-    torch.cuda.synchronize()
-    plan_build_ms = 1e3 * (time.perf_counter() - t0)
-
-    B = args.batch
-    src, tar, flows = synth_device(torch, plan, B, 1234 + rank, device)
-    tan_src = torch.empty((B, plan.tangent_pixels, 4), dtype=torch.uint8, device=device)
-    tan_tar = torch.empty_like(tan_src)
-    out = torch.empty((B, plan.erp_h, plan.erp_w, 2), dtype=torch.float32, device=device)
-    scratch = torch.empty(max(int(plan.lib.tif_ico2erp_scratch_bytes(plan.handle, B, lib.BLEND_NORMWARP)), 8),
-                          dtype=torch.uint8, device=device)
-    # erp2ico x2; stitch = k_lift + k_gather (normwarp: k_lift, k_gather<sums>, k_gather<blend>)
-    launches_per_step = 4 if blend == lib.BLEND_STRAIGHTFORWARD else 6
-
-    # The two resamplings and the stitch are independent of each other: they run on separate streams so that
-    # their blocks share the SMs (each kernel alone is issue/latency bound and leaves slots idle).
-    side = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
-    fork, joins = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
-
-    def step():
-        main = torch.cuda.current_stream()
-        if args.serial:
-            ops.erp2ico_out(plan, src, True, tan_src)
-            ops.erp2ico_out(plan, tar, True, tan_tar)
-            ops.ico2erp_flow_out(plan, flows, src, tar, blend, True, out, scratch)
-            return
-        fork.record(main)
-        for s_, img, dst, ev in ((side[0], src, tan_src, joins[0]), (side[1], tar, tan_tar, joins[1])):
-            s_.wait_event(fork)
-            with torch.cuda.stream(s_):
-                ops.erp2ico_out(plan, img, True, dst)
-                ev.record(s_)
-        ops.ico2erp_flow_out(plan, flows, src, tar, blend, True, out, scratch)
-        main.wait_event(joins[0])
-        main.wait_event(joins[1])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.02)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
-
-    # ---- per-kernel timing (CUDA events on the launching stream) and roofline ------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -299,98 +424,65 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    hw = plan.erp_h * plan.erp_w
-    P, Pref = plan.tangent_pixels, plan.referenced_tangent_pixels
-    sf, nw = lib.BLEND_STRAIGHTFORWARD, lib.BLEND_NORMWARP
-    # pass_mask: 1 = lift + normwarp face sums, 2 = blend, 4 = skip the lift kernel (reuse the records), 8 = lift only
-    kernels = {
-        "k_erp2ico": (lambda: ops.erp2ico_out(plan, src, True, tan_src), B * (hw * 3 + P * 4)),
-        "k_lift<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 8),
-                                    B * (8 * Pref)),
-        "k_gather<straightforward>": (lambda: ops.ico2erp_flow_out(plan, flows, None, None, sf, True, out, scratch, 4 | 3),
-                                      B * (8 * hw)),
-        "k_lift<normwarp>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 8),
-                             B * (8 * Pref + 3 * hw)),
-        "k_gather<sums>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 1 | 4), B * (3 * hw)),
-        "k_gather<blend>": (lambda: ops.ico2erp_flow_out(plan, flows, src, tar, nw, True, out, scratch, 2), B * (8 * hw)),
-    }
-    ktimes = {}
-    for name, (fn, nbytes) in kernels.items():
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.kernel_reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / args.kernel_reps
-        ktimes[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
-                        "frac": nbytes / (ms * 1e-3) / 1e9 / peak_gbs}
-    used = ["k_erp2ico"] + (["k_lift<straightforward>", "k_gather<straightforward>"] if blend == sf
-                            else ["k_lift<normwarp>", "k_gather<sums>", "k_gather<blend>"])
-    weight = {k: ktimes[k]["ms"] * (2 if k == "k_erp2ico" else 1) for k in used}
-    dominant = max(weight, key=weight.get)
-    traffic = None
-    try:
-        # dram__bytes_read.sum + dram__bytes_write.sum per frame pair from the committed `ncu --set full` capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tr.get("erp_h") == args.height and dominant in tr.get("bytes_per_pair", {}):
-            traffic = tr["bytes_per_pair"][dominant] * B
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": ktimes[dominant]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": ktimes[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "share_of_step": weight[dominant] / sum(weight.values()), "kernels": ktimes}
+    traffic = load_traffic()
+
+    B = args.batch
+    wl = Workload(torch, pkg, device, args.height, args.level, args.blend, B, 1234 + rank, args.warp)
+    plan = wl.plan
+
+    # ---- the timed steps ---------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_per_step, clocks = time_steps(torch, dist, world, device, lambda: wl.step(args.serial), args.steps, args.warmup, sampler)
+    value = world * B / (ms_per_step * 1e-3)
+    # what the three streams buy: the same step on one stream (a few steps, not part of `value`)
+    alt_ms, _ = time_steps(torch, dist, world, device, lambda: wl.step(not args.serial), max(3, args.steps // 4), 2)
+    streams = {"overlapped_ms_per_step": alt_ms if args.serial else ms_per_step,
+               "serial_ms_per_step": ms_per_step if args.serial else alt_ms}
+    streams["serial_over_overlapped"] = streams["serial_ms_per_step"] / streams["overlapped_ms_per_step"]
+
+    # ---- per-kernel timing (CUDA events on the launching stream) and roofline ------------------------------
+    ktimes = kernel_rooflines(torch, wl, args.kernel_reps, peak_gbs, traffic)
+    roofline = roofline_block(wl, ktimes, ms_per_step, peak_gbs, peak_src)
+    wl.step(True)
+    torch.cuda.synchronize()
+    reference_out = wl.out.clone()
+
+    # ---- the path's only exchange: the stitched flows of all ranks collected on rank 0 ---------------------
+    gather = None
+    if world > 1 and not args.no_gather:
+        gather = run_with_gather(args, torch, dist, pkg, wl, world, rank, device, ms_per_step)
 
     # ---- end to end through the public host API (pinned host buffers, copies inside the timed region) -------
     e2e = None
-    if not args.no_e2e:
-        pipe = pkg.pipeline.HostPipeline(PAD, args.height, TANGENT_W, args.blend, True, chunk=2, slots=4, device=device)
-        h_src, h_tar, h_flows = (t.cpu().pin_memory() for t in (src, tar, flows))
-        h_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        h_ts = torch.empty(tan_src.shape, dtype=torch.uint8).pin_memory()
-        h_tt = torch.empty(tan_src.shape, dtype=torch.uint8).pin_memory()
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            pipe.run(h_src, h_tar, h_flows, h_out, h_ts, h_tt)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            pipe.run(h_src, h_tar, h_flows, h_out, h_ts, h_tt)
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        ok = bool(torch.allclose(h_out.to(device), out, atol=0, rtol=0))
-        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": B * pipe.h2d_bytes_per_pair(),
-               "d2h_bytes_per_step": B * pipe.d2h_bytes_per_pair(), "steps": e2e_steps,
-               "api": "pipeline.HostPipeline.run (pinned host in/out; D2H returns both tangent stacks and the ERP flow)",
-               "matches_device_path": ok}
-        del pipe, h_src, h_tar, h_flows, h_out, h_ts, h_tt
+    if not args.no_e2e and args.level == 0:
+        e2e = run_e2e(args, torch, dist, pkg, wl, world, rank, device, reference_out)
 
-    # ---- optional collection of the stitched flows on rank 0 (the path's only exchange) --------------------
-    gather = None
-    if world > 1:
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pkg.sharding.gather_erp_flow(out, B * world, dst=0)
-        barrier()
-        a.record()
-        pkg.sharding.gather_erp_flow(out, B * world, dst=0)
-        b.record()
-        barrier()
-        t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(t.item()), "bytes_to_rank0": (world - 1) * out.numel() * 4,
-                  "note": "NCCL gather of [B,H,W,2] f32 to rank 0, outside the timed steps"}
+    # ---- the other configurations BASELINE.json names, device resident, short (N=1) -------------------------
+    configs = None
+    if world == 1 and not args.no_extra_configs and args.height == 1024 and args.level == 0:
+        del reference_out
+        configs = {}
+        extra = [("config2_2048x1024_straightforward", 1024, 0, "straightforward", 32, False),
+                 ("config3_3840x1920_normwarp_warp", 1920, 0, "normwarp", 16, True),
+                 ("config5_4096x2048_level1_80faces", 2048, 1, "normwarp", 8, False)]
+        for name, height, level, blend, batch, warp in extra:
+            torch.cuda.empty_cache()
+            w2 = Workload(torch, pkg, device, height, level, blend, batch, 99, warp)
+            ms2, _ = time_steps(torch, dist, 1, device, lambda: w2.step(False), 6, 3)
+            k2 = kernel_rooflines(torch, w2, 5, peak_gbs, traffic)
+            rf = roofline_block(w2, k2, ms2, peak_gbs, peak_src)
+            configs[name] = {"workload": workload_name(height, level, blend, warp), "pairs_per_step": batch, "steps": 6,
+                             "value": batch / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "step_frac": rf["step_frac"],
+                             "plan_build_ms": w2.plan_build_ms, "plan_device_bytes": w2.plan.device_bytes,
+                             "kernels": {k: {"ms": v["ms"], "frac": v["frac"], "gbs": v["gbs"], "algorithmic_bytes": v["algorithmic_bytes"]}
+                                         for k, v in k2.items()}}
+            del w2
+            if level == 1:
+                pkg._geometry.clear_plans()
 
     # ---- CPU baseline: the oracle port on one host core, bounded sample ----------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.level == 0:
         from oracle import cpu_baseline, synth
         s_src, s_tar = synth.synth_images(args.height, 0)
         s_flows = synth.synth_flows(TANGENT_W)
@@ -400,17 +492,130 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 images / f32 flow (f64 geometry plan)", "data": "synthetic", "config": workload_config(args, world),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "clocks": clocks, "plan": {"build_ms_outside_timed_region": plan_build_ms, "device_bytes": plan.device_bytes,
-                                           "max_faces_per_pixel": plan.max_faces_per_pixel, "accepted": plan.accepted_unique,
-                                           "referenced_tangent_pixels": Pref},
-                "gather": gather, "cpus_bound_per_rank": cpu_binding}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": wl.launches_per_step * args.steps,
+                "clocks": clocks, "streams": streams, "gather": gather, "configs": configs,
+                "plan": {"build_ms_outside_timed_region": wl.plan_build_ms, "device_bytes": plan.device_bytes,
+                         "max_faces_per_pixel": plan.max_faces_per_pixel, "accepted": plan.accepted_unique,
+                         "referenced_tangent_pixels": plan.referenced_tangent_pixels},
+                "cpus_bound_per_rank": cpu_binding}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_with_gather(args, torch, dist, pkg, wl, world, rank, device, ms_plain):
+    """The timed steps again with the collection of the stitched flows on rank 0 on the path."""
+    B, plan = wl.batch, wl.plan
+    n_items = B * world
+    total_bytes = (world - 1) * B * plan.erp_h * plan.erp_w * 8
+    info = {"mode": args.gather_mode, "bytes_into_rank0_per_step": total_bytes}
+    steps, warmup = args.steps, args.warmup
+    if args.gather_mode == "nccl":
+        def step():
+            wl.step(args.serial)
+            pkg.sharding.gather_erp_flow(wl.out, n_items, dst=0)
+        ms, _ = time_steps(torch, dist, world, device, step, steps, warmup)
+        info["note"] = "blocking dist.gather (NCCL send/recv into rank 0) after every step"
+    else:
+        buf = pkg.sharding.PeerGatherBuffer(n_items, plan.erp_h, plan.erp_w, dst=0, device=device)
+        lib = pkg._lib.load()
+        nbytes = B * plan.erp_h * plan.erp_w * 8
+        if args.gather_mode == "fused":
+            wl.out_target = buf.slice_ptr()           # the blend kernel's stores cross NVLink themselves
+            ms, _ = time_steps(torch, dist, world, device, lambda: wl.step(args.serial), steps, warmup)
+            wl.out_target = wl.out
+            info["note"] = ("peer-store epilogue: every rank's blend kernel writes its [B,H,W,2] shard straight into rank 0's "
+                            "CUDA-IPC-mapped buffer (no staging, no receive side)")
+        else:
+            copy_stream, done, free = torch.cuda.Stream(device), torch.cuda.Event(), torch.cuda.Event()
+            state = {"first": True}
+
+            def step():
+                main = torch.cuda.current_stream()
+                if not state["first"]:
+                    main.wait_event(free)             # the previous push has read wl.out
+                state["first"] = False
+                wl.step(args.serial)
+                done.record(main)
+                copy_stream.wait_event(done)
+                with torch.cuda.stream(copy_stream):
+                    pkg._lib.check(lib.tif_ipc_copy_async(buf.slice_ptr(), wl.out.data_ptr(), nbytes, copy_stream.cuda_stream), "tif_ipc_copy_async")
+                    free.record(copy_stream)
+            ms, _ = time_steps(torch, dist, world, device, step, steps, warmup)
+            info["note"] = "local result, then cudaMemcpyAsync into rank 0's peer-mapped buffer on a side stream (overlaps the next step's resampling)"
+        # the collected field on rank 0 must equal what every rank computed locally
+        torch.cuda.synchronize()
+        dist.barrier()
+        wl.step(True)
+        torch.cuda.synchronize()
+        mine = wl.out.clone()
+        if args.gather_mode == "fused":
+            wl.out_target = buf.slice_ptr()
+            wl.step(True)
+            wl.out_target = wl.out
+        else:
+            pkg._lib.check(lib.tif_ipc_copy_async(buf.slice_ptr(), mine.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream), "tif_ipc_copy_async")
+        torch.cuda.synchronize()
+        dist.barrier()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            full = buf.tensor()
+            info["matches_nccl_gather"] = bool(all(torch.equal(full[r * B:(r + 1) * B], parts[r]) for r in range(world)))
+            del full
+        del parts, mine
+        buf.close()
+    value = world * B / (ms * 1e-3)
+    ingress = total_bytes / (ms * 1e-3) / 1e9
+    info.update({"value": value, "unit": UNIT, "ms_per_step": ms, "ms_per_step_without": ms_plain,
+                 "rank0_ingress_gbs": ingress, "nvlink_peak_gbs_per_direction": 900.0, "nvlink_measured_peer_copy_gbs": 770.0,
+                 "ingress_frac_of_measured": ingress / 770.0,
+                 "limiter": "NVLink ingress of rank 0: %.2f GB per step / 770 GB/s measured peer copy = %.2f ms per step at best" %
+                            (total_bytes / 1e9, total_bytes / 770e9 * 1e3)})
+    return info
+
+
+def run_e2e(args, torch, dist, pkg, wl, world, rank, device, reference_out):
+    B = wl.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    probe = pcie_probe(torch, device)
+    if world > 1:       # all ranks probed at once: the box's aggregate ceiling
+        t = torch.tensor([probe["both_gbs_each_direction"]], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        probe["all_ranks_both_gbs_each_direction"] = float(t.item())
+    pipe = pkg.pipeline.HostPipeline(PAD, args.height, TANGENT_W, args.blend, True, chunk=2, slots=4, device=device)
+    h_src, h_tar, h_flows = (t.cpu().pin_memory() for t in (wl.src, wl.tar, wl.flows))
+    h_out = torch.empty(wl.out.shape, dtype=wl.out.dtype).pin_memory()
+    h_ts = torch.empty(pipe.tangent_out_shape(B), dtype=torch.uint8).pin_memory()
+    h_tt = torch.empty(pipe.tangent_out_shape(B), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        pipe.run(h_src, h_tar, h_flows, h_out, h_ts, h_tt)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run(h_src, h_tar, h_flows, h_out, h_ts, h_tt)
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ok = bool(torch.equal(h_out.to(device), reference_out))
+    h2d, d2h = B * pipe.h2d_bytes_per_pair(), B * pipe.d2h_bytes_per_pair()
+    per_step = dt / e2e_steps
+    ceiling = max(h2d, d2h) / (probe["both_gbs_each_direction"] * 1e9)
+    return {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": e2e_steps, "api": pipe.describe(), "matches_device_path": ok, "pcie_probe": probe,
+            "h2d_gbs": h2d / per_step / 1e9, "d2h_gbs": d2h / per_step / 1e9, "pcie_frac": ceiling / per_step,
+            "pcie_note": "pcie_frac = time the larger direction needs at this rank's measured concurrent-copy rate / measured time per step"}
 
 
 def main():

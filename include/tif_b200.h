@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TIF_ABI_VERSION 4
+#define TIF_ABI_VERSION 5
 #define TIF_MAX_FACES 128      /* 7-bit face id in a membership entry */
 #define TIF_MAX_TANGENT_DIM 2048 /* 11-bit tangent row / column in a membership entry */
 
@@ -163,6 +163,17 @@ int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp /*[B,H,W,3]*/, int ba
                    uint8_t* tangent_rgba /*[B,P,4]*/, void* stream);
 
 /*
+ * Compact forms of a tangent stack for the trip back to the host (n_pixels = B * P, a multiple of 4):
+ * TIF_PACK_RGB drops the alpha channel, which is a constant 255 for full_face_image (projection_icosahedron.py:244);
+ * TIF_PACK_GRAY_CV is what the per-face estimator computes first, cv2.cvtColor(img[:, :, :3], cv2.COLOR_BGR2GRAY)
+ * (flow_estimate.py:31-47), bit for bit: (3735 c0 + 19235 c1 + 9798 c2 + 2^14) >> 15.
+ */
+#define TIF_PACK_RGB 0
+#define TIF_PACK_GRAY_CV 1
+int tif_pack_tangent_u8(const uint8_t* tangent_rgba /*[n_pixels,4]*/, int64_t n_pixels, int format,
+                        uint8_t* out /*[n_pixels,3] or [n_pixels]*/, void* stream);
+
+/*
  * ico2erp_flow (projection_icosahedron.py:251-398): tangent flows -> ERP flow.  Nearest-pixel
  * gather, end-point lift through pixel2gnomonic / reverse_gnomonic_projection / sph2erp, seam fix
  * (wrap_around), face weights (blend), weighted mean over faces in index order, and the final
@@ -188,11 +199,17 @@ int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent_flow, cons
  * flow_warp.warp_backward (flow_warp.py:54-88): out(y,x) = bilinear(img, (y+v, x+u)).
  * flow_dtype selects float32 / float64 flow ([B,H,W,2]); float64 reproduces the reference's
  * coordinates exactly.  uint8 images are rounded half-up like scipy; float images stay float.
+ * uint8 RGB images with the 'wrap' boundary, W % 4 == 0 and 4-byte aligned buffers take a fast kernel (integer
+ * coordinates + 23-bit fractions, aligned-word taps, 2^24 fixed-point blend, float64 only where the rounding is
+ * undecided); its output is identical to the general float64 kernel's.
  */
 int tif_warp_backward_u8(const uint8_t* image /*[B,H,W,C]*/, const void* flow, int flow_dtype,
                          int batch, int h, int w, int channels, int mode, uint8_t* out, void* stream);
 int tif_warp_backward_f32(const float* image /*[B,H,W,C]*/, const void* flow, int flow_dtype,
                           int batch, int h, int w, int channels, int mode, float* out, void* stream);
+/* float64 images stay float64 (scipy's own accumulation order), so the result is the reference's bit for bit */
+int tif_warp_backward_f64(const double* image /*[B,H,W,C]*/, const void* flow, int flow_dtype,
+                          int batch, int h, int w, int channels, int mode, double* out, void* stream);
 
 /* flow_warp.flow_warp_meshgrid (flow_warp.py:15-51): end points with a single wrap; out [B,2,H,W]. */
 int tif_flow_warp_meshgrid(const void* flow_u /*[B,H,W]*/, const void* flow_v /*[B,H,W]*/, int dtype,
@@ -252,6 +269,22 @@ int64_t tif_blend_weight_points_scratch_bytes(int64_t n);
 int tif_blend_weight_points(const void* image_src, const void* image_tar, int image_dtype, int h, int w, int channels,
                             const double* x_src, const double* y_src, const double* x_tar, const double* y_tar,
                             int64_t n, int weight_kind, double* weights /*[n]*/, void* scratch, void* stream);
+
+/*
+ * Collecting the stitched flows of several GPUs on one of them (the only exchange of the sharded path, SURVEY.md 8e;
+ * the reference has no counterpart, it loops its pairs serially).  One process per GPU: the collecting process
+ * allocates the [n_items, H, W, 2] buffer with tif_ipc_alloc and exports its CUDA IPC handle (TIF_IPC_HANDLE_BYTES
+ * bytes, sent through any host channel); the others map it with tif_ipc_open and pass the device address of their own
+ * slice as `erp_flow` to tif_ico2erp_flow_f32, whose blend epilogue then stores across NVLink / NVSwitch straight into
+ * the collecting GPU's memory.  tif_ipc_copy_async moves a finished local result instead (cudaMemcpyAsync on `stream`).
+ */
+#define TIF_IPC_HANDLE_BYTES 64
+int tif_ipc_alloc(void** dev_ptr, int64_t bytes);
+int tif_ipc_free(void* dev_ptr);
+int tif_ipc_export(void* dev_ptr, unsigned char* handle /*host, TIF_IPC_HANDLE_BYTES*/);
+int tif_ipc_open(const unsigned char* handle /*host*/, void** dev_ptr);
+int tif_ipc_close(void* dev_ptr);
+int tif_ipc_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
 /* flow_postproc.erp_of_wraparound (flow_postproc.py:17-44), in place on [B,H,W,2]. */
 int tif_erp_of_wraparound(void* erp_flow, int dtype, int batch, int h, int w, double u_threshold, void* stream);

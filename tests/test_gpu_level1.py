@@ -23,8 +23,9 @@ def level1_flows(wt, heights, seed=0):
     return flows
 
 
-def test_level1_against_oracle(pkg):
-    erp_h, wt = 256, 64
+@pytest.mark.parametrize("erp_h,wt", [(256, 64), (1024, 480)])
+def test_level1_against_oracle(pkg, erp_h, wt):
+    """GPU == oracle for the 80-face subdivision, at a small size and at 2048x1024 with the default 480-pixel faces."""
     src, tar = synth.synth_images(erp_h, 4)
     plan = pkg._geometry.get_plan(PAD, erp_h, wt, level=1)
     assert plan.n_faces == 80 and len(set(plan.face_heights)) == 4

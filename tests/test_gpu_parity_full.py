@@ -21,7 +21,10 @@ def sha(a):
 
 
 def inputs(g):
-    src, tar = synth.synth_images(int(g["erp_h"]), int(g["seed"]), bool(g["smooth"]))
+    if "image_src" in g.files:          # BASELINE.json config #1: the reference's shipped demo pair, decoded
+        src, tar = g["image_src"], g["image_tar"]
+    else:
+        src, tar = synth.synth_images(int(g["erp_h"]), int(g["seed"]), bool(g["smooth"]))
     flows = synth.synth_flows(int(g["tangent_w"]), 20, float(g["u_offset"]))
     return src, tar, flows
 
@@ -50,16 +53,21 @@ def membership_hashes(plan):
     return out, accepted
 
 
-@pytest.mark.parametrize("name", ["summary_h1024_noise", "summary_h640_smooth_seam", "summary_h1920_noise"])
+@pytest.mark.parametrize("name", ["summary_h1024_noise", "summary_h640_smooth_seam", "summary_h1920_noise",
+                                  "summary_h2048_smooth", "summary_demo_pair_h640"])
 def test_reference_summaries(pkg, golden, name):
-    """Outputs of the live reference (hashes, strided samples, pole rows) at 1280x640, 2048x1024 and 3840x1920."""
+    """Outputs of the live reference (hashes, strided samples, pole rows) at 1280x640 (synthetic and the shipped demo
+    pair = BASELINE.json config #1), 2048x1024, 3840x1920 and 4096x2048 (the largest single-GPU shape)."""
     g = golden(name)
     src, tar, flows = inputs(g)
+    assert sha(src) == str(g["sha_src"]) and sha(tar) == str(g["sha_tar"]) and sha(np.stack(flows)) == str(g["sha_flows"])
     erp_h = int(g["erp_h"])
     pico, fwarp = pkg.projection_icosahedron, pkg.flow_warp
     full = np.stack(pico.erp2ico_image(src, WT, PAD, True)).astype(np.uint8)
     assert sha(full) == str(g["ico_full_sha"])                      # every uint8 sample identical
     assert bool((full[..., 3] == 255).all())
+    if "ico_tar_sha" in g.files:
+        assert sha(np.stack(pico.erp2ico_image(tar, WT, PAD, True)).astype(np.uint8)) == str(g["ico_tar_sha"])
     plan = pkg._geometry.get_plan(PAD, erp_h, WT)
     # the sha above was produced by the shared-memory staged resampler and its direct-gather fallback together (these
     # ERP heights are multiples of 8, so the rows are 16-byte multiples): most of the patches are staged
@@ -72,16 +80,32 @@ def test_reference_summaries(pkg, golden, name):
         tag = blend[:2]
         f = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
         err = np.abs(f.reshape(-1, 2)[::stride] - g["flow_%s_samples" % tag]).max(axis=1)
-        # strided samples: allow the oracle-identified discontinuity pixels (checked in full in the oracle tests)
-        assert (err > FLOW_TOL).mean() < 2e-4, (blend, err.max())
+        # the fixture flags the samples where the reference's own map is discontinuous (an end point on the +-pi seam
+        # or on the hard edge of the mode='constant' sampling); every other sample must be within tolerance
+        excuse = g["flow_%s_excuse" % tag]
+        assert ((err > FLOW_TOL) & ~excuse).sum() == 0, (blend, err.max())
+        assert excuse.mean() < 2e-3
         assert np.median(err) < 2e-5
-    # warp_backward with the reference's own float64 flow is exercised in test_config2_against_oracle
+        # the two pole rows (antipodal quirk acceptances), in full
+        poles = np.stack((f[0], f[erp_h - 1]))
+        perr = np.abs(poles - g["flow_%s_poles" % tag]).max(axis=2)
+        assert (perr > FLOW_TOL).mean() < 5e-3, (blend, perr.max())
+    # flow_warp evaluation: the GPU's float64 result of the normwarp stitch, warped by the fast uint8 kernel
+    if "warp_sha" in g.files:
+        w = fwarp.warp_backward(tar, f)
+        ref = g["warp_samples"]
+        got = w.reshape(-1)[::int(g["warp_stride"])]
+        # the flow differs from the reference's by <= 1e-3 px, so single grey levels may flip: compare loosely here,
+        # exactly (same flow on both sides) in test_config2_against_oracle / test_warp_fast_kernel
+        assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= (255 if not bool(g["smooth"]) else 2)
+        assert (got != ref).mean() < 0.02
 
 
-def test_config2_against_oracle(pkg):
-    """BASELINE.json config #2: synthetic 2048x1024 pair, 20 faces, padding 0.3, both blends, GPU vs oracle in full."""
-    erp_h = 1024
-    src, tar, flows = synth.synth(erp_h, 0, WT)
+@pytest.mark.parametrize("erp_h", [1024, 1920])
+def test_config2_against_oracle(pkg, erp_h):
+    """BASELINE.json config #2 (synthetic 2048x1024 pair) and #3 (3840x1920): 20 faces, padding 0.3, both blends, GPU vs
+    oracle over the FULL field, with the oracle-computed excuse masks only."""
+    src, tar, flows = synth.synth(erp_h, 0 if erp_h == 1024 else 1, WT)
     pico, fwarp = pkg.projection_icosahedron, pkg.flow_warp
     want_faces = tif_oracle.erp2ico_image(tar, WT, PAD, True)
     got_faces = pico.erp2ico_image(tar, WT, PAD, True)
@@ -95,113 +119,84 @@ def test_config2_against_oracle(pkg):
         err = np.abs(got - want).max(axis=2)
         assert ((err > FLOW_TOL) & ~excuse).sum() == 0, (blend, err.max())
         assert np.median(err) < 5e-6
-    # flow_warp evaluation on the oracle's float64 flow: uint8 identical
+    # flow_warp evaluation on the oracle's float64 flow, and on its float32 rounding (the fast kernel's integer
+    # coordinate path): uint8 identical
     assert np.array_equal(fwarp.warp_backward(tar, want), tif_oracle.warp_backward(tar, want))
+    want32 = want.astype(np.float32)
+    assert np.array_equal(fwarp.warp_backward(tar, want32), tif_oracle.warp_backward(tar, want32))
 
 
-def test_config3_warp_at_4k(pkg):
-    """BASELINE.json config #3: 3840x1920 with the flow_warp evaluation: exact uint8 warp for a float64 flow."""
-    erp_h = 1920
-    rng = np.random.default_rng(3)
-    tar = rng.integers(0, 256, (erp_h, 2 * erp_h, 3), dtype=np.uint8)
-    flow = rng.normal(0.0, 30.0, (erp_h, 2 * erp_h, 2))
-    flow[::7, ::5, 0] += 4000.0            # several periods of scipy's n-1 wrap
-    flow[::11, ::3, 1] -= 2500.0
-    assert np.array_equal(pkg.flow_warp.warp_backward(tar, flow), tif_oracle.warp_backward(tar, flow))
+def test_warp_fast_kernel(pkg):
+    """The uint8 RGB warp kernel (integer coordinates + 23-bit fractions, fixed-point blend) against the oracle's
+    float64 scipy restatement: negative / tiny / huge / exactly-integer flows, the period n-1 wrap on both axes,
+    float32 and float64 flows, a width that is not a multiple of 4 (general kernel) -- uint8 identical everywhere."""
+    rng = np.random.default_rng(11)
+    for h, w in ((96, 192), (50, 100), (33, 70)):          # w % 4 == 0: fast kernel; 70: general kernel
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        flow = rng.normal(0.0, 6.0, (h, w, 2)).astype(np.float32)
+        flow[::3, ::5] = np.round(flow[::3, ::5])                     # exactly integer end points
+        flow[1::7, 2::3, 0] = -np.float32(1e-20)                       # tiny negative: floor = -1, fraction rounds to 1
+        flow[2::7, 1::3, 1] = np.float32(1e-12)
+        flow[3::11, ::2, 0] += np.float32(3.0e6)                       # beyond the fast path's range
+        flow[4::11, ::2, 1] -= np.float32(7 * (h - 1) + 0.25)          # several wrap periods
+        flow[5::13, 3::4, 0] = np.float32(w - 1) - np.arange(w, dtype=np.float32)[3::4][None, :]      # lands on x = w - 1
+        flow[0, :, 1] = -0.5                                           # leaves the image upwards
+        flow[:, w - 1, 0] = 0.75                                       # ... and to the right
+        for fl in (flow, flow.astype(np.float64), flow.astype(np.float64) * 1.0000001):
+            got = pkg.flow_warp.warp_backward(img, fl)
+            want = tif_oracle.warp_backward(img, fl)
+            assert got.dtype == np.uint8 and np.array_equal(got, want), (h, w, fl.dtype, int((got != want).sum()))
+    # float64 and float32 images keep their dtype and are exact too
+    imgf = rng.uniform(0, 255, (40, 80, 3))
+    fl = rng.normal(0.0, 5.0, (40, 80, 2))
+    assert np.array_equal(pkg.flow_warp.warp_backward(imgf, fl), tif_oracle.warp_backward(imgf, fl))
+    got32 = pkg.flow_warp.warp_backward(imgf.astype(np.float32), fl)
+    assert got32.dtype == np.float32 and np.array_equal(got32, tif_oracle.warp_backward(imgf.astype(np.float32), fl))
 
 
-def test_batch_consistency_and_determinism(pkg):
-    """Size-independent properties: a batch equals its items, repeated runs are bitwise identical (the normwarp
-    face means are integer sums), a constant image resamples to itself, zero flow warps to the identity."""
-    erp_h, wt = 512, 240
-    dev = torch.device("cuda", 0)
-    pico, fwarp, fpost = pkg.projection_icosahedron, pkg.flow_warp, pkg.flow_postproc
-    batch = 5                        # not a multiple of the kernels' batch chunk (4)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(5)
-    src = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
-    tar = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
-    base = torch.from_numpy(np.stack(synth.synth_flows(wt))).to(dev)
-    flows = torch.stack([base + 0.3 * i for i in range(batch)])
-    tan = pico.erp2ico_image(src, wt, PAD)
-    assert tan.shape == (batch, 20, synth.tangent_height(wt), wt, 4) and tan.dtype == torch.uint8
-    for i in range(batch):
-        assert torch.equal(tan[i:i + 1], pico.erp2ico_image(src[i:i + 1], wt, PAD))
-    for blend in ("straightforward", "normwarp"):
-        out = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
-        assert out.shape == (batch, erp_h, 2 * erp_h, 2) and out.dtype == torch.float32
-        assert torch.equal(out, pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend))
-        for i in (0, batch - 1):
-            one = pico.ico2erp_flow(flows[i:i + 1], erp_h, PAD, src[i:i + 1], tar[i:i + 1], True, blend)
-            assert torch.equal(out[i:i + 1], one)
-        # idempotence of the final wrap: already applied by the stitch
-        again = fpost.erp_of_wraparound(out.clone())
-        assert torch.equal(again, out)
-    const = torch.full((1, erp_h, 2 * erp_h, 3), 77, dtype=torch.uint8, device=dev)
-    tc = pico.erp2ico_image(const, wt, PAD)
-    assert bool((tc[..., :3] == 77).all()) and bool((tc[..., 3] == 255).all())
-    zero = torch.zeros((batch, erp_h, 2 * erp_h, 2), dtype=torch.float32, device=dev)
-    assert torch.equal(fwarp.warp_backward(tar, zero), tar)
-    mg = fwarp.flow_warp_meshgrid(zero[..., 0].contiguous(), zero[..., 1].contiguous())
-    assert torch.equal(mg[0, 0, 3], torch.arange(2 * erp_h, device=dev, dtype=torch.float32))
-
-
-def test_host_pipeline_matches_device_path(pkg):
-    erp_h, wt, batch = 256, 120, 6
-    dev = torch.device("cuda", 0)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(9)
-    src = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
-    tar = torch.randint(0, 256, (batch, erp_h, 2 * erp_h, 3), dtype=torch.uint8, device=dev, generator=gen)
-    flows5 = torch.stack([torch.from_numpy(np.stack(synth.synth_flows(wt))).to(dev) * (1 + 0.1 * i) for i in range(batch)])
+def test_demo_pair_with_dis_flows(pkg, golden):
+    """BASELINE.json config #1 end to end on the GPU box: the shipped demo pair (decoded copy in the fixture), GPU
+    tangent images -> OpenCV DIS per face (the reference's fixed estimator stage, flow_estimate.py:18-59) -> GPU
+    stitch, against the oracle fed the same DIS flows, over the full field."""
+    cv2 = pytest.importorskip("cv2")
+    g = golden("summary_demo_pair_h640")
+    src, tar = g["image_src"], g["image_tar"]
+    erp_h = int(g["erp_h"])
     pico = pkg.projection_icosahedron
-    want = pico.ico2erp_flow(flows5, erp_h, PAD, src, tar, True, "normwarp")
-    want_tan = pico.erp2ico_image(src, wt, PAD)
-    pipe = pkg.pipeline.HostPipeline(PAD, erp_h, wt, "normwarp", True, chunk=4, slots=2, device=dev)
-    p = pipe.plan.tangent_pixels
-    h_out = torch.empty((batch, erp_h, 2 * erp_h, 2), dtype=torch.float32).pin_memory()
-    h_ts = torch.empty((batch, p, 4), dtype=torch.uint8).pin_memory()
-    h_tt = torch.empty((batch, p, 4), dtype=torch.uint8).pin_memory()
-    pipe.run(src.cpu().pin_memory(), tar.cpu().pin_memory(), flows5.reshape(batch, p, 2).cpu().pin_memory(), h_out, h_ts, h_tt)
-    assert torch.equal(h_out, want.cpu())
-    assert torch.equal(h_ts, want_tan.reshape(batch, p, 4).cpu())
+    faces_s = pico.erp2ico_image(src, WT, PAD, True)
+    faces_t = pico.erp2ico_image(tar, WT, PAD, True)
+    dis = cv2.DISOpticalFlow_create(cv2.DISOPTICAL_FLOW_PRESET_MEDIUM)
+    flows = []
+    for a, b in zip(faces_s, faces_t):
+        ga = cv2.cvtColor(a[:, :, :3].astype(np.uint8), cv2.COLOR_BGR2GRAY)
+        gb = cv2.cvtColor(b[:, :, :3].astype(np.uint8), cv2.COLOR_BGR2GRAY)
+        flows.append(dis.calc(ga, gb, None).astype(np.float32))
+    for blend in ("straightforward", "normwarp"):
+        want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend, return_debug=True)
+        got = pico.ico2erp_flow(flows, erp_h, PAD, src, tar, True, blend)
+        excuse = dbg["seam_dist"] < 1e-5
+        if blend == "normwarp":
+            excuse |= dbg["edge_dist"] < 1e-3
+        err = np.abs(got - want).max(axis=2)
+        assert ((err > FLOW_TOL) & ~excuse).sum() == 0, (blend, err.max())
+        assert excuse.mean() < 5e-3
 
 
-def test_direct_c_abi_calls(pkg):
-    """Through the C ABI with raw pointers (torch only owns the memory): argument validation and one resample."""
-    lib = pkg._lib.load()
-    erp_h, wt = 64, 32
-    plan = pkg._geometry.get_plan(PAD, erp_h, wt)
-    info = pkg._lib.TifPlanInfo()
-    assert lib.tif_plan_info(plan.handle, ctypes.byref(info)) == 0
-    assert (info.n_faces, info.erp_h, info.erp_w, info.tangent_w) == (20, erp_h, 2 * erp_h, wt)
-    assert info.tangent_pixels == 20 * 28 * 32 and info.max_faces_per_pixel >= 5 and info.device_bytes > 0
-    # 64 x 128 x 3: rows of 384 bytes are 16-byte multiples, so the shared-memory staged resampler is in use
-    assert info.stage1_patches == 2 * (20 * 28 // 8) and 0 < info.stage1_staged_patches <= info.stage1_patches       # 16 x 8 patches
-    direct = pkg._geometry.get_plan(PAD, 90, wt)          # rows of 540 bytes: every patch keeps the direct gathers
-    assert direct.stage1_staged_patches == 0 and direct.stage1_patches > 0
-    src, tar = synth.synth_images(erp_h, 3)
-    erp = torch.from_numpy(src).cuda()[None].contiguous()
-    out = torch.zeros((1, info.tangent_pixels, 4), dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    assert lib.tif_erp2ico_u8(plan.handle, erp.data_ptr(), 1, 1, out.data_ptr(), stream) == 0
+def test_plan_memory_is_returned(pkg):
+    """clear_plans() drops the op registry's references too: the plan's device tables are freed."""
+    import gc
+    geo = pkg._geometry
+    erp = torch.zeros((1, 512, 1024, 3), dtype=torch.uint8, device="cuda")
+    out = pkg.projection_icosahedron.erp2ico_image(erp, 240, PAD)          # registers the plan with the custom ops
+    plan_bytes = geo.get_plan(PAD, 512, 240).device_bytes
+    assert plan_bytes > 50e6
+    del out, erp
+    gc.collect()
     torch.cuda.synchronize()
-    want = np.stack(tif_oracle.erp2ico_image(src, wt, PAD, True)).astype(np.uint8)
-    assert np.array_equal(out.cpu().numpy().reshape(want.shape), want)
-    # a caller's buffer need not be aligned: at byte offsets 1, 2, 4 and 8 the library leaves the staged resampler
-    # (16-byte row copies) for the direct gathers, at odd offsets also the aligned word loads -- same bytes out
-    for shift in (1, 2, 4, 8):
-        raw = torch.zeros(erp.numel() + 64, dtype=torch.uint8, device="cuda")
-        raw[shift:shift + erp.numel()] = erp.reshape(-1)
-        out2 = torch.zeros_like(out)
-        assert lib.tif_erp2ico_u8(plan.handle, raw.data_ptr() + shift, 1, 1, out2.data_ptr(), stream) == 0
-        torch.cuda.synchronize()
-        assert torch.equal(out2, out), shift
-    # invalid arguments are rejected with a status, not a crash
-    assert lib.tif_erp2ico_u8(None, erp.data_ptr(), 1, 1, out.data_ptr(), stream) == -1
-    assert lib.tif_erp2ico_u8(plan.handle, erp.data_ptr(), 0, 1, out.data_ptr(), stream) == -1
-    assert lib.tif_ico2erp_flow_f32(plan.handle, out.data_ptr(), None, None, 1, 7, 1, out.data_ptr(), None, stream) == -1
-    assert lib.tif_ico2erp_flow_f32(plan.handle, out.data_ptr(), None, None, 1, 1, 1, out.data_ptr(), None, stream) == -1
-    n_sf, n_nw = lib.tif_ico2erp_scratch_bytes(plan.handle, 2, 0), lib.tif_ico2erp_scratch_bytes(plan.handle, 2, 1)
-    assert n_sf >= 2 * info.tangent_pixels * 8 and n_nw >= 2 * info.tangent_pixels * 16
-    assert lib.tif_warp_backward_u8(erp.data_ptr(), out.data_ptr(), 5, 1, erp_h, 2 * erp_h, 3, 0, out.data_ptr(), stream) == -1
+    torch.cuda.empty_cache()
+    held, _ = torch.cuda.mem_get_info()
+    geo.clear_plans()                 # every cached plan goes, this one included
+    gc.collect()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 - held > 0.8 * plan_bytes, (held, free1, plan_bytes)

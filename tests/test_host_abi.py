@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layout_and_status_strings(pkg):
     lib = pkg._lib.load()
-    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 4
+    assert lib.tif_abi_version() == pkg._lib.ABI_VERSION == 5
     sizes = [ctypes.c_int32() for _ in range(3)]
     assert lib.tif_struct_sizes(*[ctypes.byref(s) for s in sizes]) == 0
     assert [s.value for s in sizes] == [ctypes.sizeof(pkg._lib.TifFace), ctypes.sizeof(pkg._lib.TifPlanTables),
@@ -133,3 +133,33 @@ def test_level1_face_table_matches_oracle(pkg):
     assert hg.gnom_y.shape == (34980,) and hg.tangent_pixels == 34980 * 480
     hg0 = geo.HostGeometry(0.3, 64, 32, level=0)
     assert hg0.n_faces == 20 and set(hg0.face_heights) == {28}
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/flow_estimate.py"), reason="/root/reference not mounted (GPU box)")
+def test_install_dropin_binds_the_reference_caller():
+    """After install_dropin() the reference's own pipeline module (src/flow_estimate.py:1-8, imported unmodified
+    from /root/reference) resolves its bare-name imports to this package: PanoOpticalFlow.estimate would run the
+    B200 path.  Run in a subprocess so that the bare module names do not leak into the test process."""
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import __graft_entry__ as entry
+entry.build()
+pkg = entry.load_package()
+pkg.install_dropin()
+sys.path.insert(0, %r)                       # colorama / skimage / matplotlib stubs (not installed on this image)
+sys.path.append("/root/reference/src")       # appended: the product modules win for every name they provide
+import flow_estimate
+assert flow_estimate.proj_ico is pkg.projection_icosahedron, flow_estimate.proj_ico
+assert flow_estimate.proj_cm is pkg.projection_cubemap
+assert flow_estimate.flow_warp is pkg.flow_warp and flow_estimate.projection is pkg.projection
+assert flow_estimate.flow_postproc is pkg.flow_postproc
+assert flow_estimate.spherical_coordinates is pkg.spherical_coordinates
+est = flow_estimate.PanoOpticalFlow()
+assert est.face_blending_method_ico == "normwarp"
+for name in ("erp2ico_image", "ico2erp_flow", "get_icosahedron_parameters"):
+    assert getattr(flow_estimate.proj_ico, name).__module__.startswith("tangentflow_b200"), name
+print("dropin ok")
+""" % (ROOT, os.path.join(ROOT, "oracle", "_stubs"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "dropin ok" in res.stdout, res.stdout + res.stderr
