@@ -13,7 +13,7 @@ from . import polygon, spherical_coordinates, gnomonic_projection  # noqa: F401
 __all__ = ["projection_icosahedron", "flow_warp", "flow_postproc", "gnomonic_projection",
            "spherical_coordinates", "polygon", "install_dropin", "sharding"]
 
-_LAZY = ("projection_icosahedron", "projection_cubemap", "projection", "flow_warp", "flow_postproc", "flow_evaluate", "flow_io",
+_LAZY = ("projection_icosahedron", "projection_cubemap", "projection", "flow_warp", "flow_postproc", "flow_evaluate", "flow_io", "flow_vis",
          "_geometry", "_ops", "sharding", "pipeline")
 
 
@@ -28,6 +28,6 @@ def __getattr__(name):
 
 def install_dropin():
     """Make `import projection_icosahedron` (etc.) resolve to this package, as the reference's scripts expect."""
-    for name in ("projection_icosahedron", "projection_cubemap", "projection", "flow_evaluate", "flow_io", "flow_warp", "flow_postproc", "gnomonic_projection",
+    for name in ("projection_icosahedron", "projection_cubemap", "projection", "flow_evaluate", "flow_io", "flow_vis", "flow_warp", "flow_postproc", "gnomonic_projection",
                  "spherical_coordinates", "polygon"):
         sys.modules[name] = __getattr__(name) if name in _LAZY else globals()[name]

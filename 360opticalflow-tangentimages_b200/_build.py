@@ -23,6 +23,7 @@ UNITS = {
     "tif_warp.cu": [],
     "tif_rotate.cu": [],
     "tif_metrics.cu": [],
+    "tif_vis.cu": ["-fmad=false"],       # numpy evaluates u*u + v*v and the wheel interpolation without contraction
 }
 
 

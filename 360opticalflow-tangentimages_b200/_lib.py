@@ -94,6 +94,8 @@ SYMBOLS = {
     "tif_flow_error_mats": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "tif_reduce_f64_scratch_bytes": (C.c_int64, [C.c_int]),
     "tif_reduce_f64": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP]),
+    "tif_flow_rad_max": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, _VP, _VP]),
+    "tif_flow_to_color_u8": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double, _VP, C.c_int, _VP, _VP]),
     "tif_ipc_alloc": (C.c_int, [C.POINTER(_VP), C.c_int64]),
     "tif_ipc_free": (C.c_int, [_VP]),
     "tif_ipc_export": (C.c_int, [_VP, C.c_char_p]),

@@ -134,8 +134,11 @@ __device__ __forceinline__ void warp_axis(FlowT d, int pos, int n, int& i0, uint
     q = (uint32_t)((x - x0) * 8388608.0 + 0.5);
 }
 
+#ifndef TIF_WARP_MIN_BLOCKS
+#define TIF_WARP_MIN_BLOCKS 8
+#endif
 template <typename FlowT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TIF_WARP_MIN_BLOCKS)
 k_warp_rgb_fast(const uint8_t* __restrict__ image, const FlowT* __restrict__ flow, uint8_t* __restrict__ out, int batch,
                 int h, int w) {
     // warp -> 32 x 4 pixel tile, lane -> 4 adjacent pixels of one row

@@ -271,6 +271,18 @@ int tif_blend_weight_points(const void* image_src, const void* image_tar, int im
                             int64_t n, int weight_kind, double* weights /*[n]*/, void* scratch, void* stream);
 
 /*
+ * Colour-wheel rendering of a flow field (row f4): flow_vis.flow_to_color / flow_uv_to_colors (flow_vis.py:77-201).
+ * tif_flow_rad_max: max over the pixels of sqrt(u^2 + v^2) after the optional clip (`out`: one double on the device);
+ * tif_flow_to_color_u8: clip, divide by `norm` (rad_max + 1e-5; 0 = already normalised), angle -> two rows of the
+ * 55 x 3 wheel (`wheel`, device, from flow_vis.make_colorwheel), interpolate, floor(255 c); float64 arithmetic.
+ */
+int tif_flow_rad_max(const void* flow /*[n_pixels,2]*/, int dtype, int64_t n_pixels, int use_clip, double clip_lo,
+                     double clip_hi, double* out, void* stream);
+int tif_flow_to_color_u8(const void* flow /*[n_pixels,2]*/, int dtype, int64_t n_pixels, int use_clip, double clip_lo,
+                         double clip_hi, double norm, const double* wheel /*[55,3]*/, int convert_to_bgr,
+                         uint8_t* out /*[n_pixels,3]*/, void* stream);
+
+/*
  * Collecting the stitched flows of several GPUs on one of them (the only exchange of the sharded path, SURVEY.md 8e;
  * the reference has no counterpart, it loops its pairs serially).  One process per GPU: the collecting process
  * allocates the [n_items, H, W, 2] buffer with tif_ipc_alloc and exports its CUDA IPC handle (TIF_IPC_HANDLE_BYTES

@@ -1031,3 +1031,68 @@ def opticalflow_metric(flo_gt, flo_eva, flo_mask=None):
         zero(flo_mask)
         out.append(np.sqrt(np.sum(np.square(e)) / np.sum(ok)))
     return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# colour-wheel visualisation (row f4) -- flow_vis.py:19-201, image_evaluate.py:8-32
+# ------------------------------------------------------------------------------------------------
+
+def make_colorwheel():
+    """flow_vis.py:19-66: the 55 x 3 Middlebury wheel."""
+    ry, yg, gc, cb, bm, mr = 15, 6, 4, 11, 13, 6
+    wheel = np.zeros((ry + yg + gc + cb + bm + mr, 3))
+    col = 0
+    wheel[0:ry, 0] = 255
+    wheel[0:ry, 1] = np.floor(255 * np.arange(0, ry) / ry)
+    col += ry
+    wheel[col:col + yg, 0] = 255 - np.floor(255 * np.arange(0, yg) / yg)
+    wheel[col:col + yg, 1] = 255
+    col += yg
+    wheel[col:col + gc, 1] = 255
+    wheel[col:col + gc, 2] = np.floor(255 * np.arange(0, gc) / gc)
+    col += gc
+    wheel[col:col + cb, 1] = 255 - np.floor(255 * np.arange(cb) / cb)
+    wheel[col:col + cb, 2] = 255
+    col += cb
+    wheel[col:col + bm, 2] = 255
+    wheel[col:col + bm, 0] = np.floor(255 * np.arange(0, bm) / bm)
+    col += bm
+    wheel[col:col + mr, 2] = 255 - np.floor(255 * np.arange(mr) / mr)
+    wheel[col:col + mr, 0] = 255
+    return wheel
+
+
+def flow_uv_to_colors(u, v, convert_to_bgr=False):
+    """flow_vis.py:77-121."""
+    image = np.zeros((u.shape[0], u.shape[1], 3), np.uint8)
+    wheel = make_colorwheel()
+    rows = wheel.shape[0]
+    rad = np.sqrt(np.square(u) + np.square(v))
+    angle = np.arctan2(-v, -u) / np.pi
+    idx = (angle + 1) / 2 * (rows - 1)
+    k0 = np.floor(idx).astype(np.int32)
+    k1 = k0 + 1
+    k1[k1 == rows] = 0
+    ratio = idx - k0
+    for i in range(3):
+        c0 = wheel[:, i][k0] / 255.0
+        c1 = wheel[:, i][k1] / 255.0
+        color = (1 - ratio) * c0 + ratio * c1
+        inside = rad <= 1
+        color[inside] = 1 - rad[inside] * (1 - color[inside])
+        color[~inside] = color[~inside] * 0.75
+        image[:, :, 2 - i if convert_to_bgr else i] = np.floor(255 * color)
+    return image
+
+
+def flow_to_color(flow_uv, clip_flow=None, convert_to_bgr=False, min_ratio=0.0, max_ratio=1.0):
+    """flow_vis.py:124-163 (without the matplotlib bar)."""
+    if min_ratio != 0 and max_ratio != 1.0:
+        flat = flow_uv.flatten()
+        lo, hi = int(flat.size * min_ratio), int((flat.size - 1) * max_ratio)
+        clip_flow = (np.partition(flat, lo)[lo], np.partition(flat, hi)[hi])
+    if clip_flow is not None:
+        flow_uv = np.clip(flow_uv, clip_flow[0], clip_flow[1])
+    u, v = flow_uv[:, :, 0], flow_uv[:, :, 1]
+    rad_max = np.max(np.sqrt(np.square(u) + np.square(v)))
+    return flow_uv_to_colors(u / (rad_max + 1e-5), v / (rad_max + 1e-5), convert_to_bgr)

@@ -2,7 +2,7 @@
 # usage: scripts/ab_bench.sh "<defs A>" "<defs B>" ...   -- rebuilds with each set of -D knobs and prints kernel times
 for defs in "$@"; do
   TIF_NVCC_DEFS="$defs" python 360opticalflow-tangentimages_b200/_build.py --force > /dev/null
-  TIF_NVCC_DEFS="$defs" python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > /tmp/ab.json 2>/tmp/ab.err || tail -3 /tmp/ab.err
+  TIF_NVCC_DEFS="$defs" python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-extra-configs > /tmp/ab.json 2>/tmp/ab.err || tail -3 /tmp/ab.err
   python - "$defs" <<'PY'
 import json, sys
 d = json.load(open("/tmp/ab.json"))

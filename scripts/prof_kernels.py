@@ -24,7 +24,7 @@ warped = torch.empty_like(tar)
 scratch = torch.empty(int(plan.lib.tif_ico2erp_scratch_bytes(plan.handle, batch, lib.BLEND_NORMWARP)), dtype=torch.uint8, device=dev)
 for _ in range(2):
     ops.erp2ico_out(plan, src, True, tan)                                                    # k_erp2ico_staged
-    ops.ico2erp_flow_out(plan, flows, src, tar, lib.BLEND_NORMWARP, True, out, scratch)        # k_lift_nw, k_nw_face_scale, k_blend_nw
+    ops.ico2erp_flow_out(plan, flows, src, tar, lib.BLEND_NORMWARP, True, out, scratch)        # k_lift_nw, k_err_nw, k_nw_face_scale, k_blend_nw
     ops.ico2erp_flow_out(plan, flows, None, None, lib.BLEND_STRAIGHTFORWARD, True, out, scratch)   # k_lift<0>, k_gather<0>
     ops.ico2erp_flow_out(plan, flows, src, tar, lib.BLEND_NORMWARP, True, out, scratch)
     warped = ops.ops.warp_backward(tar, out, lib.WARP_WRAP)                                  # k_warp_rgb_fast
