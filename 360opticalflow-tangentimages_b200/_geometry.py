@@ -357,6 +357,8 @@ class Plan:
         self.device_bytes = info.device_bytes
         self.stage1_patches = info.stage1_patches
         self.stage1_staged_patches = info.stage1_staged_patches
+        self.stage1_tma_patches = info.stage1_tma_patches
+        self.stage1_tma_box = (info.stage1_tma_box_rows, tuple(info.stage1_tma_box_bytes))
 
     def __del__(self):
         try:

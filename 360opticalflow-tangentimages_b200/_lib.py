@@ -57,6 +57,8 @@ class TifPlanInfo(C.Structure):
         ("tangent_pixels", C.c_int64), ("max_faces_per_pixel", C.c_int32),
         ("accepted_unique", C.c_int64), ("referenced_tangent_pixels", C.c_int64), ("device_bytes", C.c_int64),
         ("stage1_patches", C.c_int64), ("stage1_staged_patches", C.c_int64),
+        ("stage1_tma_patches", C.c_int64), ("stage1_tma_box_rows", C.c_int32), ("stage1_tma_box_bytes", C.c_int32 * 2),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -74,6 +76,7 @@ SYMBOLS = {
     "tif_plan_export_stage1": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "tif_plan_export_stage2": (C.c_int, [_VP, _VP, _VP, _VP]),
     "tif_erp2ico_u8": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "tif_erp2ico_float": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "tif_pack_tangent_u8": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "tif_ico2erp_scratch_bytes": (C.c_int64, [_VP, C.c_int, C.c_int]),
     "tif_ico2erp_flow_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),

@@ -47,6 +47,10 @@
 #ifndef TIF_S1_MAX_STAGE_BYTES
 #define TIF_S1_MAX_STAGE_BYTES 4096
 #endif
+// stage of the TMA form (one box of s1_tma_pitch[1] x s1_tma_rows bytes + 16 bytes of slack)
+#ifndef TIF_S1_TMA_MAX_STAGE_BYTES
+#define TIF_S1_TMA_MAX_STAGE_BYTES 4096u
+#endif
 // a stage size is taken when this share of the patches fits it (else the next larger one is tried)
 #ifndef TIF_S1_STAGED_SHARE
 #define TIF_S1_STAGED_SHARE 0.93
@@ -88,6 +92,10 @@ struct TifPlan {
     int s1_tiles_x, s1_tiles_y;
     int64_t s1_staged_tiles;
     int s1_stage_bytes;            // stage size of k_erp2ico_staged's shared-memory ring
+    // TMA form of the staged resampler (k_erp2ico_tma): every patch whose ERP box fits one of two box shapes
+    // (s1_tma_pitch[c] bytes x s1_tma_rows rows, c = 0 / 1) is fetched by one cp.async.bulk.tensor per image
+    int s1_tma_pitch[2], s1_tma_rows;
+    int64_t s1_tma_tiles;          // patches that fit (0: TMA form unused)
     // stage 2: per ERP pixel
     uint8_t* d_s2_count;           // [H*W] number of accepting faces
     uint32_t* d_s2_entries;        // [K][H*W] packed entries, ascending face order

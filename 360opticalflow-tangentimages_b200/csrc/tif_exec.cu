@@ -9,6 +9,9 @@
 //   k_warp_backward  warp_backward      flow_warp.py:54-88
 //   k_meshgrid       flow_warp_meshgrid flow_warp.py:15-51
 //   k_wraparound     erp_of_wraparound  flow_postproc.py:17-44
+#include <cuda.h>           // CUtensorMap and its enums only: nothing of libcuda is linked
+#include <stdlib.h>
+
 #include "tif_common.cuh"
 
 #ifndef TIF_BATCH_CHUNK
@@ -31,6 +34,24 @@ __device__ __forceinline__ bool tile_pixel(int64_t idx, int width, int rows, int
     row = ty * TIF_TILE_H + lane / TIF_TILE_W;
     col = tx * TIF_TILE_W + lane % TIF_TILE_W;
     return row < rows && col < width;
+}
+
+// the same with the tile shape as a template parameter (TW x TH = 32)
+template <int TW, int TH>
+__device__ __forceinline__ bool tile_pixel_wh(int64_t idx, int width, int rows, int& row, int& col) {
+    static_assert(TW * TH == 32, "a warp owns one tile");
+    const int64_t warp = idx >> 5;
+    const int lane = (int)(idx & 31);
+    const int tiles_x = (width + TW - 1) / TW;
+    const int ty = (int)(warp / tiles_x), tx = (int)(warp - (int64_t)ty * tiles_x);
+    row = ty * TH + lane / TW;
+    col = tx * TW + lane % TW;
+    return row < rows && col < width;
+}
+
+template <int TW, int TH>
+static int64_t tile_threads_wh(int width, int rows) {
+    return (int64_t)((width + TW - 1) / TW) * ((rows + TH - 1) / TH) * 32;
 }
 
 __host__ __device__ __forceinline__ int64_t tile_threads(int width, int rows) {
@@ -272,6 +293,147 @@ k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict
     cp_async_wait<0>();
 }
 
+// ---- TMA variant -----------------------------------------------------------------------------------
+// The same resampler with the box of every image brought in by ONE cp.async.bulk.tensor (TMA) issued by one thread
+// and completing on an mbarrier, instead of one or two 16-byte cp.async per thread and image: the other 127 threads
+// spend no instruction on the copy.  The ERP batch is a 3-D uint8 tensor [B][H][3W] (tensor map built per call on the
+// host); a tensor map fixes its box shape, so the plan offers two (narrow / wide rows, one row count) and a patch
+// uses the narrowest that holds its box; patches that fit neither keep the direct gathers.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
+k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_constant__ CUtensorMap map_wide, uint32_t box_rows,
+              uint32_t pitch_narrow, uint32_t pitch_wide, uint32_t stage_bytes, const uint32_t* __restrict__ s1_base,
+              const double2* __restrict__ s1_frac64, const uint2* __restrict__ s1_tiles, int tiles_x,
+              const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
+              int batch, int batch_per_block_row, int full_face) {
+    extern __shared__ __align__(128) uint8_t stage[];           // [TIF_S1_STAGES][stage_bytes], stage_bytes % 128 == 0
+    __shared__ __align__(8) unsigned long long full_bar[TIF_S1_STAGES];
+    constexpr int STAGES = TIF_S1_STAGES;
+    const int tid = threadIdx.x;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int trow = ty * TIF_S1_TILE_H + tid / TIF_S1_TILE_W, tcol = tx * TIF_S1_TILE_W + tid % TIF_S1_TILE_W;
+    const bool valid = trow < (int)(n_pix / tangent_w) && tcol < tangent_w;
+    const int64_t p = (int64_t)trow * tangent_w + tcol;
+    const int b_begin = blockIdx.y * batch_per_block_row;
+    const int n_img = min(batch, b_begin + batch_per_block_row) - b_begin;
+    const uint2 desc = s1_tiles[blockIdx.x];
+    const uint32_t n_rows = desc.y & 0xffffu, need = desc.y >> 16;
+    if (n_rows == 0u || n_rows > box_rows || need > pitch_wide) {      // block-uniform: no box shape holds the footprint
+        if (valid) erp2ico_direct<true>(p, s1_base, s1_frac64, erp, out, n_pix, erp_h, erp_w, b_begin, b_begin + n_img, full_face);
+        return;
+    }
+    const bool wide = need > pitch_narrow;
+    const uint32_t pitch = wide ? pitch_wide : pitch_narrow;
+    const CUtensorMap* map = wide ? &map_wide : &map_narrow;
+    const uint32_t row_bytes = (uint32_t)erp_w * 3u;
+    const uint32_t box_y = desc.x / row_bytes, box_x = desc.x - box_y * row_bytes;      // first row / first byte of the box
+    const uint32_t stage0 = smem_u32(stage), bar0 = smem_u32(full_bar);
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < STAGES; ++g) mbar_init(bar0 + 8u * g, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int inext = 0;                                      // next image to request (thread 0)
+    auto request = [&](int st) {
+        if (tid == 0 && inext < n_img) {
+            mbar_expect_tx(bar0 + 8u * st, pitch * box_rows);
+            tma_load_3d(stage0 + (uint32_t)st * stage_bytes, map, bar0 + 8u * st, (int)box_x, (int)box_y, b_begin + inext);
+        }
+        ++inext;
+    };
+#pragma unroll
+    for (int g = 0; g < STAGES - 1; ++g) request(g);
+
+    uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = stage0, sh = 0u;
+    bool blend = false;
+    if (valid) {
+        bs = s1_base[p];
+        blend = !((bs & TIF_S1_OUTSIDE) && !full_face);
+    }
+    if (blend) {
+        const double2 fr = s1_frac64[p];
+        const double wx0 = 1.0 - fr.x, wx1 = 1.0 - wx0, wy0 = 1.0 - fr.y, wy1 = 1.0 - wy0;
+        w00 = (uint32_t)(wy0 * wx0 * TIF_FIX_ONE + 0.5);
+        w01 = (uint32_t)(wy0 * wx1 * TIF_FIX_ONE + 0.5);
+        w10 = (uint32_t)(wy1 * wx0 * TIF_FIX_ONE + 0.5);
+        w11 = (uint32_t)(wy1 * wx1 * TIF_FIX_ONE + 0.5);
+        // byte offset of the first tap inside the box: rows are `pitch` apart there, `row_bytes` in the image
+        const uint32_t t = (bs & 0x7fffffffu) * 3u - desc.x;
+        const uint32_t dy = t / row_bytes, dxb = t - dy * row_bytes;
+        const uint32_t o = dy * pitch + dxb;
+        tap = stage0 + (o & ~3u);
+        sh = (o & 3u) * 8u;
+    }
+    uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
+    for (int i0 = 0; i0 < n_img; i0 += STAGES) {
+        const uint32_t parity = (uint32_t)(i0 / STAGES) & 1u;
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) {
+            if (i0 + st >= n_img) break;
+            mbar_wait(bar0 + 8u * st, parity);      // the box of image i has landed
+            __syncthreads();                        // everyone is done with image i - 1: its buffer may be refilled
+            request((st + STAGES - 1) % STAGES);
+            if (blend) *o4 = erp2ico_staged_pixel(tap + (uint32_t)st * stage_bytes, pitch, sh, w00, w01, w10, w11, s1_frac64 + p);
+            else if (valid) *o4 = 0x00ffffffu;      // RGB 255, alpha 0
+            o4 += n_pix;
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libtif_b200.so does not link libcuda)
+typedef CUresult (*TifEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TifEncodeTiledFn tma_encoder() {
+    static TifEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TifEncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+// uint8 [batch][H][3W] with a box of `pitch` bytes x `rows` rows x 1 image; out-of-range parts of a box read zero
+static bool tma_erp_map(TifEncodeTiledFn enc, const uint8_t* erp, int batch, int h, int w, uint32_t pitch, uint32_t rows, CUtensorMap* map) {
+    const cuuint64_t dims[3] = {(cuuint64_t)w * 3u, (cuuint64_t)h, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 3u, (cuuint64_t)w * 3u * (cuuint64_t)h};
+    const cuuint32_t box[3] = {pitch, rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(erp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch, int full_face_image,
                               uint8_t* tangent_rgba, void* stream) {
     if (!plan || !erp || !tangent_rgba || batch <= 0) {
@@ -298,10 +460,26 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         while (srows < batch && (int64_t)tiles * srows < 148 * 16) srows *= 2;
         const int sper = (batch + srows - 1) / srows;
         dim3 sgrid(tiles, (unsigned)((batch + sper - 1) / sper));
-        const size_t smem = (size_t)TIF_S1_STAGES * plan->s1_stage_bytes;
-        k_erp2ico_staged<<<sgrid, TIF_S1_THREADS, smem, (cudaStream_t)stream>>>(
-            plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, (uint32_t)plan->s1_stage_bytes, erp,
-            tangent_rgba, plan->tangent_pixels, plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
+        // TMA form when most staged patches fit its two box shapes (TIF_S1_NO_TMA=1 in the environment keeps cp.async)
+        static const bool no_tma = getenv("TIF_S1_NO_TMA") != nullptr;
+        TifEncodeTiledFn enc = no_tma ? nullptr : tma_encoder();
+        CUtensorMap map_narrow, map_wide;
+        const bool use_tma = enc && plan->s1_tma_tiles * 10 >= plan->s1_staged_tiles * 9 &&
+                             tma_erp_map(enc, erp, batch, plan->erp_h, plan->erp_w, (uint32_t)plan->s1_tma_pitch[0], (uint32_t)plan->s1_tma_rows, &map_narrow) &&
+                             tma_erp_map(enc, erp, batch, plan->erp_h, plan->erp_w, (uint32_t)plan->s1_tma_pitch[1], (uint32_t)plan->s1_tma_rows, &map_wide);
+        if (use_tma) {
+            // a stage holds the wide box + 16 bytes (the aligned 12-byte window of the last tap may end past its row)
+            const uint32_t stage_bytes = ((uint32_t)plan->s1_tma_pitch[1] * (uint32_t)plan->s1_tma_rows + 16u + 127u) & ~127u;
+            k_erp2ico_tma<<<sgrid, TIF_S1_THREADS, (size_t)TIF_S1_STAGES * stage_bytes, (cudaStream_t)stream>>>(
+                map_narrow, map_wide, (uint32_t)plan->s1_tma_rows, (uint32_t)plan->s1_tma_pitch[0], (uint32_t)plan->s1_tma_pitch[1],
+                stage_bytes, plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, erp, tangent_rgba,
+                plan->tangent_pixels, plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
+        } else {
+            const size_t smem = (size_t)TIF_S1_STAGES * plan->s1_stage_bytes;
+            k_erp2ico_staged<<<sgrid, TIF_S1_THREADS, smem, (cudaStream_t)stream>>>(
+                plan->d_s1_base, plan->d_s1_frac64, plan->d_s1_tiles, plan->s1_tiles_x, (uint32_t)plan->s1_stage_bytes, erp,
+                tangent_rgba, plan->tangent_pixels, plan->tangent_w, plan->erp_h, plan->erp_w, batch, sper, full_face_image);
+        }
     } else if (aligned)
         k_erp2ico<true><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
                                                                     plan->tangent_pixels, plan->tangent_w, plan->erp_h,
@@ -310,6 +488,47 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         k_erp2ico<false><<<grid, threads, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, erp, tangent_rgba,
                                                                      plan->tangent_pixels, plan->tangent_w, plan->erp_h,
                                                                      plan->erp_w, batch, per_row, full_face_image);
+    TIF_CUDA_CHECK(cudaGetLastError());
+    return TIF_OK;
+}
+
+// Float images (the reference accepts any dtype: scipy samples a float image in float64 and the result is then cast
+// into its integer tangent arrays, projection_icosahedron.py:231-241): one thread per tangent pixel, float64 bilinear in
+// scipy's accumulation order, float64 out; the host applies the cast.  Not a hot path (the estimator feeds uint8).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_erp2ico_float(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64, const T* __restrict__ erp,
+                double* __restrict__ out, int64_t n_pix, int erp_h, int erp_w, int channels, int full_face) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    const int b = blockIdx.y;
+    const uint32_t bs = s1_base[p];
+    double* o = out + ((size_t)b * n_pix + p) * channels;
+    if ((bs & TIF_S1_OUTSIDE) && !full_face) {
+        for (int ch = 0; ch < channels; ++ch) o[ch] = 255.0;          // np.full(..., 255) stays where nothing is sampled
+        return;
+    }
+    const double2 fr = s1_frac64[p];
+    const T* r0 = erp + ((size_t)b * erp_h * erp_w + (size_t)(bs & 0x7fffffffu)) * channels;
+    const T* r1 = r0 + (size_t)erp_w * channels;
+    for (int ch = 0; ch < channels; ++ch)
+        o[ch] = bilinear_f64_exact((double)__ldg(r0 + ch), (double)__ldg(r0 + channels + ch), (double)__ldg(r1 + ch),
+                                   (double)__ldg(r1 + channels + ch), fr.x, fr.y);
+}
+
+extern "C" int tif_erp2ico_float(const TifPlan* plan, const void* erp, int dtype, int batch, int channels, int full_face_image,
+                                 double* tangent, void* stream) {
+    if (!plan || !erp || !tangent || batch <= 0 || channels <= 0 || (dtype != TIF_DTYPE_F32 && dtype != TIF_DTYPE_F64)) {
+        tif_set_error("tif_erp2ico_float: invalid argument");
+        return TIF_ERR_INVALID_ARG;
+    }
+    const dim3 grid((unsigned)((plan->tangent_pixels + 255) / 256), (unsigned)batch);
+    if (dtype == TIF_DTYPE_F32)
+        k_erp2ico_float<float><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, (const float*)erp, tangent,
+                                                                      plan->tangent_pixels, plan->erp_h, plan->erp_w, channels, full_face_image);
+    else
+        k_erp2ico_float<double><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_s1_base, plan->d_s1_frac64, (const double*)erp, tangent,
+                                                                       plan->tangent_pixels, plan->erp_h, plan->erp_w, channels, full_face_image);
     TIF_CUDA_CHECK(cudaGetLastError());
     return TIF_OK;
 }
@@ -966,6 +1185,11 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 #ifndef TIF_NW_BLEND_MIN_BLOCKS
 #define TIF_NW_BLEND_MIN_BLOCKS 8
 #endif
+// ERP pixels of a warp of k_blend_nw: TIF_NW_BLEND_TILE_W x (32 / TIF_NW_BLEND_TILE_W).  Wider tiles make longer
+// contiguous stores (what a peer-mapped output across NVLink wants), squarer ones fewer cache lines per record gather.
+#ifndef TIF_NW_BLEND_TILE_W
+#define TIF_NW_BLEND_TILE_W 32
+#endif
 #define TIF_NW_IMGS 4
 static_assert(TIF_NW_IMGS == TIF_MAX_CHUNK_IMAGES, "tif_plan_create bounds the ERP size by the chunk's byte offsets");
 // per-thread fixed-point error sums are flushed (warp reduction + one shared 64-bit atomic) every this many samples:
@@ -1334,7 +1558,7 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
     __syncthreads();
     const int n_pix = erp_h * erp_w;
     int r, c;
-    if (!tile_pixel((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, erp_h, r, c)) return;
+    if (!tile_pixel_wh<TIF_NW_BLEND_TILE_W, 32 / TIF_NW_BLEND_TILE_W>((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, erp_h, r, c)) return;
     const int pix = r * erp_w + c;
     const int cnt = (int)s2_count[pix];
     const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
@@ -1535,7 +1759,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             k_nw_face_scale<<<(unsigned)((batch * n_faces + 127) / 128), 128, 0, stream>>>(nw_sums, plan->d_face_mult_sum, n_faces,
                                                                                           batch, nw_scale);
             TIF_CUDA_CHECK(cudaGetLastError());
-            const dim3 grid((unsigned)((tile_threads(w, h) + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), chunks);
+            const dim3 grid((unsigned)((tile_threads_wh<TIF_NW_BLEND_TILE_W, 32 / TIF_NW_BLEND_TILE_W>(w, h) + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), chunks);
             const size_t smem = (sizeof(float4) + sizeof(int)) * n_faces;
             k_blend_nw<<<grid, TIF_NW_BLEND_THREADS, smem, stream>>>(plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries,
                                                                     plan->d_s2_snap, disp_rec, dplane, nw_scale, erp_flow, h, w,

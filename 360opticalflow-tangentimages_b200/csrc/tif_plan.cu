@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "tif_common.cuh"
@@ -654,6 +655,36 @@ extern "C" int tif_plan_create(const TifFace* faces, int n_faces, int erp_h, int
         for (size_t i = 0; i < n_tiles; ++i)
             if (h_need[i] == 0u || h_need[i] > (uint32_t)stage_bytes) h_tiles[i] = make_uint2(0u, 0u);
         plan->s1_stage_bytes = stage_bytes;
+        {
+            // Box shapes of the TMA form: a tensor map fixes its box, so two shapes share one row count R (what 95 % of
+            // the staged patches need) and differ in the row length: P0 holds about two thirds of them, P1 is the
+            // widest that keeps P1 * R inside a stage of TIF_S1_TMA_MAX_STAGE_BYTES (and TMA's 256 elements per box
+            // dimension).  A patch outside both keeps the direct gathers in k_erp2ico_tma.
+            std::vector<uint32_t> rows_of, pitch_of;
+            for (size_t i = 0; i < n_tiles; ++i)
+                if (h_tiles[i].y != 0u) {
+                    rows_of.push_back(h_tiles[i].y & 0xffffu);
+                    pitch_of.push_back(h_tiles[i].y >> 16);
+                }
+            plan->s1_tma_tiles = 0;
+            if (!rows_of.empty()) {
+                std::vector<uint32_t> r_sorted(rows_of), p_sorted(pitch_of);
+                std::sort(r_sorted.begin(), r_sorted.end());
+                std::sort(p_sorted.begin(), p_sorted.end());
+                uint32_t box_rows = (r_sorted[(size_t)(0.95 * (r_sorted.size() - 1))] + 3u) & ~3u;
+                if (box_rows > 64u) box_rows = 64u;
+                uint32_t p1 = ((TIF_S1_TMA_MAX_STAGE_BYTES - 16u) / box_rows) & ~15u;
+                if (p1 > 256u) p1 = 256u;
+                uint32_t p0 = (p_sorted[(size_t)(0.65 * (p_sorted.size() - 1))] + 15u) & ~15u;
+                if (p0 > p1) p0 = p1;
+                if (p1 >= 48u) {
+                    plan->s1_tma_rows = (int)box_rows;
+                    plan->s1_tma_pitch[0] = (int)p0;
+                    plan->s1_tma_pitch[1] = (int)p1;
+                    for (size_t i = 0; i < rows_of.size(); ++i) plan->s1_tma_tiles += rows_of[i] <= box_rows && pitch_of[i] <= p1;
+                }
+            }
+        }
         PLAN_TRY(dev_alloc(&plan->d_s1_tiles, n_tiles, plan));
         PLAN_TRY(cuda_status(cudaMemcpy(plan->d_s1_tiles, h_tiles.data(), sizeof(uint2) * n_tiles, cudaMemcpyHostToDevice), "stage-1 tile table"));
         plan->s1_tiles_x = tiles_x;
@@ -677,6 +708,10 @@ extern "C" int tif_plan_info(const TifPlan* plan, TifPlanInfo* info) {
     info->device_bytes = plan->device_bytes;
     info->stage1_patches = (int64_t)plan->s1_tiles_x * plan->s1_tiles_y;
     info->stage1_staged_patches = plan->s1_staged_tiles;
+    info->stage1_tma_patches = plan->s1_tma_tiles;
+    info->stage1_tma_box_rows = plan->s1_tma_rows;
+    info->stage1_tma_box_bytes[0] = plan->s1_tma_pitch[0];
+    info->stage1_tma_box_bytes[1] = plan->s1_tma_pitch[1];
     return TIF_OK;
 }
 

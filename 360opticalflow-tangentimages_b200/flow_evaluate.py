@@ -3,7 +3,9 @@
     available_pixel(flow, of_mask=None, unknown_value=1e7)
     EPE / EPE_mat / RMSE / RMSE_mat / AAE / AAE_mat (of_ground_truth, of_evaluation, spherical=False, of_mask=None)
 
-Per-pixel matrices and their sums are computed on the device (csrc/tif_metrics.cu).  Quirks of the reference
+Per-pixel matrices and their sums are computed on the device (csrc/tif_metrics.cu), in float64 whatever the dtype of
+the flows: float32 flows (e.g. read from .flo files) are upcast first, where the reference sums them in float32, so
+the means agree with the reference to ~1e-7 relative for float32 input and to 1e-11 for float64.  Quirks of the reference
 that are kept: available_pixel's operator precedence, the *_mat functions zero the unusable pixels of BOTH input
 arrays in place, AAE ignores its `spherical` and `of_mask` arguments, the spherical AAE_mat branch does not exist
 (the reference calls a missing function there).
@@ -33,7 +35,16 @@ def _error_mats(of_ground_truth, of_evaluation, spherical, of_mask, want_aae):
     gt_d, ev_d = torch.from_numpy(gt).to(dev), torch.from_numpy(ev).to(dev)
     mask_d = None
     if of_mask is not None:
-        mask_d = torch.from_numpy(np.ascontiguousarray(np.asarray(of_mask) != 0).astype(np.uint8)).to(dev)
+        # the reference combines `index_valid & of_mask` (src/flow_evaluate.py:48): a bitwise AND with a boolean, so an
+        # integer mask counts through its lowest bit only (2 or 254 mark a pixel unusable), and a float mask is a TypeError
+        m = np.asarray(of_mask)
+        if m.dtype == np.bool_:
+            m = m.astype(np.uint8)
+        elif np.issubdtype(m.dtype, np.integer):
+            m = (m & 1).astype(np.uint8)
+        else:
+            raise TypeError("ufunc 'bitwise_and' not supported for the input types (bool & %s)" % m.dtype)
+        mask_d = torch.from_numpy(np.ascontiguousarray(m)).to(dev)
     epe = torch.empty((h, w), dtype=torch.float64, device=dev)
     aae = torch.empty((h, w), dtype=torch.float64, device=dev) if want_aae else None
     valid = torch.empty((h, w), dtype=torch.uint8, device=dev)
@@ -79,7 +90,8 @@ def EPE_mat(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
 def EPE(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
     """Mean end-point error over the available pixels (src/flow_evaluate.py:57-67)."""
     epe, _, valid, ok = _error_mats(of_ground_truth, of_evaluation, spherical, of_mask, False)
-    return _sum(epe) / float(ok.sum())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(np.float64(_sum(epe)) / np.float64(ok.sum()))        # nan on an empty set, like np.mean([])
 
 
 def RMSE_mat(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
@@ -90,7 +102,8 @@ def RMSE_mat(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
 def RMSE(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
     """src/flow_evaluate.py:107-115."""
     epe, _, valid, ok = _error_mats(of_ground_truth, of_evaluation, spherical, of_mask, False)
-    return float(np.sqrt(_sum(epe, 2) / float(ok.sum())))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(np.sqrt(np.float64(_sum(epe, 2)) / np.float64(ok.sum())))
 
 
 def AAE_mat(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
@@ -105,7 +118,8 @@ def AAE_mat(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
 def AAE(of_ground_truth, of_evaluation, spherical=False, of_mask=None):
     """src/flow_evaluate.py:156-164: always planar and unmasked, whatever is passed."""
     _, aae, _, ok = _error_mats(of_ground_truth, of_evaluation, False, None, True)
-    return _sum(aae) / float(ok.sum())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(np.float64(_sum(aae)) / np.float64(ok.sum()))
 
 
 def opticalflow_metric(flo_gt, flo_eva, erp_flo_error_filename_prefix=None, flo_mask=None, min_ratio=0.1, max_ratio=0.9,

@@ -54,9 +54,14 @@ def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_im
     erp_image = np.asarray(erp_image)
     if erp_image.ndim == 3 and erp_image.shape[2] == 4:
         erp_image = erp_image[:, :, 0:3]
-    if erp_image.ndim != 3 or erp_image.shape[2] != 3 or erp_image.dtype != np.uint8:
-        raise NotImplementedError("erp2ico_image: only uint8 [H,W,3|4] images are on the accelerated path "
-                                  "(got %s %s)" % (erp_image.dtype, erp_image.shape))
+    if erp_image.ndim == 2:
+        # the reference expands a single-channel map to [H,W,1], builds [Ht,Wt,1] tangent images and then writes their
+        # channel 3 (projection_icosahedron.py:181-183,230-244): it never returns
+        raise IndexError("index 3 is out of bounds for axis 2 with size 1")
+    if erp_image.ndim != 3 or erp_image.shape[2] != 3:
+        raise UnboundLocalError("tangent_image: the reference logs 'The channel number is %s' and fails" % (erp_image.shape[2:],))
+    if erp_image.dtype != np.uint8:
+        return _erp2ico_image_float(erp_image, tangent_image_width, padding_size, full_face_image, subdivision_level)
     if erp_image.shape[1] != erp_image.shape[0] * 2:
         log.error("the ERP image dimession is %s", np.shape(erp_image))     # the reference logs and continues
         raise ValueError("ERP image must be 2:1, got %s" % (erp_image.shape,))
@@ -66,6 +71,30 @@ def erp2ico_image(erp_image, tangent_image_width, padding_size=0.0, full_face_im
     out = _ops.ops.erp2ico(erp_dev, _ops.register_plan(plan), bool(full_face_image))
     # the reference builds its images with np.full(..., 255): int64, 4 channels
     return [t.astype(np.int64) for t in _split_faces(out[0].cpu().numpy(), plan)]
+
+
+def _erp2ico_image_float(erp_image, tangent_image_width, padding_size, full_face_image, subdivision_level):
+    """Non-uint8 images: scipy samples them in float64 and the values are then cast into the reference's integer
+    tangent arrays (np.full(..., 255) is int64; assignment truncates toward zero), projection_icosahedron.py:231-245."""
+    if erp_image.shape[1] != erp_image.shape[0] * 2:
+        log.error("the ERP image dimession is %s", np.shape(erp_image))
+        raise ValueError("ERP image must be 2:1, got %s" % (erp_image.shape,))
+    img = np.ascontiguousarray(erp_image, dtype=np.float32 if erp_image.dtype == np.float32 else np.float64)
+    dev = _device()
+    plan = _geometry.get_plan(padding_size, img.shape[0], tangent_image_width, dev, subdivision_level)
+    img_dev = torch.from_numpy(img).to(dev)[None]
+    out = torch.empty((1, plan.tangent_pixels, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(plan.lib.tif_erp2ico_float(plan.handle, img_dev.data_ptr(), _lib.DTYPE_F32 if img.dtype == np.float32 else _lib.DTYPE_F64,
+                                              1, 3, int(bool(full_face_image)), out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "tif_erp2ico_float")
+    vals = out[0].cpu().numpy()
+    if img.dtype == np.float32:
+        vals = vals.astype(np.float32)      # scipy's output takes the input's dtype before the integer cast
+    rgb = np.trunc(vals).astype(np.int64)
+    inside = plan.export_stage1()[2].cpu().numpy().astype(bool) if not full_face_image else np.ones(plan.tangent_pixels, dtype=bool)
+    stack = np.concatenate((rgb, np.where(inside, 255, 0).astype(np.int64)[:, None]), axis=1)
+    return [np.ascontiguousarray(t) for t in _split_faces(stack, plan)]
 
 
 def ico2erp_flow(tangent_flows_list, erp_flow_height=None, padding_size=0.0, image_erp_src=None, image_erp_tar=None,

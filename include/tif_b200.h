@@ -120,6 +120,10 @@ typedef struct TifPlanInfo {
     int64_t stage1_patches;         /* 16 x 8 tangent patches of tif_erp2ico_u8 ... */
     int64_t stage1_staged_patches;  /* ... and how many of them are resampled through shared memory (0: ERP rows are
                                        not 16-byte multiples, every patch takes the direct gathers) */
+    int64_t stage1_tma_patches;     /* ... and how many fit one of the two TMA box shapes below (cp.async.bulk.tensor) */
+    int32_t stage1_tma_box_rows;    /* rows of both boxes */
+    int32_t stage1_tma_box_bytes[2];/* row length of the narrow / the wide box */
+    int32_t reserved;
 } TifPlanInfo;
 
 int tif_abi_version(void);
@@ -161,6 +165,12 @@ int tif_plan_export_stage2(const TifPlan* plan, uint8_t* count /*[H*W]*/, uint32
  */
 int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp /*[B,H,W,3]*/, int batch, int full_face_image,
                    uint8_t* tangent_rgba /*[B,P,4]*/, void* stream);
+
+/* The same for float images of any channel count (`dtype` TIF_DTYPE_F32 / F64, [B,H,W,C]): scipy samples them in float64
+ * and the reference casts the result into its integer tangent arrays (projection_icosahedron.py:231-241); `tangent` is
+ * float64 [B,P,C], the cast is the caller's.  Pixels outside the padded triangle (full_face_image == 0) hold 255. */
+int tif_erp2ico_float(const TifPlan* plan, const void* erp, int dtype, int batch, int channels, int full_face_image,
+                      double* tangent, void* stream);
 
 /*
  * Compact forms of a tangent stack for the trip back to the host (n_pixels = B * P, a multiple of 4):

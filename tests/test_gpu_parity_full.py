@@ -70,8 +70,11 @@ def test_reference_summaries(pkg, golden, name):
         assert sha(np.stack(pico.erp2ico_image(tar, WT, PAD, True)).astype(np.uint8)) == str(g["ico_tar_sha"])
     plan = pkg._geometry.get_plan(PAD, erp_h, WT)
     # the sha above was produced by the shared-memory staged resampler and its direct-gather fallback together (these
-    # ERP heights are multiples of 8, so the rows are 16-byte multiples): most of the patches are staged
+    # ERP heights are multiples of 8, so the rows are 16-byte multiples): most of the patches are staged, and up to 2K
+    # nearly all of those through the TMA form (one cp.async.bulk.tensor per patch and image)
     assert plan.stage1_staged_patches > (0.9 if erp_h <= 1024 else 0.6) * plan.stage1_patches
+    if erp_h <= 1024:
+        assert plan.stage1_tma_patches > 0.9 * plan.stage1_staged_patches and plan.stage1_tma_box[0] > 0
     hashes, accepted = membership_hashes(plan)
     assert hashes == [str(h) for h in g["mem_sha"]]                 # membership + indices bit-exact
     assert accepted == [int(a) for a in g["accepted"]]

@@ -191,3 +191,22 @@ def test_large_flows(pkg, scale):
                 excuse |= dbg["edge_dist"] < 1e-3
             bad = ((np.abs(got - want).max(axis=2)) > FLOW_TOL) & ~excuse
             assert bad.sum() == 0, (scale, wrap, blend, int(bad.sum()), float(np.abs(got - want)[bad].max()))
+
+
+def test_erp2ico_image_api_corners(pkg):
+    """Inputs the estimator never feeds but the reference accepts (projection_icosahedron.py:178-245): float images are
+    sampled in float64 and truncated into the int64 tangent arrays; a single-channel map fails in the reference with an
+    IndexError (it writes channel 3 of a 1-channel array), so it does here; RGBA input loses its alpha."""
+    pico = pkg.projection_icosahedron
+    rng = np.random.default_rng(21)
+    erp_h, wt = 64, 32
+    for dtype in (np.float64, np.float32):
+        img = rng.uniform(0.0, 255.0, (erp_h, 2 * erp_h, 3)).astype(dtype)
+        for full in (True, False):
+            got = pico.erp2ico_image(img, wt, 0.3, full)
+            want = tif_oracle.erp2ico_image(img, wt, 0.3, full)
+            assert len(got) == 20 and all(g.dtype == np.int64 and np.array_equal(g, w) for g, w in zip(got, want)), (dtype, full)
+    with pytest.raises(IndexError):
+        pico.erp2ico_image(rng.uniform(0, 1, (erp_h, 2 * erp_h)), wt, 0.3)
+    u8 = rng.integers(0, 256, (erp_h, 2 * erp_h, 4), dtype=np.uint8)
+    assert all(np.array_equal(a, b) for a, b in zip(pico.erp2ico_image(u8, wt, 0.3), pico.erp2ico_image(u8[:, :, :3].copy(), wt, 0.3)))

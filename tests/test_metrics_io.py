@@ -85,6 +85,14 @@ def test_gpu_metrics(pkg, h):
     assert np.array_equal(ok, ok_w) and np.abs(a_got - a_want).max() < 1e-12
     assert np.array_equal(fe.available_pixel(gt, mask), tif_oracle.available_pixel(gt, mask))
     assert fe.EPE(gt.copy(), ev.copy()) == fe.EPE(gt.copy(), ev.copy())          # deterministic reduction
+    # an integer mask enters through `index_valid & of_mask` (src/flow_evaluate.py:48): only its lowest bit counts
+    rng = np.random.default_rng(5)
+    imask = rng.choice(np.array([0, 1, 2, 254, 255], dtype=np.uint8), size=mask.shape)
+    assert np.array_equal(fe.available_pixel(gt, imask), fe.available_pixel(gt, (imask & 1).astype(bool)))
+    assert not fe.available_pixel(gt, np.full(mask.shape, 254, dtype=np.uint8)).any()
+    with pytest.raises(TypeError):
+        fe.available_pixel(gt, mask.astype(np.float64))
+    assert np.isnan(fe.EPE(gt.copy(), ev.copy(), False, np.zeros(mask.shape, dtype=bool)))        # empty set: nan, no exception
     with pytest.raises(AttributeError):
         fe.AAE_mat(gt.copy(), ev.copy(), True)
     for m in (None, mask):

@@ -159,3 +159,18 @@ def test_oracle_on_demo_pair_config1():
     a = ref["projection_icosahedron"].erp2ico_image(img, 480, 0.3, True)
     b = tif_oracle.erp2ico_image(img, 480, 0.3, True)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_erp2ico_float_images_against_live_reference():
+    """Float ERP images (projection_icosahedron.py:231-241: sampled in float64, cast into the int64 tangent arrays)."""
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(21)
+    for dtype in (np.float64, np.float32):
+        img = rng.uniform(0.0, 255.0, (64, 128, 3)).astype(dtype)
+        for full in (True, False):
+            a = ref["projection_icosahedron"].erp2ico_image(img, 32, 0.3, full)
+            b = tif_oracle.erp2ico_image(img, 32, 0.3, full)
+            assert all(x.dtype == y.dtype and np.array_equal(x, y) for x, y in zip(a, b)), (dtype, full)
+    with pytest.raises(IndexError):
+        ref["projection_icosahedron"].erp2ico_image(rng.uniform(0, 1, (64, 128)), 32, 0.3)
