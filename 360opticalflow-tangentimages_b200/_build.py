@@ -49,6 +49,11 @@ def build_library(force=False, verbose=False):
     Safe to call from several processes at once (torchrun ranks): the build is serialised with a file
     lock, skipped when the content hash of sources + flags matches the stamp of the existing library,
     and the library is replaced atomically."""
+    override = os.environ.get("TIF_B200_LIB")
+    if override:            # an experiment variant built ahead of time (build_variant): use it as it is
+        if not os.path.exists(override):
+            raise RuntimeError("TIF_B200_LIB=%s does not exist" % override)
+        return override
     os.makedirs(BUILD_DIR, exist_ok=True)
     defs = os.environ.get("TIF_NVCC_DEFS", "").split()        # experiment knobs, e.g. -DTIF_STITCH_MIN_BLOCKS=6
     sources = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "tif_common.cuh"), os.path.join(CSRC, "tif_bilinear.cuh"),
@@ -87,6 +92,37 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(name, defs, units=("tif_exec.cu", "tif_plan.cu", "tif_warp.cu")):
+    """A/B experiments: compile `units` with extra -D knobs and link build/variants/<name>.so, reusing the objects of
+    the regular build for the other units.  Select it at run time with TIF_B200_LIB=<path> (see _lib.LIB_PATH), so the
+    GPU box spends no time compiling."""
+    build_library()
+    vdir = os.path.join(BUILD_DIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = _nvcc()
+    objects = []
+    for unit, extra in UNITS.items():
+        obj = os.path.join(BUILD_DIR, unit.replace(".cu", ".o"))
+        if unit in units:
+            obj = os.path.join(vdir, unit.replace(".cu", ".o"))
+            cmd = [nvcc] + ARCH + COMMON + extra + list(defs) + ["-c", os.path.join(CSRC, unit), "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                print(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed for %s (%s)" % (unit, name))
+        objects.append(obj)
+    out = os.path.join(BUILD_DIR, "variants", name + ".so")
+    res = subprocess.run([nvcc] + ARCH + ["-shared", "-o", out] + objects + ["-lcudart"], capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed (%s)" % name)
+    return out
+
+
 if __name__ == "__main__":
     import sys
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2].split()))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libtif_b200.so")
+LIB_PATH = os.environ.get("TIF_B200_LIB") or os.path.join(PKG_DIR, "libtif_b200.so")      # the override: A/B variants of _build.build_variant
 
 TIF_OK = 0
 ABI_VERSION = 5

@@ -325,6 +325,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Producer / consumer ring without a block-wide barrier: `full[st]` completes when the TMA box of a stage has landed
+// (transaction bytes), `empty[st]` when every warp has blended from it (one arrival per warp).  Thread 0 is the only
+// producer: after its own pixel of image i it refills the stage image i - 1 used, and waits for that stage's `empty`
+// phase only -- the other warps have normally released it already, so the warps drift up to TIF_S1_STAGES - 1 images
+// apart instead of meeting at a __syncthreads per image.
 __global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
 k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_constant__ CUtensorMap map_wide, uint32_t box_rows,
               uint32_t pitch_narrow, uint32_t pitch_wide, uint32_t stage_bytes, const uint32_t* __restrict__ s1_base,
@@ -332,7 +341,7 @@ k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_const
               const uint8_t* __restrict__ erp, uint8_t* __restrict__ out, int64_t n_pix, int tangent_w, int erp_h, int erp_w,
               int batch, int batch_per_block_row, int full_face) {
     extern __shared__ __align__(128) uint8_t stage[];           // [TIF_S1_STAGES][stage_bytes], stage_bytes % 128 == 0
-    __shared__ __align__(8) unsigned long long full_bar[TIF_S1_STAGES];
+    __shared__ __align__(8) unsigned long long bars[2 * TIF_S1_STAGES];      // full[0..S), empty[0..S)
     constexpr int STAGES = TIF_S1_STAGES;
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -352,23 +361,26 @@ k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_const
     const CUtensorMap* map = wide ? &map_wide : &map_narrow;
     const uint32_t row_bytes = (uint32_t)erp_w * 3u;
     const uint32_t box_y = desc.x / row_bytes, box_x = desc.x - box_y * row_bytes;      // first row / first byte of the box
-    const uint32_t stage0 = smem_u32(stage), bar0 = smem_u32(full_bar);
+    const uint32_t stage0 = smem_u32(stage), full0 = smem_u32(bars), empty0 = full0 + 8u * STAGES;
     if (tid == 0) {
 #pragma unroll
-        for (int g = 0; g < STAGES; ++g) mbar_init(bar0 + 8u * g, 1u);
+        for (int g = 0; g < STAGES; ++g) {
+            mbar_init(full0 + 8u * g, 1u);
+            mbar_init(empty0 + 8u * g, TIF_S1_THREADS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    int inext = 0;                                      // next image to request (thread 0)
-    auto request = [&](int st) {
-        if (tid == 0 && inext < n_img) {
-            mbar_expect_tx(bar0 + 8u * st, pitch * box_rows);
-            tma_load_3d(stage0 + (uint32_t)st * stage_bytes, map, bar0 + 8u * st, (int)box_x, (int)box_y, b_begin + inext);
-        }
-        ++inext;
-    };
+    const uint32_t box_bytes = pitch * box_rows;
+    if (tid == 0) {
 #pragma unroll
-    for (int g = 0; g < STAGES - 1; ++g) request(g);
+        for (int g = 0; g < STAGES - 1; ++g) {
+            if (g < n_img) {
+                mbar_expect_tx(full0 + 8u * g, box_bytes);
+                tma_load_3d(stage0 + (uint32_t)g * stage_bytes, map, full0 + 8u * g, (int)box_x, (int)box_y, b_begin + g);
+            }
+        }
+    }
 
     uint32_t bs = 0u, w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u, tap = stage0, sh = 0u;
     bool blend = false;
@@ -391,17 +403,28 @@ k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_const
         sh = (o & 3u) * 8u;
     }
     uint32_t* o4 = reinterpret_cast<uint32_t*>(out) + (size_t)b_begin * n_pix + p;
+    const bool lane0 = (tid & 31) == 0;
     for (int i0 = 0; i0 < n_img; i0 += STAGES) {
         const uint32_t parity = (uint32_t)(i0 / STAGES) & 1u;
 #pragma unroll
         for (int st = 0; st < STAGES; ++st) {
-            if (i0 + st >= n_img) break;
-            mbar_wait(bar0 + 8u * st, parity);      // the box of image i has landed
-            __syncthreads();                        // everyone is done with image i - 1: its buffer may be refilled
-            request((st + STAGES - 1) % STAGES);
+            const int i = i0 + st;
+            if (i >= n_img) break;
+            mbar_wait(full0 + 8u * st, parity);     // the box of image i has landed
             if (blend) *o4 = erp2ico_staged_pixel(tap + (uint32_t)st * stage_bytes, pitch, sh, w00, w01, w10, w11, s1_frac64 + p);
             else if (valid) *o4 = 0x00ffffffu;      // RGB 255, alpha 0
             o4 += n_pix;
+            __syncwarp();
+            if (lane0) mbar_arrive(empty0 + 8u * st);           // this warp is done with stage st
+            if (tid == 0) {
+                const int j = i + STAGES - 1;                   // next image to request, into the stage image i - 1 used
+                if (j < n_img) {
+                    const int sj = (st + STAGES - 1) % STAGES;
+                    if (i >= 1) mbar_wait(empty0 + 8u * sj, st == 0 ? (parity ^ 1u) : parity);
+                    mbar_expect_tx(full0 + 8u * sj, box_bytes);
+                    tma_load_3d(stage0 + (uint32_t)sj * stage_bytes, map, full0 + 8u * sj, (int)box_x, (int)box_y, b_begin + j);
+                }
+            }
         }
     }
 }
@@ -460,9 +483,13 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         while (srows < batch && (int64_t)tiles * srows < 148 * 16) srows *= 2;
         const int sper = (batch + srows - 1) / srows;
         dim3 sgrid(tiles, (unsigned)((batch + sper - 1) / sper));
-        // TMA form when most staged patches fit its two box shapes (TIF_S1_NO_TMA=1 in the environment keeps cp.async)
-        static const bool no_tma = getenv("TIF_S1_NO_TMA") != nullptr;
-        TifEncodeTiledFn enc = no_tma ? nullptr : tma_encoder();
+        // The TMA form is opt-in (TIF_S1_TMA=1 in the environment, read per call): measured on B200 it is 7 % slower than
+        // the cp.async ring (0.45 against 0.42 ms per 32 images at 2K, with or without a block barrier per image) -- a
+        // patch's box is ~20 rows of ~80 bytes, and the TMA unit, like the 1-D bulk copies before it, is bound by rows
+        // per clock, not by bytes; a tensor map also fixes the box shape, so every patch fetches the largest box of
+        // its class instead of its own footprint.
+        const char* tma_env = getenv("TIF_S1_TMA");
+        TifEncodeTiledFn enc = (tma_env && tma_env[0] == '1') ? tma_encoder() : nullptr;
         CUtensorMap map_narrow, map_wide;
         const bool use_tma = enc && plan->s1_tma_tiles * 10 >= plan->s1_staged_tiles * 9 &&
                              tma_erp_map(enc, erp, batch, plan->erp_h, plan->erp_w, (uint32_t)plan->s1_tma_pitch[0], (uint32_t)plan->s1_tma_rows, &map_narrow) &&
@@ -1185,11 +1212,6 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 #ifndef TIF_NW_BLEND_MIN_BLOCKS
 #define TIF_NW_BLEND_MIN_BLOCKS 8
 #endif
-// ERP pixels of a warp of k_blend_nw: TIF_NW_BLEND_TILE_W x (32 / TIF_NW_BLEND_TILE_W).  Wider tiles make longer
-// contiguous stores (what a peer-mapped output across NVLink wants), squarer ones fewer cache lines per record gather.
-#ifndef TIF_NW_BLEND_TILE_W
-#define TIF_NW_BLEND_TILE_W 32
-#endif
 #define TIF_NW_IMGS 4
 static_assert(TIF_NW_IMGS == TIF_MAX_CHUNK_IMAGES, "tif_plan_create bounds the ERP size by the chunk's byte offsets");
 // per-thread fixed-point error sums are flushed (warp reduction + one shared 64-bit atomic) every this many samples:
@@ -1437,32 +1459,37 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
     // flight while step i is evaluated (the chain entry -> source pixel is two dependent global loads, and a block
     // has only about three steps to hide them in).
     const uint8_t* __restrict__ src_chunk = erp_src + (size_t)b0 * image_bytes;
+    const uint32_t* __restrict__ src_words = reinterpret_cast<const uint32_t*>(src_chunk);      // SRC_ALIGNED only
     const uint32_t last_word = (uint32_t)(((size_t)n_img * image_bytes - 1) >> 2);      // last readable word of the chunk
     float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.y * max_k * ((size_t)erp_h * erp_w);
-    const int n_pix = erp_h * erp_w;
+    const unsigned n_pix = (unsigned)erp_h * (unsigned)erp_w;
     auto load_entry = [&](uint32_t i) { return i < s_end ? __ldg(smp + i) : make_uint2(0u, 0u); };
     struct SrcWords {
         uint32_t w[2 * TIF_NW_IMGS];
     };
-    // source pixel of a sample in the 4 images: 3 bytes at an arbitrary phase, fetched as two aligned words each
+    // source pixel of a sample in the 4 images: 3 bytes at an arbitrary phase, fetched as two aligned words each.
+    // The images of a chunk are a whole number of words apart (SRC_ALIGNED), so the byte phase is the sample's own.
     auto load_src = [&](const uint2& sm, SrcWords& sw) {
         const uint32_t a = ((sm.x >> 16) * (uint32_t)erp_w + (sm.x & 0xffffu)) * 3u;
 #pragma unroll
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
-            const uint32_t ab = img_off[bb] + a;
             if (SRC_ALIGNED) {
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(src_chunk);
-                const uint32_t wi = ab >> 2;
-                sw.w[2 * bb] = __ldg(q + wi);
-                sw.w[2 * bb + 1] = __ldg(q + min(wi + 1u, last_word));
+                const uint32_t wi = (a >> 2) + (img_off[bb] >> 2);
+                sw.w[2 * bb] = __ldg(src_words + wi);
+                // the second word is read only where it exists (the pixel's bytes never reach past the last word)
+                sw.w[2 * bb + 1] = wi < last_word ? __ldg(src_words + wi + 1) : 0u;
             } else {
-                const uint8_t* q = src_chunk + ab;
+                const uint8_t* q = src_chunk + (img_off[bb] + a);
                 sw.w[2 * bb] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
                 sw.w[2 * bb + 1] = 0u;
             }
         }
     };
-    int cur_f = -1, pending = 0;
+    // Face sums: every step adds the raw bits of fma(d * mult, 1024, 2^23) = 0x4B000000 + round(d * mult * 1024) of the
+    // 4 images to per-thread 32-bit accumulators (lanes without a sample have mult = 0 and add the bare offset); the
+    // offsets, `pending` per lane, leave again modulo 2^32 when the warp's total is taken.
+    int cur_f = -1;
+    unsigned pending = 0u;
     unsigned acc[TIF_NW_IMGS];
 #pragma unroll
     for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] = 0u;
@@ -1470,12 +1497,12 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         if (cur_f >= 0) {
 #pragma unroll
             for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
-                const unsigned total = __reduce_add_sync(0xffffffffu, acc[bb]);
+                const unsigned total = __reduce_add_sync(0xffffffffu, acc[bb] - pending * 0x4B000000u);
                 if (lane == 0 && total) atomicAdd(&sh_sum[bb * n_faces + cur_f], (unsigned long long)total);
                 acc[bb] = 0u;
             }
         }
-        pending = 0;
+        pending = 0u;
     };
     uint2 sm_next = load_entry(i_first + TIF_NW_BLOCK);
     SrcWords sw_cur;
@@ -1488,31 +1515,34 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         SrcWords sw_next;
         load_src(sm_next, sw_next);
         const int c = (int)(sm.x & 0xffffu);
-        const int pix = (int)(sm.x >> 16) * erp_w + c;
-        const int f = (int)(sm.y >> 24), k = (int)((sm.y >> 16) & 0xffu);
-        const float mult = (float)((sm.y >> 8) & 7u);
+        const unsigned pix = (sm.x >> 16) * (unsigned)erp_w + (unsigned)c;
+        const int f = (int)(sm.y >> 24);
+        const unsigned k = (sm.y >> 16) & 0xffu;
+        const float mult = (float)((sm.y >> 8) & 7u);          // 0 for a lane without a sample
         const unsigned local = sm.y & (TIF_NW_BLOCK - 1);
+        const unsigned sh_src = ((pix * 3u) & 3u) * 8u;
         float d[TIF_NW_IMGS];
-        unsigned fixed[TIF_NW_IMGS];
+        float s0[TIF_NW_IMGS], s1[TIF_NW_IMGS], s2[TIF_NW_IMGS];
+        int tmax = 0;
 #pragma unroll
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
-            const uint32_t spx = SRC_ALIGNED ? __funnelshift_r(sw_cur.w[2 * bb], sw_cur.w[2 * bb + 1], ((img_off[bb] + (uint32_t)pix * 3u) & 3u) * 8u)
-                                             : sw_cur.w[2 * bb];
+            const uint32_t spx = SRC_ALIGNED ? __funnelshift_r(sw_cur.w[2 * bb], sw_cur.w[2 * bb + 1], sh_src) : sw_cur.w[2 * bb];
             const float4 L = sh_lift[bb * TIF_NW_BLOCK + local];
             const uint32_t tb = sh_base[bb * TIF_NW_BLOCK + local];
-            const float s0 = byte_m(spx, 0), s1 = byte_m(spx, 1), s2 = byte_m(spx, 2);        // 2^23 + source pixel
-            d[bb] = fabsf(L.x + (byte_m(tb, 0) - s0)) + fabsf(L.y + (byte_m(tb, 1) - s1)) + fabsf(L.z + (byte_m(tb, 2) - s2));
-            // the reference samples at c + fu after its seam fix (:350-361): the end point taken the short way round
-            // from this column; outside [0, W-1] reads 255.  2 (x_end - c) in [-W, W] <=> short way without a fold
-            // (wrap_around=False leaves theta_t wrapped into [-pi, pi): always inside).  Rare: seam columns only.
-            const int t = __float_as_int(L.w) - 2 * c;
-            if (wrap_around && (unsigned)(t + erp_w) > 2u * (unsigned)erp_w)
-                d[bb] = (8388608.0f + 255.0f - s0) + (8388608.0f + 255.0f - s1) + (8388608.0f + 255.0f - s2);
-            // face-global sum of |diff| (x multiplicity) as order-independent fixed point: round to nearest through
-            // the 2^23 mantissa trick (765 x 7 x 1024 < 2^23)
-            fixed[bb] = __float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f)) - 0x4B000000u;
+            s0[bb] = byte_m(spx, 0), s1[bb] = byte_m(spx, 1), s2[bb] = byte_m(spx, 2);        // 2^23 + source pixel
+            d[bb] = fabsf(L.x + (byte_m(tb, 0) - s0[bb])) + fabsf(L.y + (byte_m(tb, 1) - s1[bb])) + fabsf(L.z + (byte_m(tb, 2) - s2[bb]));
+            tmax = max(tmax, abs(__float_as_int(L.w) - 2 * c));
         }
-        if (has) dplane_chunk[(size_t)k * n_pix + pix] = make_float4(d[0], d[1], d[2], d[3]);
+        // the reference samples at c + fu after its seam fix (:350-361): the end point taken the short way round
+        // from this column; outside [0, W-1] reads 255.  2 |x_end - c| <= W <=> short way without a fold
+        // (wrap_around=False leaves theta_t wrapped into [-pi, pi): always inside).  Rare: seam columns only.
+        if (wrap_around && tmax > erp_w) {
+#pragma unroll
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
+                if (abs(__float_as_int(sh_lift[bb * TIF_NW_BLOCK + local].w) - 2 * c) > erp_w)
+                    d[bb] = (8388608.0f + 255.0f - s0[bb]) + (8388608.0f + 255.0f - s1[bb]) + (8388608.0f + 255.0f - s2[bb]);
+        }
+        if (has) dplane_chunk[k * n_pix + pix] = make_float4(d[0], d[1], d[2], d[3]);
         // lanes hold consecutive samples of a list sorted by tangent pixel, hence by face: the warp almost always
         // sees one face and keeps per-thread partial sums; a warp straddling two faces uses shared atomics directly
         const int f0 = __shfl_sync(0xffffffffu, f, 0);          // lane 0 is valid: the valid lanes are a prefix
@@ -1521,12 +1551,16 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
                 flush();
                 cur_f = f0;
             }
+            // face-global sum of |diff| (x multiplicity) as order-independent fixed point: round to nearest through
+            // the 2^23 mantissa trick (765 x 7 x 1024 < 2^23)
 #pragma unroll
-            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] += has ? fixed[bb] : 0u;
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] += __float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f));
             ++pending;
         } else if (has) {
 #pragma unroll
-            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) atomicAdd(&sh_sum[bb * n_faces + f], (unsigned long long)fixed[bb]);
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
+                atomicAdd(&sh_sum[bb * n_faces + f],
+                          (unsigned long long)(__float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f)) - 0x4B000000u));
         }
         sm = sm_next;
         sm_next = sm_next2;
@@ -1538,16 +1572,19 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         if (sh_sum[i]) atomicAdd(&nw_sums[(size_t)b0 * n_faces + i], sh_sum[i]);
 }
 
+// grid = (ceil(W / TIF_NW_BLEND_THREADS), H, chunks): a block owns a run of one ERP row, so that row, column and pixel
+// index need no division and every warp stores 256 contiguous bytes per image (what a peer-mapped output across
+// NVLink wants).  Per pixel the kernel does little more than its sample loop, so the per-thread set-up counts.
 __global__ void __launch_bounds__(TIF_NW_BLEND_THREADS, TIF_NW_BLEND_MIN_BLOCKS)
 k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
            const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
            const float2* __restrict__ disp_rec, const float4* __restrict__ dplane, const float* __restrict__ nw_scale,
            float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int max_k, int batch,
-           int wrap_around) {
+           int wrap_around, float inv_w, int split /* erp_of_wraparound: first column of the right half */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sh_scale = reinterpret_cast<float4*>(smem_raw);                   // [F] -log2(e) / (3 mean_f) of the 4 images
     int* sh_offset = reinterpret_cast<int*>(sh_scale + n_faces);              // [F] first pixel of each face
-    const int b0 = blockIdx.y * TIF_NW_IMGS;
+    const int b0 = blockIdx.z * TIF_NW_IMGS;
     for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
         sh_offset[f] = faces[f].pix_offset;
         float sc[TIF_NW_IMGS];
@@ -1555,18 +1592,12 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb) sc[bb] = (b0 + bb < batch) ? nw_scale[(size_t)(b0 + bb) * n_faces + f] : 0.0f;
         sh_scale[f] = make_float4(sc[0], sc[1], sc[2], sc[3]);
     }
-    __syncthreads();
-    const int n_pix = erp_h * erp_w;
-    int r, c;
-    if (!tile_pixel_wh<TIF_NW_BLEND_TILE_W, 32 / TIF_NW_BLEND_TILE_W>((int64_t)blockIdx.x * blockDim.x + threadIdx.x, erp_w, erp_h, r, c)) return;
-    const int pix = r * erp_w + c;
-    const int cnt = (int)s2_count[pix];
-    const float wf = (float)erp_w, half_w = 0.5f * (float)erp_w, inv_w = 1.0f / (float)erp_w;
-    const float4* __restrict__ disp_chunk = reinterpret_cast<const float4*>(disp_rec + (size_t)blockIdx.y * n_tangent * TIF_NW_IMGS);
-    const float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.y * max_k * (size_t)n_pix + pix;
-    float acc_u[TIF_NW_IMGS], acc_v[TIF_NW_IMGS], acc_w[TIF_NW_IMGS];
-#pragma unroll
-    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+    const int c = blockIdx.x * TIF_NW_BLEND_THREADS + threadIdx.x;
+    const unsigned n_pix = (unsigned)erp_h * (unsigned)erp_w;
+    const unsigned pix = blockIdx.y * (unsigned)erp_w + (unsigned)c;
+    // the first entry, snap offset and error are requested before the table barrier
+    const int cnt = c < erp_w ? (int)__ldg(s2_count + pix) : 0;
+    const float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.z * max_k * (size_t)n_pix + pix;
     uint32_t e_next = 0u;
     float2 sn_next = make_float2(0.0f, 0.0f);
     float4 d_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1575,14 +1606,26 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
         sn_next = __ldg(s2_snap + pix);
         d_next = __ldg(dplane_chunk);
     }
+    __syncthreads();
+    if (c >= erp_w) return;
+    const float wf = (float)erp_w, half_w = 0.5f * wf;
+    const float4* __restrict__ disp_chunk = reinterpret_cast<const float4*>(disp_rec + (size_t)blockIdx.z * n_tangent * TIF_NW_IMGS);
+    float acc_u[TIF_NW_IMGS], acc_v[TIF_NW_IMGS], acc_w[TIF_NW_IMGS];
+#pragma unroll
+    for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
+    const uint32_t* __restrict__ e_ptr = s2_entries + pix;
+    const float2* __restrict__ sn_ptr = s2_snap + pix;
     for (int k = 0; k < cnt; ++k) {
         const uint32_t e = e_next;
         const float2 sn = sn_next;
         const float4 dd = d_next;
         if (k + 1 < cnt) {                           // next entry in flight while this one is blended
-            e_next = __ldg(s2_entries + (size_t)(k + 1) * n_pix + pix);
-            sn_next = __ldg(s2_snap + (size_t)(k + 1) * n_pix + pix);
-            d_next = __ldg(dplane_chunk + (size_t)(k + 1) * n_pix);
+            e_ptr += n_pix;
+            sn_ptr += n_pix;
+            dplane_chunk += n_pix;
+            e_next = __ldg(e_ptr);
+            sn_next = __ldg(sn_ptr);
+            d_next = __ldg(dplane_chunk);
         }
         const int f = (int)TIF_E_FACE(e);
         const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
@@ -1604,14 +1647,13 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
             acc_w[bb] += w;
         }
     }
-    const int split = (int)((double)erp_w - 1.0 - 0.5 * (double)erp_w);
+    float2* __restrict__ o = reinterpret_cast<float2*>(out) + (size_t)b0 * n_pix + pix;
 #pragma unroll
     for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
-        const int b = b0 + bb;
-        if (b >= batch) break;
+        if (b0 + bb >= batch) break;
         float u = acc_u[bb], v = acc_v[bb];
-        if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393
-            const float inv = 1.0f / acc_w[bb];
+        if (acc_w[bb] != 0.0f) {      // projection_icosahedron.py:389-393; the weights are flushed to zero below 2^-126, so
+            const float inv = rcp_newton(acc_w[bb]);      // a non-zero sum is a normal number
             u *= inv;
             v *= inv;
         }
@@ -1622,7 +1664,7 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
                 if (u < -half_w) u += wf;
             }
         }
-        reinterpret_cast<float2*>(out)[(size_t)b * n_pix + pix] = make_float2(u, v);
+        o[(size_t)bb * n_pix] = make_float2(u, v);
     }
 }
 
@@ -1759,12 +1801,13 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             k_nw_face_scale<<<(unsigned)((batch * n_faces + 127) / 128), 128, 0, stream>>>(nw_sums, plan->d_face_mult_sum, n_faces,
                                                                                           batch, nw_scale);
             TIF_CUDA_CHECK(cudaGetLastError());
-            const dim3 grid((unsigned)((tile_threads_wh<TIF_NW_BLEND_TILE_W, 32 / TIF_NW_BLEND_TILE_W>(w, h) + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), chunks);
+            const dim3 grid((unsigned)((w + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), (unsigned)h, chunks);
             const size_t smem = (sizeof(float4) + sizeof(int)) * n_faces;
             k_blend_nw<<<grid, TIF_NW_BLEND_THREADS, smem, stream>>>(plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries,
                                                                     plan->d_s2_snap, disp_rec, dplane, nw_scale, erp_flow, h, w,
                                                                     plan->tangent_w, n_tangent, plan->max_faces_per_pixel, batch,
-                                                                    wrap_around);
+                                                                    wrap_around, 1.0f / (float)w,
+                                                                    (int)((double)w - 1.0 - 0.5 * (double)w));
         }
     }
 #undef GATHER_ARGS

@@ -3,6 +3,7 @@ summaries, config #3 (3840x1920, warp enabled) against the reference summaries, 
 (batch consistency, determinism, identities) and direct C-ABI calls."""
 import ctypes
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -70,11 +71,17 @@ def test_reference_summaries(pkg, golden, name):
         assert sha(np.stack(pico.erp2ico_image(tar, WT, PAD, True)).astype(np.uint8)) == str(g["ico_tar_sha"])
     plan = pkg._geometry.get_plan(PAD, erp_h, WT)
     # the sha above was produced by the shared-memory staged resampler and its direct-gather fallback together (these
-    # ERP heights are multiples of 8, so the rows are 16-byte multiples): most of the patches are staged, and up to 2K
-    # nearly all of those through the TMA form (one cp.async.bulk.tensor per patch and image)
+    # ERP heights are multiples of 8, so the rows are 16-byte multiples): most of the patches are staged
     assert plan.stage1_staged_patches > (0.9 if erp_h <= 1024 else 0.6) * plan.stage1_patches
     if erp_h <= 1024:
+        # the opt-in TMA form (one cp.async.bulk.tensor per patch and image, mbarrier producer / consumer ring) gives
+        # the same bytes; up to 2K nearly all staged patches fit its two box shapes
         assert plan.stage1_tma_patches > 0.9 * plan.stage1_staged_patches and plan.stage1_tma_box[0] > 0
+        os.environ["TIF_S1_TMA"] = "1"
+        try:
+            assert sha(np.stack(pico.erp2ico_image(src, WT, PAD, True)).astype(np.uint8)) == str(g["ico_full_sha"])
+        finally:
+            del os.environ["TIF_S1_TMA"]
     hashes, accepted = membership_hashes(plan)
     assert hashes == [str(h) for h in g["mem_sha"]]                 # membership + indices bit-exact
     assert accepted == [int(a) for a in g["accepted"]]
