@@ -1203,16 +1203,36 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 // Measured alternatives (B200, 32 pairs of 2048x1024): the same two phases as separate kernels with the target samples
 // in HBM: 0.86 + 0.88 ms against 1.54 ms fused; source pixels staged by 4-byte cp.async: 1.76 ms; the sample steps of
 // a block taken three at a time with all loads up front: 1.80 ms (registers: the lift phase spills).
+// launch shapes measured on B200 (32 pairs of 2048x1024): k_lift_nw 256 x 4 (64 registers) 1.34-1.37 ms; 256 x 3: 1.48-1.52,
+// 128 x 7: 1.44, 128 x 6 / 128 x 8: 1.48 / 1.45-1.49, 512 x 2: 1.50.  At 64 registers the kernel spills ~100 bytes and
+// its time moves by +-2 % with the register allocation (taps of 1 or 2 images grouped, multiplicity folded into the
+// fixed-point scale or not); a block-uniform face flag (no per-step shuffle + vote) costs more registers than it saves.  k_blend_nw is bound by the latency of its displacement gathers and wants resident warps: 64 x 20 (51
+// registers) 0.47 ms, 128 x 10: 0.48, 128 x 8: 0.53, 128 x 12 (spills): 0.53, 256 x 4: 0.56; gathers requested one sample
+// ahead (TIF_BLEND_PIPE): 0.54.
 #ifndef TIF_NW_LIFT_MIN_BLOCKS
-#define TIF_NW_LIFT_MIN_BLOCKS 7
+#define TIF_NW_LIFT_MIN_BLOCKS 4
+#endif
+#ifndef TIF_NW_LIFT_GROUP
+#define TIF_NW_LIFT_GROUP 2
+#endif
+#ifndef TIF_NW_WORD_TAPS
+#define TIF_NW_WORD_TAPS 1
+#endif
+#ifndef TIF_NW_FOLD_MULT
+#define TIF_NW_FOLD_MULT 0
 #endif
 #ifndef TIF_NW_BLEND_THREADS
-#define TIF_NW_BLEND_THREADS 128
+#define TIF_NW_BLEND_THREADS 64
 #endif
 #ifndef TIF_NW_BLEND_MIN_BLOCKS
-#define TIF_NW_BLEND_MIN_BLOCKS 8
+#define TIF_NW_BLEND_MIN_BLOCKS 20
 #endif
 #define TIF_NW_IMGS 4
+#ifndef TIF_BLEND_PIPE
+#define TIF_BLEND_PIPE 0
+#endif
+static_assert(TIF_NW_FIXED_SCALE == 1024.0f, "k_lift_nw folds the scale into the multiplicity as a shift by 10");
+static_assert(TIF_NW_IMGS % TIF_NW_LIFT_GROUP == 0, "the images of a thread are split into whole groups");
 static_assert(TIF_NW_IMGS == TIF_MAX_CHUNK_IMAGES, "tif_plan_create bounds the ERP size by the chunk's byte offsets");
 // per-thread fixed-point error sums are flushed (warp reduction + one shared 64-bit atomic) every this many samples:
 // 32 lanes x 16 samples x 765 x 7 x 1024 < 2^32
@@ -1291,7 +1311,7 @@ __device__ __forceinline__ bool lift_fast(const LiftFrame& fr, float2 uv, float 
     return fmaxf(fabsf(disp_x), fabsf(disp_y)) <= TIF_NW_MAX_F32_DISP;
 }
 
-template <bool SRC_ALIGNED /* erp_src is 4-byte aligned: source pixels come as aligned words */>
+template <bool SRC_ALIGNED /* erp_src and erp_tar are 4-byte aligned and so is every image of the batch: pixels and taps come as aligned words addressed by 32-bit word indices */>
 __global__ void __launch_bounds__(TIF_NW_BLOCK, TIF_NW_LIFT_MIN_BLOCKS)
 k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __restrict__ ref_list, int n_ref,
           const int4* __restrict__ ref_pos, const double* __restrict__ s1_ex, const double* __restrict__ s1_ey,
@@ -1355,7 +1375,7 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         const float exf = __int_as_float(pos.z), eyf = __int_as_float(pos.w);
         const uint8_t* __restrict__ tar_chunk = erp_tar + (size_t)b0 * image_bytes;
         float2* __restrict__ disp_out = disp_rec + ((size_t)blockIdx.y * n_tangent + p) * TIF_NW_IMGS;
-        constexpr int G = TIF_LIFT_GROUP;
+        constexpr int G = TIF_NW_LIFT_GROUP;
         constexpr unsigned kNoSample = 0xffffffffu;
 #pragma unroll
         for (int g0 = 0; g0 < TIF_NW_IMGS; g0 += G) {
@@ -1417,10 +1437,22 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
             for (int j = 0; j < G; ++j) {
                 raw0[j].w0 = raw0[j].w1 = raw0[j].w2 = raw1[j].w0 = raw1[j].w1 = raw1[j].w2 = 0u;
                 if (off[j] != kNoSample && !tail[j]) {
-                    const uint8_t* r0 = tar_chunk + off[j];
-                    const uint8_t* r1 = r0 + row_bytes;
-                    raw0[j] = load_raw_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3));
-                    raw1[j] = load_raw_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3));
+                    if (SRC_ALIGNED && TIF_NW_WORD_TAPS) {
+                        // word-aligned images: 32-bit word indices from the chunk base, no pointer arithmetic
+                        const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(tar_chunk);
+                        const unsigned i0 = off[j] >> 2, i1 = (off[j] + row_bytes) >> 2;
+                        raw0[j].w0 = __ldg(q + i0);
+                        raw0[j].w1 = __ldg(q + i0 + 1);
+                        if ((off[j] & 3u) == 3u) raw0[j].w2 = __ldg(q + i0 + 2);
+                        raw1[j].w0 = __ldg(q + i1);
+                        raw1[j].w1 = __ldg(q + i1 + 1);
+                        if (((off[j] + row_bytes) & 3u) == 3u) raw1[j].w2 = __ldg(q + i1 + 2);
+                    } else {
+                        const uint8_t* r0 = tar_chunk + off[j];
+                        const uint8_t* r1 = r0 + row_bytes;
+                        raw0[j] = load_raw_pair(r0, (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3));
+                        raw1[j] = load_raw_pair(r1, (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3));
+                    }
                 }
             }
 #pragma unroll
@@ -1434,6 +1466,9 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
                     if (tail[j]) {
                         load_tap_pair_bytes(r0, lo0, hi0);
                         load_tap_pair_bytes(r1, lo1, hi1);
+                    } else if (SRC_ALIGNED && TIF_NW_WORD_TAPS) {
+                        align_pair(raw0[j], off[j] & 3u, lo0, hi0);
+                        align_pair(raw1[j], (off[j] + row_bytes) & 3u, lo1, hi1);
                     } else {
                         align_pair(raw0[j], (unsigned)(reinterpret_cast<uintptr_t>(r0) & 3), lo0, hi0);
                         align_pair(raw1[j], (unsigned)(reinterpret_cast<uintptr_t>(r1) & 3), lo1, hi1);
@@ -1518,7 +1553,13 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         const unsigned pix = (sm.x >> 16) * (unsigned)erp_w + (unsigned)c;
         const int f = (int)(sm.y >> 24);
         const unsigned k = (sm.y >> 16) & 0xffu;
+#if TIF_NW_FOLD_MULT
+        const float mult_fixed = (float)(((sm.y >> 8) & 7u) << 10);          // multiplicity x TIF_NW_FIXED_SCALE; 0 for a lane without a sample
+#define NW_FIXED(dv) fmaf((dv), mult_fixed, 8388608.0f)
+#else
         const float mult = (float)((sm.y >> 8) & 7u);          // 0 for a lane without a sample
+#define NW_FIXED(dv) fmaf((dv) * mult, TIF_NW_FIXED_SCALE, 8388608.0f)
+#endif
         const unsigned local = sm.y & (TIF_NW_BLOCK - 1);
         const unsigned sh_src = ((pix * 3u) & 3u) * 8u;
         float d[TIF_NW_IMGS];
@@ -1554,13 +1595,12 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
             // face-global sum of |diff| (x multiplicity) as order-independent fixed point: round to nearest through
             // the 2^23 mantissa trick (765 x 7 x 1024 < 2^23)
 #pragma unroll
-            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] += __float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f));
+            for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc[bb] += __float_as_uint(NW_FIXED(d[bb]));
             ++pending;
         } else if (has) {
 #pragma unroll
             for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
-                atomicAdd(&sh_sum[bb * n_faces + f],
-                          (unsigned long long)(__float_as_uint(fmaf(d[bb] * mult, TIF_NW_FIXED_SCALE, 8388608.0f)) - 0x4B000000u));
+                atomicAdd(&sh_sum[bb * n_faces + f], (unsigned long long)(__float_as_uint(NW_FIXED(d[bb])) - 0x4B000000u));
         }
         sm = sm_next;
         sm_next = sm_next2;
@@ -1615,10 +1655,42 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
     for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
     const uint32_t* __restrict__ e_ptr = s2_entries + pix;
     const float2* __restrict__ sn_ptr = s2_snap + pix;
+    auto tangent_pixel = [&](uint32_t e) {
+        return (unsigned)(sh_offset[TIF_E_FACE(e)] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
+    };
+#if TIF_BLEND_PIPE
+    // displacement gathers one sample ahead (entries two ahead): the gather of sample k + 1 is in flight while sample k
+    // is blended
+    uint32_t e_next2 = cnt > 1 ? __ldg(e_ptr + n_pix) : 0u;
+    float4 q01_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q23_next = q01_next;
+    if (cnt > 0) {
+        const unsigned t0 = tangent_pixel(e_next);
+        q01_next = __ldg(disp_chunk + 2u * t0);
+        q23_next = __ldg(disp_chunk + 2u * t0 + 1u);
+    }
+    e_ptr += n_pix;
+#endif
     for (int k = 0; k < cnt; ++k) {
         const uint32_t e = e_next;
         const float2 sn = sn_next;
         const float4 dd = d_next;
+#if TIF_BLEND_PIPE
+        const float4 q01 = q01_next, q23 = q23_next;
+        if (k + 1 < cnt) {
+            e_next = e_next2;
+            const unsigned t1 = tangent_pixel(e_next);
+            q01_next = __ldg(disp_chunk + 2u * t1);
+            q23_next = __ldg(disp_chunk + 2u * t1 + 1u);
+            sn_ptr += n_pix;
+            dplane_chunk += n_pix;
+            sn_next = __ldg(sn_ptr);
+            d_next = __ldg(dplane_chunk);
+            if (k + 2 < cnt) {
+                e_ptr += n_pix;
+                e_next2 = __ldg(e_ptr);
+            }
+        }
+#else
         if (k + 1 < cnt) {                           // next entry in flight while this one is blended
             e_ptr += n_pix;
             sn_ptr += n_pix;
@@ -1627,10 +1699,10 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
             sn_next = __ldg(sn_ptr);
             d_next = __ldg(dplane_chunk);
         }
-        const int f = (int)TIF_E_FACE(e);
-        const unsigned tpix = (unsigned)(sh_offset[f] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
+        const unsigned tpix = tangent_pixel(e);
         const float4 q01 = __ldg(disp_chunk + 2u * tpix), q23 = __ldg(disp_chunk + 2u * tpix + 1u);
-        const float4 sc = sh_scale[f];
+#endif
+        const float4 sc = sh_scale[TIF_E_FACE(e)];
         const float du[TIF_NW_IMGS] = {q01.x, q01.z, q23.x, q23.z}, dv[TIF_NW_IMGS] = {q01.y, q01.w, q23.y, q23.w};
         const float de[TIF_NW_IMGS] = {dd.x, dd.y, dd.z, dd.w}, ds[TIF_NW_IMGS] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
@@ -1790,7 +1862,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         plan->d_blk_smp, tangent_flow, erp_src, erp_tar, disp_rec, dplane, nw_sums, h, w, plan->tangent_w, n_tangent,  \
         plan->max_faces_per_pixel, batch, wrap_around, lift_u_scale, lift_v_scale, polar
             // every image of the batch starts on a word boundary when the buffer does and H * W * 3 is a multiple of 4
-            if (reinterpret_cast<uintptr_t>(erp_src) % 4 == 0 && ((size_t)h * w * 3) % 4 == 0)
+            if (reinterpret_cast<uintptr_t>(erp_src) % 4 == 0 && reinterpret_cast<uintptr_t>(erp_tar) % 4 == 0 && ((size_t)h * w * 3) % 4 == 0)
                 k_lift_nw<true><<<grid, TIF_NW_BLOCK, smem, stream>>>(LIFT_NW_ARGS);
             else
                 k_lift_nw<false><<<grid, TIF_NW_BLOCK, smem, stream>>>(LIFT_NW_ARGS);
