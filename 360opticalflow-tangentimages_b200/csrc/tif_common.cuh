@@ -109,7 +109,7 @@ struct TifPlan {
                                    //  face << 25 | row inside the face << 11 | column
     double* d_face_mult_sum;       // [F] sum of multiplicities of accepted pixels (normwarp mean denominator / 3)
     // normwarp (icosahedron plans): the accepted samples regrouped by the tangent pixel they snap to
-    int4* d_ref_pos;               // [P_ref] own ERP position of every work-list entry: floor(x), floor(y), float bits of the fractions
+    int4* d_ref_pos;               // [P_ref] per work-list entry: own ERP position (floor(x) + 1 | floor(y) + 1 << 16, float bits of the two fractions) and its tangent pixel index
     uint2* d_smp;                  // [S] work-list order: {ERP row << 16 | column, face << 24 | plane k << 16 | multiplicity << 8 | entry % TIF_NW_BLOCK}
     uint32_t* d_blk_smp;           // [ceil(P_ref / TIF_NW_BLOCK) + 1] first sample of every block of TIF_NW_BLOCK work-list entries
     int64_t n_samples;             // S = accepted_unique

@@ -1326,8 +1326,7 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
     // face mean is small, wherever the faces disagree by hundreds of pixels (garbage estimator flows next to a pole).
     float4* sh_lift = reinterpret_cast<float4*>(smem_raw);                                   // [4][TIF_NW_BLOCK] remainder rgb, x code
     uint32_t* sh_base = reinterpret_cast<uint32_t*>(sh_lift + TIF_NW_IMGS * TIF_NW_BLOCK);   // [4][TIF_NW_BLOCK] R | G << 8 | B << 16
-    LiftFace* sh_face = reinterpret_cast<LiftFace*>(sh_base + TIF_NW_IMGS * TIF_NW_BLOCK);   // [F]
-    unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_face + n_faces);   // [4][F]
+    unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_base + TIF_NW_IMGS * TIF_NW_BLOCK);   // [4][F]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.y * TIF_NW_IMGS;
     const int n_img = min(TIF_NW_IMGS, batch - b0);
@@ -1339,40 +1338,39 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
     for (int bb = 0; bb < TIF_NW_IMGS; ++bb) img_off[bb] = (unsigned)min(bb, n_img - 1) * image_bytes;
 
     // Every thread starts with a chain of dependent loads (work-list entry -> flows -> ... ; sample-list entry -> source
-    // pixel -> ...), and there are few warps per SM to hide it: request all of it before the block's first barrier.
+    // pixel -> ...), a block lives for ~13 us and 4 blocks share an SM: the start-up latency shows.  So there is no
+    // barrier before the lift -- the per-face constants come straight from the (cached) global table instead of a
+    // shared copy -- and the work-list record carries the tangent pixel index, so the flows are the second link of the
+    // chain, not the third.
     const int idx = blockIdx.x * TIF_NW_BLOCK + tid;
     const bool live = idx < n_ref;
     uint32_t ref = 0u;
     int4 pos = make_int4(0, 0, 0, 0);
-    int p = 0;
     float2 uvs[TIF_NW_IMGS];
     if (live) {
+        pos = __ldg(ref_pos + idx);                  // own ERP position (floor x + 1 | floor y + 1 << 16, fractions), tangent pixel
         ref = (uint32_t)__ldg(ref_list + idx);       // face << 25 | row inside the face << 11 | column
-        pos = __ldg(ref_pos + idx);                  // own ERP position: floor x, floor y, fractions
     }
     const uint32_t s_begin = __ldg(blk_smp + blockIdx.x), s_end = __ldg(blk_smp + blockIdx.x + 1);
     const unsigned lane = (unsigned)tid & 31u;
     const uint32_t i_first = s_begin + (uint32_t)tid;
     const uint2 sm_first = i_first < s_end ? __ldg(smp + i_first) : make_uint2(0u, 0u);
+    const int p = pos.w;
     if (live) {
-        // the face's first stack row straight from the (cached) global table: the flows do not wait for the barrier
-        p = (__ldg(&lift_faces[TIF_E_FACE(ref)].first_row) + (int)TIF_E_IY(ref)) * tangent_w + (int)TIF_E_IX(ref);
         const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
 #pragma unroll
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
             uvs[bb] = __ldg(flow_chunk + ((unsigned)min(bb, n_img - 1) * (unsigned)n_tangent + (unsigned)p));
     }
-    for (int i = tid; i < n_faces * (int)(sizeof(LiftFace) / 16); i += TIF_NW_BLOCK)
-        reinterpret_cast<uint4*>(sh_face)[i] = __ldg(reinterpret_cast<const uint4*>(lift_faces) + i);
-    for (int i = tid; i < TIF_NW_IMGS * n_faces; i += TIF_NW_BLOCK) sh_sum[i] = 0ull;
-    __syncthreads();
+    for (int i = tid; i < TIF_NW_IMGS * n_faces; i += TIF_NW_BLOCK) sh_sum[i] = 0ull;       // ordered by the barrier after phase 1
 
     // ---- phase 1: lift one work-list entry per thread --------------------------------------------------------
     if (live) {
-        const LiftFace& F = sh_face[TIF_E_FACE(ref)];
+        const LiftFace& F = lift_faces[TIF_E_FACE(ref)];
         const int tcol = (int)TIF_E_IX(ref), frow = (int)TIF_E_IY(ref);
         const LiftFrame fr = lift_frame(F, tcol, frow, polar.sin2);
-        const float exf = __int_as_float(pos.z), eyf = __int_as_float(pos.w);
+        const int pos_x = (pos.x & 0xffff) - 1, pos_y = (int)((unsigned)pos.x >> 16) - 1;
+        const float exf = __int_as_float(pos.y), eyf = __int_as_float(pos.z);
         const uint8_t* __restrict__ tar_chunk = erp_tar + (size_t)b0 * image_bytes;
         float2* __restrict__ disp_out = disp_rec + ((size_t)blockIdx.y * n_tangent + p) * TIF_NW_IMGS;
         constexpr int G = TIF_NW_LIFT_GROUP;
@@ -1394,8 +1392,8 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
                     float df, dg;
                     split_floor(dx, di, df);
                     split_floor(dy, dj, dg);
-                    xi = pos.x + di;
-                    yi = pos.y + dj;
+                    xi = pos_x + di;
+                    yi = pos_y + dj;
                     fx[j] = exf + df;
                     fy[j] = eyf + dg;
                     if (fx[j] >= 1.0f) { fx[j] -= 1.0f; xi += 1; }
@@ -1855,8 +1853,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if ((pass_mask & (1 | 8)) && !skip_lift) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             const dim3 grid((unsigned)((n_ref + TIF_NW_BLOCK - 1) / TIF_NW_BLOCK), chunks);
-            const size_t smem = (sizeof(float4) + sizeof(uint32_t)) * TIF_NW_IMGS * TIF_NW_BLOCK + sizeof(LiftFace) * n_faces +
-                                sizeof(unsigned long long) * TIF_NW_IMGS * n_faces;
+            const size_t smem = (sizeof(float4) + sizeof(uint32_t)) * TIF_NW_IMGS * TIF_NW_BLOCK + sizeof(unsigned long long) * TIF_NW_IMGS * n_faces;
 #define LIFT_NW_ARGS                                                                                                    \
     plan->d_lift_faces, n_faces, plan->d_ref_list, n_ref, plan->d_ref_pos, plan->d_s1_ex, plan->d_s1_ey, plan->d_smp,   \
         plan->d_blk_smp, tangent_flow, erp_src, erp_tar, disp_rec, dplane, nw_sums, h, w, plan->tangent_w, n_tangent,  \

@@ -283,7 +283,8 @@ k_plan_ref_pos(const int32_t* __restrict__ ref_list, int n_ref, const LiftFace* 
     const int64_t p = (int64_t)(lift_faces[TIF_E_FACE(ref)].first_row + (int)TIF_E_IY(ref)) * tangent_w + (int)TIF_E_IX(ref);
     const double ex = s1_ex[p], ey = s1_ey[p];
     const double fx = floor(ex), fy = floor(ey);
-    ref_pos[i] = make_int4((int)fx, (int)fy, __float_as_int((float)(ex - fx)), __float_as_int((float)(ey - fy)));
+    // x, y in [-1, 65534]: one word, biased by 1
+    ref_pos[i] = make_int4(((int)fx + 1) | (((int)fy + 1) << 16), __float_as_int((float)(ex - fx)), __float_as_int((float)(ey - fy)), (int)p);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,8 +1,8 @@
 #!/bin/bash
-# usage: scripts/ab_warp.sh "<defs A>" "<defs B>" ...   -- warp_backward kernel time at 3840x1920 for each set of -D knobs
-for defs in "$@"; do
-  TIF_NVCC_DEFS="$defs" python 360opticalflow-tangentimages_b200/_build.py --force > /dev/null
-  TIF_NVCC_DEFS="$defs" python - "$defs" <<'PY'
+# usage (GPU box): scripts/ab_warp.sh [variant ...]   -- warp_backward kernel time at 2048x1024 and 3840x1920 with the regular
+# library and with each prebuilt variant (see scripts/ab_variants.sh)
+run() {
+python - "$1" <<'PY'
 import sys, torch
 sys.path.insert(0, ".")
 import __graft_entry__ as e
@@ -26,7 +26,12 @@ for h in (1024, 1920):
     for _ in range(10): run()
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
-    print("[%s] h=%d  %.3f ms per %d images  frac %.3f" % (sys.argv[1], h, ms, B, B * h * 2 * h * 14 / (ms * 1e-3) / 6543.7e9))
+    print("[%s] h=%d  %.3f ms per %d images  frac %.3f" % (sys.argv[1], h, ms, B, B * h * 2 * h * 14 / (ms * 1e-3) / 6543.7e9), flush=True)
 PY
+}
+unset TIF_B200_LIB
+run base
+for n in "$@"; do
+  export TIF_B200_LIB=$PWD/360opticalflow-tangentimages_b200/build/variants/$n.so
+  run $n
 done
-python 360opticalflow-tangentimages_b200/_build.py --force > /dev/null
