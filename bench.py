@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the run with the collection of the flows on rank 0")
-    ap.add_argument("--gather-mode", default="fused", choices=["fused", "copy", "nccl"],
+    ap.add_argument("--gather-mode", default="copy", choices=["fused", "copy", "nccl"],
                     help="fused: the blend kernel stores into rank 0's peer-mapped buffer; copy: local result + "
                          "cudaMemcpyAsync to the peer buffer on a side stream; nccl: dist.gather after each step")
     ap.add_argument("--serial", action="store_true", help="launch the step's kernels on one stream (no overlap)")
@@ -301,7 +301,7 @@ class Workload:
         return sum(nbytes * per_step for _, nbytes, per_step in self.kernels().values())
 
 
-def time_steps(torch, dist, world, device, fn, steps, warmup, sampler=None):
+def time_steps(torch, dist, world, device, fn, steps, warmup, sampler=None, drain=None):
     """K steps between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
     def barrier():
         if world > 1:
@@ -318,6 +318,8 @@ def time_steps(torch, dist, world, device, fn, steps, warmup, sampler=None):
     ev0.record()
     for _ in range(steps):
         fn()
+    if drain is not None:       # work the steps left on a side stream belongs to the timed region
+        torch.cuda.current_stream().wait_stream(drain)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -530,22 +532,35 @@ def run_with_gather(args, torch, dist, pkg, wl, world, rank, device, ms_plain):
             info["note"] = ("peer-store epilogue: every rank's blend kernel writes its [B,H,W,2] shard straight into rank 0's "
                             "CUDA-IPC-mapped buffer (no staging, no receive side)")
         else:
-            copy_stream, done, free = torch.cuda.Stream(device), torch.cuda.Event(), torch.cuda.Event()
-            state = {"first": True}
+            # Two local result buffers: the push of step i (side stream, copy engine) overlaps all of step i + 1, and
+            # step i + 2 waits until the push of step i has read its buffer.  No rank waits for another: the pushes of
+            # the ranks drift apart until rank 0's NVLink ingress is busy all the time, which is the bound of this
+            # exchange (`limiter`).
+            copy_stream = torch.cuda.Stream(device)
+            outs = [wl.out, torch.empty_like(wl.out)]
+            done, free = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
+            state = {"i": 0}
 
             def step():
                 main = torch.cuda.current_stream()
-                if not state["first"]:
-                    main.wait_event(free)             # the previous push has read wl.out
-                state["first"] = False
+                k = state["i"] & 1
+                if state["i"] >= 2:
+                    main.wait_event(free[k])          # the push of step i - 2 has read this buffer
+                state["i"] += 1
+                wl.out_target = outs[k]
                 wl.step(args.serial)
                 done.record(main)
                 copy_stream.wait_event(done)
                 with torch.cuda.stream(copy_stream):
-                    pkg._lib.check(lib.tif_ipc_copy_async(buf.slice_ptr(), wl.out.data_ptr(), nbytes, copy_stream.cuda_stream), "tif_ipc_copy_async")
-                    free.record(copy_stream)
-            ms, _ = time_steps(torch, dist, world, device, step, steps, warmup)
-            info["note"] = "local result, then cudaMemcpyAsync into rank 0's peer-mapped buffer on a side stream (overlaps the next step's resampling)"
+                    pkg._lib.check(lib.tif_ipc_copy_async(buf.slice_ptr(), outs[k].data_ptr(), nbytes, copy_stream.cuda_stream), "tif_ipc_copy_async")
+                    free[k].record(copy_stream)
+
+            def timed_step():
+                step()
+            ms, _ = time_steps(torch, dist, world, device, timed_step, steps, warmup, drain=copy_stream)
+            wl.out_target = wl.out
+            info["note"] = ("local result (two buffers), then cudaMemcpyAsync into rank 0's peer-mapped buffer on a side stream: the push of "
+                            "step i overlaps step i + 1; the timed region ends when the last push has landed")
         # the collected field on rank 0 must equal what every rank computed locally
         torch.cuda.synchronize()
         dist.barrier()
