@@ -4,11 +4,10 @@
 // tensor cores.  Geometry comes from the TifPlan (tif_plan.cu); one thread owns one output pixel
 // and loops over a chunk of the batch so that plan entries are read once per chunk.
 //
-//   k_erp2ico        erp2ico_image      projection_icosahedron.py:233-245 (+ scipy map_coordinates, a18)
-//   k_stitch         ico2erp_flow       projection_icosahedron.py:333-396, projection.py:15-61
-//   k_warp_backward  warp_backward      flow_warp.py:54-88
-//   k_meshgrid       flow_warp_meshgrid flow_warp.py:15-51
-//   k_wraparound     erp_of_wraparound  flow_postproc.py:17-44
+//   k_erp2ico_staged / k_erp2ico / k_erp2ico_tma   erp2ico_image   projection_icosahedron.py:233-245 (+ scipy map_coordinates, a18)
+//   k_lift + k_gather                              ico2erp_flow    projection_icosahedron.py:333-396 (straightforward; cubemap stage)
+//   k_lift_nw + k_nw_face_scale + k_blend_nw       ico2erp_flow    the same with face_blending_method="normwarp", projection.py:15-61
+// (warp_backward, flow_warp_meshgrid, erp_of_wraparound: tif_warp.cu)
 #include <cuda.h>           // CUtensorMap and its enums only: nothing of libcuda is linked
 #include <stdlib.h>
 
@@ -208,7 +207,7 @@ __device__ __forceinline__ uint32_t erp2ico_staged_pixel(uint32_t a0, uint32_t p
 }
 
 // TIF_S1_STAGES buffers of `stage_bytes` each in dynamic shared memory; the plan picks the stage size from the boxes
-// it found (4 KB at 1280x640, 8 KB at 2K and 4K with the default 480-pixel tangent images)
+// it found between TIF_S1_MIN_STAGE_BYTES and TIF_S1_MAX_STAGE_BYTES (2 KB at 1280x640, 4 KB at 2K and 4K with 480-pixel tangent images)
 __global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
 k_erp2ico_staged(const uint32_t* __restrict__ s1_base, const double2* __restrict__ s1_frac64,
                  const uint2* __restrict__ s1_tiles, int tiles_x, uint32_t stage_bytes, const uint8_t* __restrict__ erp,

@@ -14,11 +14,11 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import ncu_raw_summary  # noqa: E402
 import ncu_source_summary  # noqa: E402
 
-KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_lift<0", "k_lift<straightforward>"), ("k_lift<(bool)0", "k_lift<straightforward>"),
-               ("k_lift<1", "k_lift<normwarp>"), ("k_lift<(bool)1", "k_lift<normwarp>"),
+# substring of the ncu kernel name -> the kernel's name in bench.py's roofline.kernels
+KERNEL_KEYS = [("k_erp2ico", "k_erp2ico"), ("k_lift_nw", "k_lift_nw"), ("k_blend_nw", "k_blend_nw"),
+               ("k_lift<0", "k_lift<straightforward>"), ("k_lift<(int)0", "k_lift<straightforward>"),
                ("k_gather<0", "k_gather<straightforward>"), ("k_gather<(int)0", "k_gather<straightforward>"),
-               ("k_gather<1", "k_gather<sums>"), ("k_gather<(int)1", "k_gather<sums>"),
-               ("k_gather<2", "k_gather<blend>"), ("k_gather<(int)2", "k_gather<blend>")]
+               ("k_warp_rgb_fast", "k_warp_backward")]
 
 
 def capture(fn, *args):
@@ -81,10 +81,21 @@ def main():
         for key, label in KERNEL_KEYS:
             if key in name:
                 traffic.setdefault(label, []).append(tot / batch)
-    traffic = {k: max(v) for k, v in traffic.items()}       # bulk launch (the polar-band launch is the small one)
-    json.dump({"tag": tag, "erp_h": erp_h, "batch_under_ncu": batch, "bytes_per_pair": traffic,
-               "note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch / batch; k_erp2ico is per image"},
-              open(os.path.join(out, "traffic.json"), "w"), indent=1)
+    traffic = {k: max(v) for k, v in traffic.items()}
+    # bench.py looks the figures up per configuration ("h<ERP height>_l<subdivision level>"); other configurations of
+    # an earlier capture are kept
+    path = os.path.join(out, "traffic.json")
+    try:
+        doc = json.load(open(path))
+        if not isinstance(doc.get("bytes_per_pair", {}).get("h%d_l0" % erp_h, {}), dict) or "tag" in doc:
+            doc = {"bytes_per_pair": {k: v for k, v in doc.get("bytes_per_pair", {}).items() if isinstance(v, dict)}}
+    except Exception:
+        doc = {"bytes_per_pair": {}}
+    doc["bytes_per_pair"]["h%d_l0" % erp_h] = traffic
+    doc.setdefault("captures", {})["h%d_l0" % erp_h] = {"tag": tag, "batch_under_ncu": batch}
+    doc["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch / batch under ncu --set full; k_erp2ico and "
+                   "k_warp_backward are per image, the stitch kernels per frame pair")
+    json.dump(doc, open(path, "w"), indent=1)
     print(open(os.path.join(out, "launches_%s.md" % tag)).read())
     print(json.dumps(traffic, indent=1))
 
