@@ -771,25 +771,27 @@ k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __re
     constexpr bool NW = SAMPLE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LiftFace* sh_face = reinterpret_cast<LiftFace*>(smem_raw);
+    // The thread's chain of dependent loads (work-list entry -> first row of its face -> flows) starts before the
+    // shared face table is filled, so that the flows are in flight across the barrier: the kernel is latency bound.
+    // the work list holds only tangent pixels that some ERP pixel reads (half of the stack), in tile order
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < n_ref;
+    const uint32_t ref = live ? (uint32_t)__ldg(ref_list + idx) : 0u;       // face << 25 | row inside the face << 11 | column
+    const int tcol = (int)TIF_E_IX(ref), trow = __ldg(&lift_faces[TIF_E_FACE(ref)].first_row) + (int)TIF_E_IY(ref);
+    const int p = trow * tangent_w + tcol;
+    const int b0 = blockIdx.y * TIF_LIFT_IMGS;
+    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
+    float2 uvs[TIF_LIFT_IMGS];
+#pragma unroll
+    for (int bb = 0; bb < TIF_LIFT_IMGS; ++bb)
+        uvs[bb] = (live && b0 + bb < batch) ? __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p)) : make_float2(0.0f, 0.0f);
     // the per-face constants come ready from the plan (the reciprocals are float64 divisions): 16-byte copies
     static_assert(sizeof(LiftFace) % 16 == 0, "LiftFace is copied in 16-byte pieces");
     for (int i = threadIdx.x; i < n_faces * (int)(sizeof(LiftFace) / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(sh_face)[i] = __ldg(reinterpret_cast<const uint4*>(lift_faces) + i);
     __syncthreads();
-    // the work list holds only tangent pixels that some ERP pixel reads (half of the stack), in tile order
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_ref) return;
-    const uint32_t ref = (uint32_t)__ldg(ref_list + idx);       // face << 25 | row inside the face << 11 | column
+    if (!live) return;
     const LiftFace& F = sh_face[TIF_E_FACE(ref)];
-    const int tcol = (int)TIF_E_IX(ref), trow = F.first_row + (int)TIF_E_IY(ref);
-    const int p = trow * tangent_w + tcol;
-    const int b0 = blockIdx.y * TIF_LIFT_IMGS;
-    const float2* __restrict__ flow_chunk = reinterpret_cast<const float2*>(tflow) + (size_t)b0 * n_tangent;
-    // all flows of the chunk are requested before anything depends on them (the kernel is latency bound)
-    float2 uvs[TIF_LIFT_IMGS];
-#pragma unroll
-    for (int bb = 0; bb < TIF_LIFT_IMGS; ++bb)
-        uvs[bb] = (b0 + bb < batch) ? __ldg(flow_chunk + ((unsigned)bb * (unsigned)n_tangent + (unsigned)p)) : make_float2(0.0f, 0.0f);
 
     // ---- per tangent pixel, once for the chunk of images -------------------------------------------------
     float a0, bz0, cy0;

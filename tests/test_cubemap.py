@@ -147,7 +147,11 @@ def test_gpu_matches_reference_fixture(pkg, golden, name):
     assert ((err > FLOW_TOL) & ~seam).sum() == 0, err.max()
     weighted = pcm.cubemap2erp_flow(flows, None, erp_h, pad, src, tar, True)
     err = np.abs(weighted - g["flow_weighted"]).max(axis=2)
-    assert ((err > FLOW_TOL) & ~weighted_excuse(erp_h, pad, src, tar, flows, dbg)).sum() == 0, err.max()
+    excuse = weighted_excuse(erp_h, pad, src, tar, flows, dbg)
+    # the excuse stays an exception: a few percent of the pixels (on IID-noise images nearly every ERP pixel has a
+    # target sample somewhere near a rounding step of SOME channel of SOME face: 2e-3 x 2 x 3 channels x faces)
+    assert excuse.mean() < 0.04, excuse.mean()
+    assert ((err > FLOW_TOL) & ~excuse).sum() == 0, err.max()
 
 
 @pytest.mark.gpu
