@@ -331,7 +331,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Producer / consumer ring without a block-wide barrier: `full[st]` completes when the TMA box of a stage has landed
 // (transaction bytes), `empty[st]` when every warp has blended from it (one arrival per warp).  Thread 0 is the only
-// producer: after its own pixel of image i it refills the stage image i - 1 used, and waits for that stage's `empty`
+// producer: before its own pixel of image i it refills the stage image i - 1 used, and waits for that stage's `empty`
 // phase only -- the other warps have normally released it already, so the warps drift up to TIF_S1_STAGES - 1 images
 // apart instead of meeting at a __syncthreads per image.
 __global__ void __launch_bounds__(TIF_S1_THREADS, TIF_ERP2ICO_STAGED_MIN_BLOCKS)
@@ -410,14 +410,10 @@ k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_const
         for (int st = 0; st < STAGES; ++st) {
             const int i = i0 + st;
             if (i >= n_img) break;
-            mbar_wait(full0 + 8u * st, parity);     // the box of image i has landed
-            if (blend) *o4 = erp2ico_staged_pixel(tap + (uint32_t)st * stage_bytes, pitch, sh, w00, w01, w10, w11, s1_frac64 + p);
-            else if (valid) *o4 = 0x00ffffffu;      // RGB 255, alpha 0
-            o4 += n_pix;
-            __syncwarp();
-            if (lane0) mbar_arrive(empty0 + 8u * st);           // this warp is done with stage st
             if (tid == 0) {
-                const int j = i + STAGES - 1;                   // next image to request, into the stage image i - 1 used
+                // producer, BEFORE its own pixel of image i: the stage image i - 1 used is refilled with image i + STAGES - 1
+                // as soon as every warp has released it, so the request does not queue behind this warp's arithmetic
+                const int j = i + STAGES - 1;
                 if (j < n_img) {
                     const int sj = (st + STAGES - 1) % STAGES;
                     if (i >= 1) mbar_wait(empty0 + 8u * sj, st == 0 ? (parity ^ 1u) : parity);
@@ -425,6 +421,12 @@ k_erp2ico_tma(const __grid_constant__ CUtensorMap map_narrow, const __grid_const
                     tma_load_3d(stage0 + (uint32_t)sj * stage_bytes, map, full0 + 8u * sj, (int)box_x, (int)box_y, b_begin + j);
                 }
             }
+            mbar_wait(full0 + 8u * st, parity);     // the box of image i has landed
+            if (blend) *o4 = erp2ico_staged_pixel(tap + (uint32_t)st * stage_bytes, pitch, sh, w00, w01, w10, w11, s1_frac64 + p);
+            else if (valid) *o4 = 0x00ffffffu;      // RGB 255, alpha 0
+            o4 += n_pix;
+            __syncwarp();
+            if (lane0) mbar_arrive(empty0 + 8u * st);           // this warp is done with stage st
         }
     }
 }
@@ -483,11 +485,13 @@ extern "C" int tif_erp2ico_u8(const TifPlan* plan, const uint8_t* erp, int batch
         while (srows < batch && (int64_t)tiles * srows < 148 * 16) srows *= 2;
         const int sper = (batch + srows - 1) / srows;
         dim3 sgrid(tiles, (unsigned)((batch + sper - 1) / sper));
-        // The TMA form is opt-in (TIF_S1_TMA=1 in the environment, read per call): measured on B200 it is 7 % slower than
-        // the cp.async ring (0.45 against 0.42 ms per 32 images at 2K, with or without a block barrier per image) -- a
-        // patch's box is ~20 rows of ~80 bytes, and the TMA unit, like the 1-D bulk copies before it, is bound by rows
-        // per clock, not by bytes; a tensor map also fixes the box shape, so every patch fetches the largest box of
-        // its class instead of its own footprint.
+        // The TMA form is opt-in (TIF_S1_TMA=1 in the environment, read per call): measured on B200 it is 5 % slower than
+        // the cp.async ring (0.44 against 0.42 ms per 32 images at 2K) -- with a block barrier per image (0.44), with the
+        // producer / consumer mbarrier ring (0.45; requests issued before the producer's own pixel: 0.44), with 3 / 6 / 8
+        // stages (0.46 / 0.44 / 0.50) and with a grid of 4 x 5 box shapes instead of two, which removes the over-fetch
+        // of a fixed box (0.45).  Under ncu it executes as many instructions as the cp.async kernel (the copy code
+        // it saves comes back as try_wait polls): the boxes arrive late.  A box is ~20 rows of ~100 bytes, and the TMA
+        // unit, like the 1-D bulk copies before it, is bound by rows per clock, not by bytes.
         const char* tma_env = getenv("TIF_S1_TMA");
         TifEncodeTiledFn enc = (tma_env && tma_env[0] == '1') ? tma_encoder() : nullptr;
         CUtensorMap map_narrow, map_wide;
