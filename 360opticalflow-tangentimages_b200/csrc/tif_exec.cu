@@ -1226,7 +1226,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 #define TIF_NW_WORD_TAPS 1
 #endif
 #ifndef TIF_NW_FOLD_MULT
-#define TIF_NW_FOLD_MULT 0
+#define TIF_NW_FOLD_MULT 1
 #endif
 #ifndef TIF_NW_BLEND_THREADS
 #define TIF_NW_BLEND_THREADS 64
@@ -1333,7 +1333,6 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
     // face mean is small, wherever the faces disagree by hundreds of pixels (garbage estimator flows next to a pole).
     float4* sh_lift = reinterpret_cast<float4*>(smem_raw);                                   // [4][TIF_NW_BLOCK] remainder rgb, x code
     uint32_t* sh_base = reinterpret_cast<uint32_t*>(sh_lift + TIF_NW_IMGS * TIF_NW_BLOCK);   // [4][TIF_NW_BLOCK] R | G << 8 | B << 16
-    unsigned long long* sh_sum = reinterpret_cast<unsigned long long*>(sh_base + TIF_NW_IMGS * TIF_NW_BLOCK);   // [4][F]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.y * TIF_NW_IMGS;
     const int n_img = min(TIF_NW_IMGS, batch - b0);
@@ -1369,7 +1368,6 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
             uvs[bb] = __ldg(flow_chunk + ((unsigned)min(bb, n_img - 1) * (unsigned)n_tangent + (unsigned)p));
     }
-    for (int i = tid; i < TIF_NW_IMGS * n_faces; i += TIF_NW_BLOCK) sh_sum[i] = 0ull;       // ordered by the barrier after phase 1
 
     // ---- phase 1: lift one work-list entry per thread --------------------------------------------------------
     if (live) {
@@ -1527,7 +1525,11 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
     };
     // Face sums: every step adds the raw bits of fma(d * mult, 1024, 2^23) = 0x4B000000 + round(d * mult * 1024) of the
     // 4 images to per-thread 32-bit accumulators (lanes without a sample have mult = 0 and add the bare offset); the
-    // offsets, `pending` per lane, leave again modulo 2^32 when the warp's total is taken.
+    // offsets, `pending` per lane, leave again modulo 2^32 when the warp's total is taken.  The total goes straight to
+    // the global 64-bit sums as a fire-and-forget reduction (RED.ADD.64: one per warp, image and tile; integer, hence
+    // order-independent): a shared-memory stage in between cost a 64-bit compare-and-swap loop per warp, a barrier and
+    // a pass over the table at the end of every block -- 12 % of the kernel's stall samples.
+    unsigned long long* __restrict__ sums_chunk = nw_sums + (size_t)b0 * n_faces;       // [b0 + bb][f]
     int cur_f = -1;
     unsigned pending = 0u;
     unsigned acc[TIF_NW_IMGS];
@@ -1538,7 +1540,7 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
 #pragma unroll
             for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
                 const unsigned total = __reduce_add_sync(0xffffffffu, acc[bb] - pending * 0x4B000000u);
-                if (lane == 0 && total) atomicAdd(&sh_sum[bb * n_faces + cur_f], (unsigned long long)total);
+                if (lane == 0 && total && bb < n_img) atomicAdd(sums_chunk + bb * n_faces + cur_f, (unsigned long long)total);
                 acc[bb] = 0u;
             }
         }
@@ -1605,16 +1607,13 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
         } else if (has) {
 #pragma unroll
             for (int bb = 0; bb < TIF_NW_IMGS; ++bb)
-                atomicAdd(&sh_sum[bb * n_faces + f], (unsigned long long)(__float_as_uint(NW_FIXED(d[bb])) - 0x4B000000u));
+                if (bb < n_img) atomicAdd(sums_chunk + bb * n_faces + f, (unsigned long long)(__float_as_uint(NW_FIXED(d[bb])) - 0x4B000000u));
         }
         sm = sm_next;
         sm_next = sm_next2;
         sw_cur = sw_next;
     }
     flush();
-    __syncthreads();
-    for (int i = tid; i < n_img * n_faces; i += TIF_NW_BLOCK)        // [b0 + bb][f] is one contiguous run of nw_sums
-        if (sh_sum[i]) atomicAdd(&nw_sums[(size_t)b0 * n_faces + i], sh_sum[i]);
 }
 
 // grid = (ceil(W / TIF_NW_BLEND_THREADS), H, chunks): a block owns a run of one ERP row, so that row, column and pixel
@@ -1860,7 +1859,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
         if ((pass_mask & (1 | 8)) && !skip_lift) {
             TIF_CUDA_CHECK(cudaMemsetAsync(nw_sums, 0, nw_sums_bytes(plan, batch), stream));
             const dim3 grid((unsigned)((n_ref + TIF_NW_BLOCK - 1) / TIF_NW_BLOCK), chunks);
-            const size_t smem = (sizeof(float4) + sizeof(uint32_t)) * TIF_NW_IMGS * TIF_NW_BLOCK + sizeof(unsigned long long) * TIF_NW_IMGS * n_faces;
+            const size_t smem = (sizeof(float4) + sizeof(uint32_t)) * TIF_NW_IMGS * TIF_NW_BLOCK;
 #define LIFT_NW_ARGS                                                                                                    \
     plan->d_lift_faces, n_faces, plan->d_ref_list, n_ref, plan->d_ref_pos, plan->d_s1_ex, plan->d_s1_ey, plan->d_smp,   \
         plan->d_blk_smp, tangent_flow, erp_src, erp_tar, disp_rec, dplane, nw_sums, h, w, plan->tangent_w, n_tangent,  \
