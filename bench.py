@@ -476,7 +476,8 @@ def run_ours(args):
             configs[name] = {"workload": workload_name(height, level, blend, warp), "pairs_per_step": batch, "steps": 6,
                              "value": batch / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "step_frac": rf["step_frac"],
                              "plan_build_ms": w2.plan_build_ms, "plan_device_bytes": w2.plan.device_bytes,
-                             "kernels": {k: {"ms": v["ms"], "frac": v["frac"], "gbs": v["gbs"], "algorithmic_bytes": v["algorithmic_bytes"]}
+                             "kernels": {k: {"ms": v["ms"], "frac": v["frac"], "gbs": v["gbs"], "algorithmic_bytes": v["algorithmic_bytes"],
+                                             "traffic": v["traffic"], "dram_over_algorithmic": v["dram_over_algorithmic"]}
                                          for k, v in k2.items()}}
             del w2
             if level == 1:
