@@ -136,6 +136,28 @@ def test_config2_against_oracle(pkg, erp_h):
     assert np.array_equal(fwarp.warp_backward(tar, want32), tif_oracle.warp_backward(tar, want32))
 
 
+@pytest.mark.parametrize("pad,wt,wrap", [(0.1, 480, True), (0.0, 320, False)])
+def test_2k_other_paddings_and_widths(pkg, pad, wt, wrap):
+    """2048x1024 with other face tables than the bench's (padding 0.1 / none, another tangent width, both seam
+    conventions): other box sizes for the staged resampler, other membership counts (K) and sample lists for the stitch."""
+    erp_h = 1024
+    src, tar, flows = synth.synth(erp_h, 2, wt)
+    pico = pkg.projection_icosahedron
+    for full in (True, False):
+        assert all(np.array_equal(a, b) for a, b in zip(pico.erp2ico_image(src, wt, pad, full), tif_oracle.erp2ico_image(src, wt, pad, full)))
+    for blend in ("straightforward", "normwarp"):
+        want, dbg = tif_oracle.ico2erp_flow(flows, erp_h, pad, src, tar, wrap, blend, return_debug=True)
+        got = pico.ico2erp_flow(flows, erp_h, pad, src, tar, wrap, blend)
+        excuse = dbg["seam_dist"] < 1e-5
+        if not wrap:
+            excuse |= dbg["fu_spread"] > 0.25 * want.shape[1]
+        if blend == "normwarp":
+            excuse |= dbg["edge_dist"] < 1e-3
+        err = np.abs(got - want).max(axis=2)
+        assert ((err > FLOW_TOL) & ~excuse).sum() == 0, (pad, wt, blend, err.max())
+        assert excuse.mean() < 0.02
+
+
 def test_warp_fast_kernel(pkg):
     """The uint8 RGB warp kernel (integer coordinates + 23-bit fractions, fixed-point blend) against the oracle's
     float64 scipy restatement: negative / tiny / huge / exactly-integer flows, the period n-1 wrap on both axes,
