@@ -729,6 +729,38 @@ __device__ __noinline__ void lift_precise(const LiftFace* F, int tcol, int trow,
     }
 }
 
+// The cubemap stage's target sample (SAMPLE 2) is rounded to uint8 like scipy's output (projection.py:103-104), and its
+// weight 0.95 / ||diff||_2 turns one flipped rounding into a flow error far above tolerance.  A float32 sample that
+// lands within TIF_U8_ROUND_GUARD grey levels of a rounding step (the float32 lift moves the sampling position by
+// ~1e-6 px, times an image gradient of up to 255 per pixel, plus the float32 blend) is therefore re-evaluated here:
+// float64 end point, scipy's float64 bilinear in its accumulation order, round half up.  0.6 % of the samples.
+#define TIF_U8_ROUND_GUARD 1.0e-3f
+__device__ __noinline__ void sample_u8_exact(const LiftFace* F, int tcol, int trow, float u, float v, int erp_w, int erp_h,
+                                             const double* __restrict__ s1_ex, const double* __restrict__ s1_ey, int p,
+                                             const uint8_t* __restrict__ img, float* t) {
+    float disp[2];
+    double end[2];
+    lift_precise(F, tcol, trow, u, v, erp_w, erp_h, s1_ex, s1_ey, p, disp, end);
+    double x = end[0];
+    const double y = end[1], xf = floor(x);
+    if (xf >= (double)erp_w) x -= (double)erp_w;          // x is periodic: the same single fold as the float32 route
+    else if (xf < 0.0) x += (double)erp_w;
+    if (!(y >= 0.0 && y <= (double)(erp_h - 1) && x >= 0.0 && x <= (double)(erp_w - 1))) {
+        t[0] = t[1] = t[2] = 255.0f;            // mode='constant', cval=255
+        return;
+    }
+    const double y0f = floor(y), x0f = floor(x);
+    const int y0 = (int)y0f, x0 = (int)x0f;
+    const int y1 = y0 + 1 >= erp_h ? erp_h - 2 : y0 + 1, x1 = x0 + 1 >= erp_w ? erp_w - 2 : x0 + 1;      // weight 0 there
+    const double fy = __dsub_rn(y, y0f), fx = __dsub_rn(x, x0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const double p00 = (double)__ldg(img + ((size_t)y0 * erp_w + x0) * 3 + ch), p01 = (double)__ldg(img + ((size_t)y0 * erp_w + x1) * 3 + ch);
+        const double p10 = (double)__ldg(img + ((size_t)y1 * erp_w + x0) * 3 + ch), p11 = (double)__ldg(img + ((size_t)y1 * erp_w + x1) * 3 + ch);
+        t[ch] = (float)scipy_round_u8(bilinear_f64_exact(p00, p01, p10, p11, fx, fy));
+    }
+}
+
 // Displacement of the flow end point of ONE tangent pixel, projection_icosahedron.py:336-347:
 //   pixel2gnomonic (gnomonic_projection.py:186-194) of (ix + u, iy + v), reverse_gnomonic_projection (:76-85),
 //   sph_coord_modulo + sph2erp (spherical_coordinates.py:237-238, 59-60, 122-124),
@@ -965,9 +997,20 @@ k_lift(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* __re
                 t2 = byte_f(lo0, 2) * w00 + byte_f(hi0, 1) * w01 + byte_f(lo1, 2) * w10 + byte_f(hi1, 1) * w11;
             }
             if (SAMPLE == 2) {          // scipy uint8 output: trunc(t + 0.5)
-                t0 = floorf(t0 + 0.5f);
-                t1 = floorf(t1 + 0.5f);
-                t2 = floorf(t2 + 0.5f);
+                const float r0 = t0 + 0.5f, r1 = t1 + 0.5f, r2 = t2 + 0.5f;
+                const float near = fminf(fminf(fabsf(r0 - rintf(r0)), fabsf(r1 - rintf(r1))), fabsf(r2 - rintf(r2)));
+                if (off[j] != kNoSample && near < TIF_U8_ROUND_GUARD) {
+                    float te[3];
+                    sample_u8_exact(&F, tcol, trow, uvs[bb].x, uvs[bb].y, erp_w, erp_h, s1_ex, s1_ey, p,
+                                    erp_tar + (size_t)(b0 + bb) * image_bytes, te);
+                    t0 = te[0];
+                    t1 = te[1];
+                    t2 = te[2];
+                } else {
+                    t0 = floorf(r0);
+                    t1 = floorf(r1);
+                    t2 = floorf(r2);
+                }
             }
             // 21-bit fixed point (x 8192, round to nearest) through the 2^23 mantissa trick: no XU conversions
             const uint32_t q0 = __float_as_uint(fmaf(t0, TIF_RGB_FIX, 8388608.0f)) - 0x4B000000u;

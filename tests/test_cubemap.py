@@ -106,10 +106,15 @@ def test_host_tables_match_oracle(pkg):
 # GPU
 # ---------------------------------------------------------------------------------------------------------
 
+# a target sample this close to a uint8 rounding step may round the other way (the kernel re-evaluates samples within
+# 1e-3 of a step in float64; what is left is the difference of two float64 routes to the same end point)
+STEP_GUARD = 1e-6
+
+
 def weighted_excuse(erp_h, pad, src, tar, flows, dbg):
     """Pixels where the reference's own map is discontinuous within tolerance of a contributing end point: the
     +-pi seam (no seam fix in this stage), the hard 255 edge of mode='constant', and -- specific to this stage,
-    whose images stay uint8 -- a target sample within 2e-3 grey levels of a uint8 rounding step."""
+    whose images stay uint8 -- a target sample within STEP_GUARD grey levels of a uint8 rounding step."""
     erp_w = 2 * erp_h
     exc = np.zeros((erp_h, erp_w), dtype=bool)
     img = np.asarray(tar).astype(np.float64)
@@ -120,7 +125,7 @@ def weighted_excuse(erp_h, pad, src, tar, flows, dbg):
         step = np.zeros(tx.shape, dtype=bool)
         for ch in range(3):
             t = tif_oracle.map_coordinates_order1(img[:, :, ch], ty, tx, "constant", 255)
-            step |= np.abs((t + 0.5) - np.round(t + 0.5)) < 2e-3
+            step |= np.abs((t + 0.5) - np.round(t + 0.5)) < STEP_GUARD
         bad = near | edge | step
         exc[r[bad], c[bad]] = True
     return exc
@@ -148,9 +153,8 @@ def test_gpu_matches_reference_fixture(pkg, golden, name):
     weighted = pcm.cubemap2erp_flow(flows, None, erp_h, pad, src, tar, True)
     err = np.abs(weighted - g["flow_weighted"]).max(axis=2)
     excuse = weighted_excuse(erp_h, pad, src, tar, flows, dbg)
-    # the excuse stays an exception: a few percent of the pixels (on IID-noise images nearly every ERP pixel has a
-    # target sample somewhere near a rounding step of SOME channel of SOME face: 2e-3 x 2 x 3 channels x faces)
-    assert excuse.mean() < 0.04, excuse.mean()
+    # the excuse stays an exception (seam and edge pixels)
+    assert excuse.mean() < 0.01, excuse.mean()
     assert ((err > FLOW_TOL) & ~excuse).sum() == 0, err.max()
 
 
@@ -186,4 +190,4 @@ def test_gpu_cubemap_2k(pkg, golden):
     assert np.array_equal(got, want)
     weighted = pcm.cubemap2erp_flow(flows, None, erp_h, pad, src, tar, True)
     err = np.abs(weighted.reshape(-1, 2)[::st] - g["flow_weighted_samples"]).max(axis=1)
-    assert np.median(err) < 2e-5 and (err > FLOW_TOL).mean() < 5e-3
+    assert np.median(err) < 2e-5 and (err > FLOW_TOL).mean() < 1e-4          # strided samples: seam / edge pixels only
