@@ -1241,14 +1241,14 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 // The weight of a sample is exp(-mean_ch|tar(end point) - src(ERP pixel)| / G_f) with G_f the mean of that warp error
 // over ALL samples of the face, so every sample's error is needed twice: for G_f and for the blend.
 //
-//   k_lift_nw   a block lifts TIF_NW_BLOCK work-list entries (tangent pixels) x 4 images: displacement to HBM
-//               (32 bytes per tangent pixel and chunk), bilinear sample of the target image at the end point to
+//   k_lift_nw   a block lifts TIF_NW_BLOCK work-list entries (tangent pixels) x 4 images: absolute end point to HBM as
+//               32-bit fixed point (32 bytes per tangent pixel and chunk), bilinear sample of the target image at the end point to
 //               SHARED memory.  It then walks the plan's sample list of exactly those tangent pixels (d_smp,
 //               tangent-pixel major, one sample per thread and step, coalesced): |target sample - source pixel| per
 //               channel goes to the dense plane [k][pixel] of the chunk (one 16-byte store for the 4 images, read
 //               back coalesced by the blend) and, times the multiplicity, as fixed point into the face sums.
 //               The target samples never leave the SM, and no pass gathers them per ERP pixel.
-//   k_blend_nw  one thread per ERP pixel x 4 images, faces in index order: flow = displacement + snap offset,
+//   k_blend_nw  one thread per ERP pixel x 4 images, faces in index order: flow = end point - ERP pixel (integers),
 //               weight = 2^(error x scale_f) from the stored errors, weighted mean, final wrap.
 // Measured alternatives (B200, 32 pairs of 2048x1024): the same two phases as separate kernels with the target samples
 // in HBM: 0.86 + 0.88 ms against 1.54 ms fused; source pixels staged by 4-byte cp.async: 1.76 ms; the sample steps of
@@ -1258,7 +1258,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 // its time moves by +-2 % with the register allocation (taps of 1 or 2 images grouped, multiplicity folded into the
 // fixed-point scale or not); a block-uniform face flag (no per-step shuffle + vote) costs more registers than it saves.  k_blend_nw is bound by the latency of its displacement gathers and wants resident warps: 64 x 20 (51
 // registers) 0.47 ms, 128 x 10: 0.48, 128 x 8: 0.53, 128 x 12 (spills): 0.53, 256 x 4: 0.56; gathers requested one sample
-// ahead (TIF_BLEND_PIPE): 0.54.
+// ahead: 0.54.
 #ifndef TIF_NW_LIFT_MIN_BLOCKS
 #define TIF_NW_LIFT_MIN_BLOCKS 4
 #endif
@@ -1278,9 +1278,6 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 #define TIF_NW_BLEND_MIN_BLOCKS 20
 #endif
 #define TIF_NW_IMGS 4
-#ifndef TIF_BLEND_PIPE
-#define TIF_BLEND_PIPE 0
-#endif
 static_assert(TIF_NW_FIXED_SCALE == 1024.0f, "k_lift_nw folds the scale into the multiplicity as a shift by 10");
 static_assert(TIF_NW_IMGS % TIF_NW_LIFT_GROUP == 0, "the images of a thread are split into whole groups");
 static_assert(TIF_NW_IMGS == TIF_MAX_CHUNK_IMAGES, "tif_plan_create bounds the ERP size by the chunk's byte offsets");
@@ -1368,7 +1365,7 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
           const uint2* __restrict__ smp, const uint32_t* __restrict__ blk_smp, const float* __restrict__ tflow,
           const uint8_t* __restrict__ erp_src, const uint8_t* __restrict__ erp_tar, float2* __restrict__ disp_rec,
           float4* __restrict__ dplane, unsigned long long* __restrict__ nw_sums, int erp_h, int erp_w, int tangent_w,
-          int n_tangent, int max_k, int batch, int wrap_around, float u_scale, float v_scale, PolarBand polar) {
+          int n_tangent, int max_k, int batch, int wrap_around, float u_scale, float v_scale, PolarBand polar, int fix_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // target sample of every (image, tangent pixel) of the block: value = tap (y0, x0) [exact bytes, sh_base] + a small
     // float remainder [sh_lift.xyz].  Kept apart because |sample - source pixel| is often a few grey levels while the
@@ -1458,13 +1455,20 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
                     fx[j] = (float)(end[0] - fax);
                     fy[j] = (float)(end[1] - fay);
                 }
-                disp_out[bb] = make_float2(dx, dy);
                 // target sample at the absolute end point, scipy mode='constant', cval=255 (projection.py:52): x is
                 // periodic (the seam conventions only move the end point by whole image widths); own position in
                 // [-0.5, W - 0.5) plus at most half a turn: one fold brings x into [0, W).  The gap (W-1, W) and
                 // anything outside [0, H-1] vertically reads 255 outright.
                 if (xi >= erp_w) xi -= erp_w;
                 else if (xi < 0) xi += erp_w;
+                // the record of the blend: the end point itself, integer part and fraction (both exact here) as one
+                // fixed-point number per axis; the flow of a sample is then end point - ERP pixel in integers
+                {
+                    const float fix_one = (float)(1 << fix_bits);
+                    const int rx = xi * (1 << fix_bits) + (__float_as_int(fmaf(fx[j], fix_one, 12582912.0f)) - 0x4B400000);
+                    const int ry = yi * (1 << fix_bits) + (__float_as_int(fmaf(fy[j], fix_one, 12582912.0f)) - 0x4B400000);
+                    reinterpret_cast<int2*>(disp_out)[bb] = make_int2(rx, ry);
+                }
                 xcode[j] = 2 * xi + (fx[j] != 0.0f ? 1 : 0);
                 const bool x_ok = (xi < erp_w - 1) | ((xi == erp_w - 1) & (fx[j] == 0.0f));
                 const bool y_ok = ((unsigned)yi < (unsigned)(erp_h - 1)) | ((yi == erp_h - 1) & (fy[j] == 0.0f));
@@ -1664,10 +1668,9 @@ k_lift_nw(const LiftFace* __restrict__ lift_faces, int n_faces, const int32_t* _
 // NVLink wants).  Per pixel the kernel does little more than its sample loop, so the per-thread set-up counts.
 __global__ void __launch_bounds__(TIF_NW_BLEND_THREADS, TIF_NW_BLEND_MIN_BLOCKS)
 k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restrict__ s2_count,
-           const uint32_t* __restrict__ s2_entries, const float2* __restrict__ s2_snap,
-           const float2* __restrict__ disp_rec, const float4* __restrict__ dplane, const float* __restrict__ nw_scale,
+           const uint32_t* __restrict__ s2_entries, const int2* __restrict__ end_rec, const float4* __restrict__ dplane, const float* __restrict__ nw_scale,
            float* __restrict__ out, int erp_h, int erp_w, int tangent_w, int n_tangent, int max_k, int batch,
-           int wrap_around, float inv_w, int split /* erp_of_wraparound: first column of the right half */) {
+           int wrap_around, float inv_w, int split /* erp_of_wraparound: first column of the right half */, int fix_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sh_scale = reinterpret_cast<float4*>(smem_raw);                   // [F] -log2(e) / (3 mean_f) of the 4 images
     int* sh_offset = reinterpret_cast<int*>(sh_scale + n_faces);              // [F] first pixel of each face
@@ -1682,82 +1685,49 @@ k_blend_nw(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __rest
     const int c = blockIdx.x * TIF_NW_BLEND_THREADS + threadIdx.x;
     const unsigned n_pix = (unsigned)erp_h * (unsigned)erp_w;
     const unsigned pix = blockIdx.y * (unsigned)erp_w + (unsigned)c;
-    // the first entry, snap offset and error are requested before the table barrier
+    // the first entry and error are requested before the table barrier
     const int cnt = c < erp_w ? (int)__ldg(s2_count + pix) : 0;
     const float4* __restrict__ dplane_chunk = dplane + (size_t)blockIdx.z * max_k * (size_t)n_pix + pix;
     uint32_t e_next = 0u;
-    float2 sn_next = make_float2(0.0f, 0.0f);
     float4 d_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (cnt > 0) {
         e_next = __ldg(s2_entries + pix);
-        sn_next = __ldg(s2_snap + pix);
         d_next = __ldg(dplane_chunk);
     }
     __syncthreads();
     if (c >= erp_w) return;
     const float wf = (float)erp_w, half_w = 0.5f * wf;
-    const float4* __restrict__ disp_chunk = reinterpret_cast<const float4*>(disp_rec + (size_t)blockIdx.z * n_tangent * TIF_NW_IMGS);
+    const int c_fix = c << fix_bits, r_fix = (int)blockIdx.y << fix_bits, w_fix = erp_w << fix_bits, half_fix = w_fix >> 1;
+    const float fix_inv = 1.0f / (float)(1 << fix_bits);
+    const float4* __restrict__ disp_chunk = reinterpret_cast<const float4*>(end_rec + (size_t)blockIdx.z * n_tangent * TIF_NW_IMGS);
     float acc_u[TIF_NW_IMGS], acc_v[TIF_NW_IMGS], acc_w[TIF_NW_IMGS];
 #pragma unroll
     for (int bb = 0; bb < TIF_NW_IMGS; ++bb) acc_u[bb] = acc_v[bb] = acc_w[bb] = 0.0f;
     const uint32_t* __restrict__ e_ptr = s2_entries + pix;
-    const float2* __restrict__ sn_ptr = s2_snap + pix;
     auto tangent_pixel = [&](uint32_t e) {
         return (unsigned)(sh_offset[TIF_E_FACE(e)] + (int)TIF_E_IY(e) * tangent_w + (int)TIF_E_IX(e));
     };
-#if TIF_BLEND_PIPE
-    // displacement gathers one sample ahead (entries two ahead): the gather of sample k + 1 is in flight while sample k
-    // is blended
-    uint32_t e_next2 = cnt > 1 ? __ldg(e_ptr + n_pix) : 0u;
-    float4 q01_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q23_next = q01_next;
-    if (cnt > 0) {
-        const unsigned t0 = tangent_pixel(e_next);
-        q01_next = __ldg(disp_chunk + 2u * t0);
-        q23_next = __ldg(disp_chunk + 2u * t0 + 1u);
-    }
-    e_ptr += n_pix;
-#endif
     for (int k = 0; k < cnt; ++k) {
         const uint32_t e = e_next;
-        const float2 sn = sn_next;
         const float4 dd = d_next;
-#if TIF_BLEND_PIPE
-        const float4 q01 = q01_next, q23 = q23_next;
-        if (k + 1 < cnt) {
-            e_next = e_next2;
-            const unsigned t1 = tangent_pixel(e_next);
-            q01_next = __ldg(disp_chunk + 2u * t1);
-            q23_next = __ldg(disp_chunk + 2u * t1 + 1u);
-            sn_ptr += n_pix;
-            dplane_chunk += n_pix;
-            sn_next = __ldg(sn_ptr);
-            d_next = __ldg(dplane_chunk);
-            if (k + 2 < cnt) {
-                e_ptr += n_pix;
-                e_next2 = __ldg(e_ptr);
-            }
-        }
-#else
         if (k + 1 < cnt) {                           // next entry in flight while this one is blended
             e_ptr += n_pix;
-            sn_ptr += n_pix;
             dplane_chunk += n_pix;
             e_next = __ldg(e_ptr);
-            sn_next = __ldg(sn_ptr);
             d_next = __ldg(dplane_chunk);
         }
         const unsigned tpix = tangent_pixel(e);
         const float4 q01 = __ldg(disp_chunk + 2u * tpix), q23 = __ldg(disp_chunk + 2u * tpix + 1u);
-#endif
         const float4 sc = sh_scale[TIF_E_FACE(e)];
         const float du[TIF_NW_IMGS] = {q01.x, q01.z, q23.x, q23.z}, dv[TIF_NW_IMGS] = {q01.y, q01.w, q23.y, q23.w};
         const float de[TIF_NW_IMGS] = {dd.x, dd.y, dd.z, dd.w}, ds[TIF_NW_IMGS] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
         for (int bb = 0; bb < TIF_NW_IMGS; ++bb) {
-            float fu = du[bb] + sn.x;        // end point minus this ERP pixel, the short way round
-            const float fv = dv[bb] + sn.y;
-            if (fu > half_w) fu -= wf;
-            else if (fu < -half_w) fu += wf;
+            int fui = __float_as_int(du[bb]) - c_fix;          // end point minus this ERP pixel, the short way round
+            if (fui > half_fix) fui -= w_fix;
+            else if (fui < -half_fix) fui += w_fix;
+            float fu = (float)fui * fix_inv;
+            const float fv = (float)(__float_as_int(dv[bb]) - r_fix) * fix_inv;
             // wrap_around=False: the reference leaves theta_t wrapped into [-pi, pi): c + fu lies in [-0.5, W - 0.5)
             if (!wrap_around) fu -= wf * floorf(((float)c + fu + 0.5f) * inv_w);
             const float w = exp2_approx(de[bb] * ds[bb]);         // projection.py:57-58: exp(-(mean_ch |diff|) / mean_all)
@@ -1897,6 +1867,9 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             return TIF_ERR_INVALID_ARG;
         }
         const unsigned chunks = (unsigned)((batch + TIF_NW_IMGS - 1) / TIF_NW_IMGS);
+        // fraction bits of the fixed-point end points in the records: 18 (4e-6 px) while (W + 2) << bits fits 31 bits
+        int nw_fix_bits = 18;
+        while (((long long)(w + 2) << nw_fix_bits) >= (1ll << 31)) --nw_fix_bits;
         float2* disp_rec = (float2*)records;
         float4* dplane = (float4*)((unsigned char*)records + nw_disp_bytes(plan, batch));
         if ((pass_mask & (1 | 8)) && !skip_lift) {
@@ -1906,7 +1879,7 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
 #define LIFT_NW_ARGS                                                                                                    \
     plan->d_lift_faces, n_faces, plan->d_ref_list, n_ref, plan->d_ref_pos, plan->d_s1_ex, plan->d_s1_ey, plan->d_smp,   \
         plan->d_blk_smp, tangent_flow, erp_src, erp_tar, disp_rec, dplane, nw_sums, h, w, plan->tangent_w, n_tangent,  \
-        plan->max_faces_per_pixel, batch, wrap_around, lift_u_scale, lift_v_scale, polar
+        plan->max_faces_per_pixel, batch, wrap_around, lift_u_scale, lift_v_scale, polar, nw_fix_bits
             // every image of the batch starts on a word boundary when the buffer does and H * W * 3 is a multiple of 4
             if (reinterpret_cast<uintptr_t>(erp_src) % 4 == 0 && reinterpret_cast<uintptr_t>(erp_tar) % 4 == 0 && ((size_t)h * w * 3) % 4 == 0)
                 k_lift_nw<true><<<grid, TIF_NW_BLOCK, smem, stream>>>(LIFT_NW_ARGS);
@@ -1922,10 +1895,10 @@ extern "C" int tif_ico2erp_flow_f32_ex(const TifPlan* plan, const float* tangent
             const dim3 grid((unsigned)((w + TIF_NW_BLEND_THREADS - 1) / TIF_NW_BLEND_THREADS), (unsigned)h, chunks);
             const size_t smem = (sizeof(float4) + sizeof(int)) * n_faces;
             k_blend_nw<<<grid, TIF_NW_BLEND_THREADS, smem, stream>>>(plan->d_faces, n_faces, plan->d_s2_count, plan->d_s2_entries,
-                                                                    plan->d_s2_snap, disp_rec, dplane, nw_scale, erp_flow, h, w,
+                                                                    reinterpret_cast<const int2*>(disp_rec), dplane, nw_scale, erp_flow, h, w,
                                                                     plan->tangent_w, n_tangent, plan->max_faces_per_pixel, batch,
                                                                     wrap_around, 1.0f / (float)w,
-                                                                    (int)((double)w - 1.0 - 0.5 * (double)w));
+                                                                    (int)((double)w - 1.0 - 0.5 * (double)w), nw_fix_bits);
         }
     }
 #undef GATHER_ARGS
