@@ -1256,9 +1256,10 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 // launch shapes measured on B200 (32 pairs of 2048x1024): k_lift_nw 256 x 4 (64 registers) 1.34-1.37 ms; 256 x 3: 1.48-1.52,
 // 128 x 7: 1.44, 128 x 6 / 128 x 8: 1.48 / 1.45-1.49, 512 x 2: 1.50.  At 64 registers the kernel spills ~100 bytes and
 // its time moves by +-2 % with the register allocation (taps of 1 or 2 images grouped, multiplicity folded into the
-// fixed-point scale or not); a block-uniform face flag (no per-step shuffle + vote) costs more registers than it saves.  k_blend_nw is bound by the latency of its displacement gathers and wants resident warps: 64 x 20 (51
-// registers) 0.47 ms, 128 x 10: 0.48, 128 x 8: 0.53, 128 x 12 (spills): 0.53, 256 x 4: 0.56; gathers requested one sample
-// ahead: 0.54.
+// fixed-point scale or not); a block-uniform face flag (no per-step shuffle + vote) costs more registers than it saves.  k_blend_nw is bound by the latency of its record gathers and wants resident warps: with the
+// snap offsets 64 x 20 (48 registers) 0.47 ms, 128 x 10: 0.48, 128 x 8: 0.53, 128 x 12 (spills): 0.53, 256 x 4: 0.56, gathers
+// requested one sample ahead: 0.54; without them (fixed-point end points) 64 x 24 (40 registers) 0.433, 64 x 20: 0.445,
+// 128 x 12: 0.438, 64 x 28 and beyond (spills): 0.52.
 #ifndef TIF_NW_LIFT_MIN_BLOCKS
 #define TIF_NW_LIFT_MIN_BLOCKS 4
 #endif
@@ -1275,7 +1276,7 @@ k_gather(const TifFace* __restrict__ faces, int n_faces, const uint8_t* __restri
 #define TIF_NW_BLEND_THREADS 64
 #endif
 #ifndef TIF_NW_BLEND_MIN_BLOCKS
-#define TIF_NW_BLEND_MIN_BLOCKS 20
+#define TIF_NW_BLEND_MIN_BLOCKS 24
 #endif
 #define TIF_NW_IMGS 4
 static_assert(TIF_NW_FIXED_SCALE == 1024.0f, "k_lift_nw folds the scale into the multiplicity as a shift by 10");
